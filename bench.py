@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py — PMG images/sec on B200 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our CUDA path
+    python bench.py --impl reference [--gpus N] --steps K --warmup W  # CPU baseline arm (host cores)
+
+For N>1 launch with torchrun (one rank per GPU); rank 0 prints the line.  Workload (config.workload):
+BASELINE.json configs[2] at its largest single-GPU batch — PMG eval forward, committed hparams,
+1024 images / GPU, 3×224×224 bf16, synthetic images + seeded synthetic checkpoint.  Weak scaling: the
+per-GPU batch is fixed, the only collective is one all-gather of the packed logits per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_IMAGE = 77_348_864
+CONV_GRAM_FLOPS = 34_654_208            # conv stack + chan_proj + Gram
+BYTES_PER_IMAGE = 3 * 224 * 224 * 2 + 52 * 4   # bf16 image in + fp32 logits out
+STAGE_FLOPS = {                          # per image, committed config
+    "conv0": 9_633_792, "conv1": 12_845_056, "conv2": 3_211_264, "chan_proj": 4_816_896, "gram": 4_147_200,
+    "token_proj": 31_850_496, "encoder_layer": 5_370_624, "pool_heads": 102_912,
+    "backbone_gram": 34_654_208, "encoder": 10_741_248,
+}
+STAGE_BYTES = {                          # per image algorithmic HBM bytes when the stage runs as its own kernel
+    "conv0": 3 * 224 * 224 * 2 + 32 * 56 * 56 * 4, "pool_heads": 9 * 192 * 4 + 52 * 4,
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "source": "measured (MEASURED_PEAKS.json, burst)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [s.strip() for s in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_port(batch, seed=0):
+    import torch
+    from oracle import synth
+    from oracle.pmg_torch_port import PMGTorchPort
+    torch.set_num_threads(os.cpu_count() or 1)
+    port = PMGTorchPort(synth.pmg_state_dict(0), synth.PMG_TASKS, 3, 4)
+    x = torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(seed))
+    return port, x
+
+
+def time_cpu_baseline(budget_s=12.0, batch=64):
+    """Reference-equivalent CPU forward (oracle/pmg_torch_port.py) on the host cores: bounded sample."""
+    port, x = cpu_port(batch)
+    for _ in range(2):
+        port(x)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        port(x); n += 1
+        el = time.perf_counter() - t0
+        if el > budget_s or n >= 200:
+            break
+    return {"value": round(n * batch / el, 1), "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{n} forwards of batch {batch} (3x224x224 fp32) in {el:.1f}s, torch CPU ATen ops = the "
+                      f"reference's op sequence (oracle/pmg_torch_port.py), {os.cpu_count()} threads"}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    batch = 256
+    port, x = cpu_port(batch)
+    for _ in range(max(1, args.warmup)):
+        port(x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        port(x)
+    el = time.perf_counter() - t0
+    v = args.steps * batch / el
+    line = {
+        "impl": "reference", "metric": "pmg_images_per_sec", "value": round(v, 1), "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1e3 * el / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample_per_step": f"{batch} images (bounded CPU sample of the 1024/GPU batch)"},
+        "cpu_baseline": {"value": round(v, 1), "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{args.steps} steps x {batch} images, torch CPU, {os.cpu_count()} threads"},
+        "e2e": {"value": round(v, 1), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+WORKLOAD = ("PMG eval forward, committed hparams (ndf32 patch_div3 gram96 d192 L2 H4, 12 tasks/52 classes), "
+            "3x224x224 bf16, 1024 images per GPU, synthetic images + seeded synthetic checkpoint")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="images per GPU per step")
+    ap.add_argument("--e2e-chunk", type=int, default=128)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--force-generic", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import pmg_b200
+    from pmg_b200 import _lib
+    from pmg_b200.runner import HostPipeline, gather_logits
+    from oracle import synth   # seeded synthetic checkpoint generator (test infra; weights only, not compute)
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path); use --impl reference for the CPU arm"
+    W = max(3, args.warmup)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    hp, tasks = synth.PMG_HPARAMS, synth.PMG_TASKS
+    model = pmg_b200.MultiTaskPatchGANGramModelNonOverlapV2(
+        input_nc=3, ndf=hp["ndf"], norm="batch", patch_size=hp["patch_size"], patch_div=hp["patch_div"],
+        num_classes_per_task=tasks, gram_channels=hp["gram_channels"], d_model=hp["d_model"],
+        transformer_layers=hp["transformer_layers"], transformer_heads=hp["transformer_heads"])
+    model.load_state_dict({k: torch.from_numpy(np.array(v)) for k, v in synth.pmg_state_dict(0).items()})
+    model.to(dev).eval()
+    model.force_generic = args.force_generic
+    B = args.batch
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    x = torch.randn(B, 3, 224, 224, device=dev, generator=gen).to(torch.bfloat16)
+    GB = B * world
+
+    def step():
+        with torch.no_grad():
+            lg = model.forward_packed(x)
+            if world > 1:
+                lg = gather_logits(lg, GB)
+        return lg
+
+    def fence():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        step()
+    fence()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+    e1.record()
+    fence()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = GB * args.steps / (ms / 1e3)
+
+    # ---- end to end through the public API: pinned host batch → H2D → forward → D2H logits, every step
+    x_host = x.cpu().pin_memory()
+    pipe = HostPipeline(model, chunk=args.e2e_chunk, device=dev)
+    for _ in range(3):
+        pipe.infer(x_host)
+    fence()
+    e0.record()
+    for _ in range(args.steps):
+        res = pipe.infer(x_host)
+        if world > 1:
+            pass  # logits stay per rank on the host in the e2e arm: the D2H read is the result delivery
+    e1.record()
+    fence()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_e2e = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    e2e_value = GB * args.steps / (ms_e2e / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-stage device times (events between kernels, on the launching stream) → roofline
+    import ctypes
+    pk = peaks()
+    cfgp = ctypes.byref(model._cfg)
+    stages = (_lib.PmgStageTime * 64)()
+    n_st = ctypes.c_int(0)
+    acc = {}
+    reps = 5
+    lg = torch.empty((B, 52), dtype=torch.float32, device=dev)
+    flags = _lib.PMG_FLAG_FORCE_GENERIC if args.force_generic else 0
+    for _ in range(reps):
+        rc = _lib.lib.pmg_forward_profile(cfgp, model._packed.data_ptr(), x.data_ptr(), _lib.PMG_BF16, B, 224, 224,
+                                          lg.data_ptr(), model._ws.data_ptr(), model._ws.numel(), flags,
+                                          torch.cuda.current_stream().cuda_stream, stages, 64, ctypes.byref(n_st))
+        _lib.check(rc, "pmg_forward_profile")
+        for i in range(n_st.value):
+            nm = stages[i].name.decode()
+            acc.setdefault(nm, []).append(stages[i].ms)
+    # a stage name can repeat inside one forward (encoder_layer ×2): average per launch
+    per_launch = {k: sum(v) / len(v) for k, v in acc.items()}
+    per_forward = {k: sum(v) / reps for k, v in acc.items()}
+    dom = max(per_forward, key=per_forward.get)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as f:
+            traffic = json.load(f).get(dom)
+    dom_flops = STAGE_FLOPS.get(dom, 0) * B
+    ach = dom_flops / (per_launch[dom] / 1e3) / 1e12
+    roofline = {
+        "kernel": dom, "bound": "tensor", "achieved": round(ach, 2), "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+        "frac": round(ach / pk["bf16_tflops"], 4), "traffic": traffic, "peak_source": pk["source"],
+        "ms_per_launch": round(per_launch[dom], 4), "share_of_forward": round(per_forward[dom] / sum(per_forward.values()), 3),
+        "stage_ms": {k: round(v, 4) for k, v in per_forward.items()},
+        "forward": {
+            "tensor_frac": round(value / world * FLOPS_PER_IMAGE / 1e12 / pk["bf16_tflops"], 4),
+            "conv_gram_tensor_frac": round(value / world * CONV_GRAM_FLOPS / 1e12 / pk["bf16_tflops"], 4),
+            "hbm_frac": round(value / world * BYTES_PER_IMAGE / 1e9 / pk["hbm_gbs"], 4),
+            "flops_per_image": FLOPS_PER_IMAGE, "bytes_per_image": BYTES_PER_IMAGE,
+        },
+    }
+    launches = model.launches_per_forward(B) * args.steps
+    line = {
+        "metric": "pmg_images_per_sec", "value": round(value, 1), "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": W, "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": GB, "per_gpu_batch": B, "parallelism": f"dp{world}",
+                   "l2_policy": f"input {B * 3 * 224 * 224 * 2 / 1e6:.0f} MB per GPU per step > 126 MB L2",
+                   "path": "generic-fp32" if args.force_generic else "default",
+                   "collective": "one all_gather of (B_local,52) fp32 logits per step" if world > 1 else "none"},
+        "clocks": clocks,
+        "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": B * 3 * 224 * 224 * 2,
+                "d2h_bytes_per_step": B * 52 * 4, "ms_per_step": round(ms_e2e / args.steps, 4),
+                "api": "pmg_b200.runner.HostPipeline.infer(pinned host bf16 batch) -> pinned host logits",
+                "chunk": args.e2e_chunk},
+        "gpu_launches": launches,
+        "roofline": roofline,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = time_cpu_baseline()
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,49 @@
+"""Binding the UNMODIFIED reference scripts to the B200 module.
+
+The reference imports its model by module path (``from Models.models_PMG import
+MultiTaskPatchGANGramModelNonOverlapV2`` — utils/PMG/PMG_model_utils.py:9-11) and is run as
+``python test_PMG.py …`` from its own checkout, so ``sys.path[0]`` always resolves ``Models`` to the
+reference's package.  ``install_as_reference_models()`` pre-seeds ``sys.modules['Models.models_PMG']``
+with this package's module, after which ``build_model_from_hparams`` / ``load_best_model`` /
+``test_PMG.py --mode benchmark`` / ``Functions/PMG_evaluation.py`` run unchanged on the CUDA kernels.
+
+    python -m pmg_b200.compat /path/to/reference/test_PMG.py --mode benchmark …
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import runpy
+import sys
+import types
+
+
+def install_as_reference_models() -> None:
+    from . import models_PMG
+    pkg = sys.modules.get("Models")
+    if pkg is None:
+        try:
+            pkg = importlib.import_module("Models")       # the reference's namespace/package if on sys.path
+        except ImportError:
+            pkg = types.ModuleType("Models")
+            pkg.__path__ = []                              # mark as package
+            sys.modules["Models"] = pkg
+    sys.modules["Models.models_PMG"] = models_PMG
+    setattr(pkg, "models_PMG", models_PMG)
+
+
+def main(argv=None) -> int:
+    argv = list(sys.argv[1:] if argv is None else argv)
+    if not argv:
+        print(__doc__)
+        return 2
+    script = os.path.abspath(argv[0])
+    sys.path.insert(0, os.path.dirname(script))            # what `python script.py` would have done
+    install_as_reference_models()
+    sys.argv = [script] + argv[1:]
+    runpy.run_path(script, run_name="__main__")
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

@@ -1,0 +1,289 @@
+"""Drop-in replacement for the reference module ``Models/models_PMG.py``.
+
+``MultiTaskPatchGANGramModelNonOverlapV2`` keeps the reference constructor signature
+(Models/models_PMG.py:78-92), registers exactly the same parameters / buffers under the same names
+(the 81 keys of Model_weights/PMG/hyperparameters_PMG.json:53-135, so ``load_state_dict(strict=True)``
+from utils/PMG/PMG_model_utils.py:187 works), exposes the attributes the reference's callers read
+(``feature_extractor``, ``se``, ``chan_proj``, ``token_proj``, ``transformer``, ``task_pool.query``,
+``classifiers``, ``patch_div``, ``num_classes_per_task`` …) and returns the same
+``Dict[task, Tensor(B, ncls)]`` from ``forward``.
+
+What differs is the inside of ``forward`` (reference :176-199): the sub-modules are parameter
+holders only; the arithmetic runs in hand-written sm_100a CUDA kernels behind the C ABI of
+``include/pmg_b200.h`` (``libpmg_b200.so``).  There is no CPU path and no eager-PyTorch fallback: a
+CPU tensor, train mode, or a missing library raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+__all__ = ["MultiTaskPatchGANGramModelNonOverlapV2", "TaskAttentionPooling", "TransformerBlock", "SEBlock"]
+
+
+class SEBlock(nn.Module):
+    """Channel attention of the reference (models_PMG.py:15-30).  Off-path in every committed config
+    (``use_channel_attention: false``); kept only so the name resolves — the kernels do not implement it."""
+
+    def __init__(self, C: int, r: int = 16):
+        super().__init__()
+        raise NotImplementedError(
+            "use_channel_attention=True (SEBlock) is not implemented by the B200 kernels; the committed "
+            "hyperparameters_PMG.json sets it to false")
+
+
+class TaskAttentionPooling(nn.Module):
+    """Holder of the per-task query vectors (reference models_PMG.py:36-57).
+
+    The pooling itself (s = tok·q_t, softmax over tokens, weighted sum — no 1/sqrt(d)) is fused with
+    the classifier heads inside the CUDA library."""
+
+    def __init__(self, d_model: int, tasks: Dict[str, int]):
+        super().__init__()
+        self.tasks = list(tasks.keys())
+        self.query = nn.ParameterDict({name: nn.Parameter(torch.randn(d_model)) for name in self.tasks})
+
+    def forward(self, tokens):  # pragma: no cover - parameter holder
+        raise RuntimeError("TaskAttentionPooling is fused into the PMG CUDA forward; call the model instead")
+
+
+class TransformerBlock(nn.Module):
+    """Holder of the shared pre-LN encoder stack (reference models_PMG.py:60-72)."""
+
+    def __init__(self, d_model=256, nhead=4, dim_feedforward=512, dropout=0.1, num_layers=1):
+        super().__init__()
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            self.encoder = nn.TransformerEncoder(
+                nn.TransformerEncoderLayer(d_model=d_model, nhead=nhead, dim_feedforward=dim_feedforward,
+                                           dropout=dropout, batch_first=True, norm_first=True),
+                num_layers=num_layers)
+
+    def forward(self, x):  # pragma: no cover - parameter holder
+        raise RuntimeError("TransformerBlock is fused into the PMG CUDA forward; call the model instead")
+
+
+def _backbone_plan(input_nc: int, ndf: int, patch_size: int):
+    """(cin, cout, k) per conv — the reference's layer-count loop, models_PMG.py:107-128."""
+    plan, cin, width, rf = [], input_nc, ndf, patch_size
+    while rf > 4 and width <= 512:
+        plan.append((cin, width, 4))
+        cin, width, rf = width, width * 2, rf / 4
+    plan.append((cin, width, 1))
+    return plan
+
+
+class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
+    def __init__(
+        self,
+        input_nc: int = 3,
+        ndf: int = 64,
+        norm: str = "batch",
+        patch_size: int = 70,
+        patch_div: int = 4,
+        num_classes_per_task: Dict[str, int] | None = None,
+        use_channel_attention: bool = False,
+        use_token_attention: bool = True,
+        gram_channels: int = 64,
+        d_model: int = 256,
+        transformer_layers: int = 1,
+        transformer_heads: int = 4,
+    ):
+        super().__init__()
+        if norm in ("instance", "group"):
+            raise NotImplementedError(
+                f"norm={norm!r}: the B200 kernels fold BatchNorm2d(eval) into the conv epilogue; "
+                "instance/group norm are not implemented (committed config uses 'batch')")
+        self.num_classes_per_task = num_classes_per_task or {}
+        if not self.num_classes_per_task:
+            raise ValueError("num_classes_per_task must name at least one task")
+        self.patch_div = patch_div
+        self.use_channel_attention = use_channel_attention
+        self.use_token_attention = use_token_attention
+        self.gram_channels = gram_channels
+
+        stack = []
+        for cin, cout, k in _backbone_plan(input_nc, ndf, patch_size):
+            stack.append(nn.Conv2d(cin, cout, kernel_size=k, stride=k, padding=0, bias=False))
+            stack.append(nn.BatchNorm2d(cout, affine=True))
+            stack.append(nn.LeakyReLU(0.2, inplace=True))
+        self.feature_extractor = nn.Sequential(*stack)
+        self.C = stack[-3].out_channels
+
+        self.se = SEBlock(self.C) if use_channel_attention else nn.Identity()
+        self.chan_proj = nn.Conv2d(self.C, gram_channels, kernel_size=1, bias=False)
+        self.Cr = gram_channels
+        self.token_proj = nn.Linear(self.Cr * self.Cr, d_model)
+        n_tf = transformer_layers if (use_token_attention and transformer_layers > 0) else 0
+        self.transformer = (TransformerBlock(d_model=d_model, nhead=transformer_heads,
+                                             dim_feedforward=2 * d_model, dropout=0.1, num_layers=n_tf)
+                            if n_tf > 0 else nn.Identity())
+        self.task_pool = TaskAttentionPooling(d_model=d_model, tasks=self.num_classes_per_task)
+        self.classifiers = nn.ModuleDict({t: nn.Linear(d_model, n) for t, n in self.num_classes_per_task.items()})
+
+        # ---- kernel-side state: never part of state_dict ----
+        self._cfg = _lib.make_config(input_nc, ndf, int(patch_size), patch_div, gram_channels, d_model, n_tf,
+                                     transformer_heads, list(self.num_classes_per_task.values()))
+        if _lib.lib.pmg_param_count(ctypes.byref(self._cfg)) < 0:
+            raise ValueError("configuration rejected by the PMG CUDA library (pmg_param_count < 0)")
+        self._n_logits = _lib.lib.pmg_logits_per_image(ctypes.byref(self._cfg))
+        self._packed: Optional[torch.Tensor] = None
+        self._packed_key: Optional[Tuple] = None
+        self._ws: Optional[torch.Tensor] = None
+        self._lock = threading.Lock()
+        self.force_generic = False      # tests: route through the shape-generic kernels
+
+    # kernel-side state is rebuilt on demand; keep it out of pickles / deepcopies
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        for k in ("_packed", "_packed_key", "_ws", "_lock", "_staged"):
+            st.pop(k, None)
+        c = st.pop("_cfg")
+        st["_cfg_tuple"] = (c.input_nc, c.ndf, c.patch_size, c.patch_div, c.gram_channels, c.d_model,
+                            c.transformer_layers, c.transformer_heads, [c.ncls[i] for i in range(c.n_tasks)])
+        return st
+
+    def __setstate__(self, st):
+        st = dict(st)
+        cfg = st.pop("_cfg_tuple")
+        super().__setstate__(st)
+        self._cfg = _lib.make_config(*cfg)
+        self._packed = self._packed_key = self._ws = None
+        self._lock = threading.Lock()
+
+    # ------------------------------------------------------------------ weight packing
+    def _abi_params(self):
+        """Parameter tensors in the order include/pmg_b200.h documents for pmg_pack_weights."""
+        out = []
+        mods = list(self.feature_extractor)
+        for i in range(0, len(mods), 3):
+            conv, bn = mods[i], mods[i + 1]
+            out += [conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        out += [self.chan_proj.weight, self.token_proj.weight, self.token_proj.bias]
+        if not isinstance(self.transformer, nn.Identity):
+            for layer in self.transformer.encoder.layers:
+                out += [layer.self_attn.in_proj_weight, layer.self_attn.in_proj_bias,
+                        layer.self_attn.out_proj.weight, layer.self_attn.out_proj.bias,
+                        layer.linear1.weight, layer.linear1.bias, layer.linear2.weight, layer.linear2.bias,
+                        layer.norm1.weight, layer.norm1.bias, layer.norm2.weight, layer.norm2.bias]
+        out += [self.task_pool.query[t] for t in self.num_classes_per_task]
+        for t in self.num_classes_per_task:
+            out += [self.classifiers[t].weight, self.classifiers[t].bias]
+        return out
+
+    def _ensure_packed(self, device: torch.device, stream_ptr: int) -> torch.Tensor:
+        params = self._abi_params()
+        key = (device, tuple((p.data_ptr(), p._version) for p in params))
+        if self._packed is not None and key == self._packed_key:
+            return self._packed
+        staged = []
+        for p in params:
+            if p.device != device:
+                raise RuntimeError(f"model parameters live on {p.device} but the input is on {device}; "
+                                   "call model.to(device) first")
+            t = p.detach()
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.float().contiguous()
+            staged.append(t)
+        n = len(staged)
+        ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in staged])
+        nbytes = _lib.lib.pmg_packed_bytes(ctypes.byref(self._cfg))
+        if nbytes == 0:
+            raise _lib.PmgError("pmg_packed_bytes: unsupported configuration")
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _lib.check(_lib.lib.pmg_pack_weights(ctypes.byref(self._cfg), ptrs, n, packed.data_ptr(), nbytes, stream_ptr),
+                   "pmg_pack_weights")
+        self._packed, self._packed_key = packed, key
+        self._staged = staged   # keep alive until the pack kernels have run
+        return packed
+
+    # ------------------------------------------------------------------ forward
+    def _run(self, x: torch.Tensor, want_gram: bool = False, taps: bool = False):
+        if self.training:
+            raise RuntimeError("PMG B200 kernels implement the eval forward only (BatchNorm running stats, "
+                               "dropout inert): call model.eval()")
+        if not isinstance(x, torch.Tensor) or x.dim() != 4:
+            raise ValueError("expected a (B, C, H, W) tensor")
+        if not x.is_cuda:
+            raise RuntimeError("PMG B200 forward needs a CUDA tensor: there is no CPU fallback")
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise RuntimeError("the PMG B200 forward is inference-only: no autograd graph is recorded "
+                               "(input requires grad). Use torch.no_grad().")
+        if x.dtype == torch.bfloat16:
+            dt = _lib.PMG_BF16
+        elif x.dtype == torch.float32:
+            dt = _lib.PMG_F32
+        else:
+            raise TypeError(f"input dtype {x.dtype} not supported (float32 or bfloat16)")
+        B, Cin, H, W = x.shape
+        if Cin != self._cfg.input_nc:
+            raise ValueError(f"expected {self._cfg.input_nc} input channels, got {Cin}")
+        x = x.contiguous()
+        cfgp = ctypes.byref(self._cfg)
+        with self._lock, torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            packed = self._ensure_packed(x.device, stream)
+            need = _lib.lib.pmg_workspace_bytes(cfgp, B, H, W)
+            if need == 0:
+                raise ValueError(f"input {tuple(x.shape)} is too small for this backbone / patch split")
+            if self._ws is None or self._ws.device != x.device or self._ws.numel() < need:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+            logits = torch.empty((B, self._n_logits), dtype=torch.float32, device=x.device)
+            gram = None
+            extra = {}
+            tp = None
+            np_ = self.patch_div * self.patch_div
+            if want_gram:
+                gram = torch.empty((B, np_, self.Cr, self.Cr), dtype=torch.float32, device=x.device)
+            if taps:
+                hc, wc = H, W
+                for m in self.feature_extractor:
+                    if isinstance(m, nn.Conv2d) and m.kernel_size[0] == 4:
+                        hc, wc = hc // 4, wc // 4
+                d = self.token_proj.out_features
+                extra = {"chan": torch.empty((B, hc, wc, self.Cr), dtype=torch.float32, device=x.device),
+                         "tokens_in": torch.empty((B, np_, d), dtype=torch.float32, device=x.device),
+                         "tokens_out": torch.empty((B, np_, d), dtype=torch.float32, device=x.device)}
+                tp = _lib.PmgTaps(extra["chan"].data_ptr(), extra["tokens_in"].data_ptr(), extra["tokens_out"].data_ptr())
+            flags = _lib.PMG_FLAG_FORCE_GENERIC if self.force_generic else 0
+            rc = _lib.lib.pmg_forward(cfgp, packed.data_ptr(), x.data_ptr(), dt, B, H, W, logits.data_ptr(),
+                                      gram.data_ptr() if gram is not None else None,
+                                      ctypes.byref(tp) if tp is not None else None,
+                                      self._ws.data_ptr(), self._ws.numel(), flags, stream)
+            _lib.check(rc, "pmg_forward")
+        return logits, gram, extra
+
+    def _split(self, logits: torch.Tensor) -> Dict[str, torch.Tensor]:
+        out, o = {}, 0
+        for t, n in self.num_classes_per_task.items():
+            out[t] = logits[:, o:o + n]
+            o += n
+        return out
+
+    def forward(self, x):
+        logits, _, _ = self._run(x)
+        return self._split(logits)
+
+    def forward_packed(self, x) -> torch.Tensor:
+        """(B, Σncls) fp32 — the dict of ``forward`` as one tensor, columns in Tasks.json order."""
+        return self._run(x)[0]
+
+    def forward_with_gram(self, x):
+        """(dict, G) with G = per-patch Gram (B, patch_div², Cr, Cr) of reference line :188."""
+        logits, gram, _ = self._run(x, want_gram=True)
+        return self._split(logits), gram
+
+    def forward_debug(self, x):
+        """Test hook: (packed logits, gram, {chan, tokens_in, tokens_out})."""
+        return self._run(x, want_gram=True, taps=True)
+
+    def launches_per_forward(self, B: int, H: int = 224, W: int = 224) -> int:
+        flags = _lib.PMG_FLAG_FORCE_GENERIC if self.force_generic else 0
+        return _lib.lib.pmg_forward_launch_count(ctypes.byref(self._cfg), B, H, W, flags)

