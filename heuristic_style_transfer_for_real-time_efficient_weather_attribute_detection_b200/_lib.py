@@ -36,7 +36,7 @@ class PmgError(RuntimeError):
 EXPORTS = [
     "pmg_abi_version", "pmg_status_string", "pmg_last_cuda_error", "pmg_param_count", "pmg_packed_bytes",
     "pmg_pack_weights", "pmg_workspace_bytes", "pmg_logits_per_image", "pmg_forward_launch_count",
-    "pmg_forward", "pmg_forward_profile", "pmg_gram_batched",
+    "pmg_forward", "pmg_forward_profile", "pmg_gram_batched", "pmg_tc_gemm",
 ]
 
 
@@ -72,6 +72,9 @@ def _load() -> C.CDLL:
     lib.pmg_forward_profile.restype = C.c_int
     lib.pmg_gram_batched.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p]
     lib.pmg_gram_batched.restype = C.c_int
+    lib.pmg_tc_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                C.c_void_p, C.c_void_p]
+    lib.pmg_tc_gemm.restype = C.c_int
     if lib.pmg_abi_version() != 1:
         raise ImportError("libpmg_b200.so ABI version mismatch — rebuild")
     return lib

@@ -1,0 +1,91 @@
+// tc_host.cuh — host helpers for the tcgen05 GEMM: TMA tensor-map encoding (driver entry point fetched
+// through the runtime, so the library does not link libcuda) and the templated launcher.
+#pragma once
+
+#include "pmg_common.cuh"
+#include "tc_gemm.cuh"
+
+namespace tc {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// bf16 row-major [rows, cols] (cols contiguous, row pitch = pitch_elems), box = box_rows × 64 cols,
+// 128-byte swizzle; out-of-bounds rows/cols read as zero.
+inline int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
+                          uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { pmg::set_cuda_error(cudaErrorNotSupported, "cuTensorMapEncodeTiled entry point"); return PMG_ERR_CUDA; }
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {pitch_elems * 2};
+    cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { pmg::set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled"); return PMG_ERR_CUDA; }
+    return PMG_OK;
+}
+
+// A: [M, K] bf16 planes (lo may be null ⇒ single plane), pitch lda; B: [N, K] bf16, pitch ldb.
+// k_cols = columns that really exist in memory (≤ K); TMA zero-fills [k_cols, K) — used for conv0's K = 48.
+template <int BN, int NA>
+int launch_gemm_t(const void* A_hi, const void* A_lo, int lda, const void* B, int ldb, GemmParams p, int splits,
+                  int k_cols, cudaStream_t st) {
+    if (p.K % GEMM_BK || p.N % BN || p.M < 1 || splits < 1 || k_cols > p.K || k_cols < 1) return PMG_ERR_BAD_SHAPE;
+    CUtensorMap ta_hi, ta_lo, tb;
+    int rc;
+    if ((rc = make_tmap_bf16(&ta_hi, A_hi, p.M, k_cols, lda, GEMM_BM))) return rc;
+    if ((rc = make_tmap_bf16(&ta_lo, NA == 2 ? A_lo : A_hi, p.M, k_cols, lda, GEMM_BM))) return rc;
+    if ((rc = make_tmap_bf16(&tb, B, p.N, k_cols, ldb, BN))) return rc;
+    const int total_kb = p.K / GEMM_BK;
+    p.kblocks_per_split = (total_kb + splits - 1) / splits;
+    const int eff_splits = (total_kb + p.kblocks_per_split - 1) / p.kblocks_per_split;
+    constexpr int smem = gemm_smem_bytes<BN, NA>();
+    static bool attr_set = false;   // idempotent; racing threads set the same value
+    if (!attr_set) {
+        PMG_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "gemm smem attr");
+        attr_set = true;
+    }
+    dim3 grid((p.M + GEMM_BM - 1) / GEMM_BM, eff_splits, p.N / BN);
+    gemm_kernel<BN, NA><<<grid, GEMM_THREADS, smem, st>>>(ta_hi, ta_lo, tb, p);
+    PMG_LAUNCH_OK("tc gemm");
+    return PMG_OK;
+}
+
+// number of split-K partial buffers launch_gemm_t will actually write for (K, splits)
+inline int effective_splits(int K, int splits) {
+    const int total_kb = K / GEMM_BK;
+    const int per = (total_kb + splits - 1) / splits;
+    return (total_kb + per - 1) / per;
+}
+
+inline int launch_gemm(int BN, int NA, const void* A_hi, const void* A_lo, int lda, const void* B, int ldb,
+                       const GemmParams& p, int splits, cudaStream_t st, int k_cols = 0) {
+    if (k_cols <= 0) k_cols = p.K;
+#define PMG_GEMM_CASE(bn)                                                                                 \
+    if (BN == bn) return NA == 2 ? launch_gemm_t<bn, 2>(A_hi, A_lo, lda, B, ldb, p, splits, k_cols, st)   \
+                                 : launch_gemm_t<bn, 1>(A_hi, A_lo, lda, B, ldb, p, splits, k_cols, st);
+    PMG_GEMM_CASE(32)
+    PMG_GEMM_CASE(64)
+    PMG_GEMM_CASE(96)
+    PMG_GEMM_CASE(128)
+    PMG_GEMM_CASE(192)
+#undef PMG_GEMM_CASE
+    return PMG_ERR_UNSUPPORTED;
+}
+
+}  // namespace tc

@@ -133,6 +133,13 @@ int pmg_forward_profile(const pmg_config* cfg, const void* packed, const void* x
 int pmg_gram_batched(const void* F, int f_dtype, int B, int C, int HW, float scale, float* G,
                      pmg_stream_t stream);
 
+/* Building block of the fast path, exported for unit tests and micro-benchmarks: one tcgen05 + TMA GEMM
+ *   out[M,N] (fp32) = (a_hi[M,K] + a_lo[M,K]) · b[N,K]^T      bf16 row-major operands, a_lo may be null
+ * bn = N-tile (32, 64, 96, 128 or 192; N % bn == 0), K % 64 == 0.  splits > 1 writes split-K partial sums
+ * out[s][M,N] (s < effective splits) that the caller adds up. */
+int pmg_tc_gemm(const void* a_hi, const void* a_lo, const void* b, int M, int N, int K, int bn, int splits,
+                float* out, pmg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
