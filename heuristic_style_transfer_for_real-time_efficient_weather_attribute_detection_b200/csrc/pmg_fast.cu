@@ -16,6 +16,7 @@
 // the 9-token attention core and the task pooling + heads are small CUDA-core kernels.
 #include "pmg_common.cuh"
 #include "tc_host.cuh"
+#include "tc_gram.cuh"
 
 namespace pmg {
 
@@ -132,53 +133,6 @@ __global__ void __launch_bounds__(256) im2col0_kernel(const void* __restrict__ x
             hi[0] = r0.x; hi[1] = r0.y; hi[2] = r1.x; hi[3] = r1.y;
         }
         *reinterpret_cast<uint4*>(a_hi + r * 48 + j * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Per-patch Gram for the committed shape (14×14 map, replicate pad to 15×15, 3×3 patches of 5×5, Cr = 96)
-// models_PMG.py:157-174,188.  Block = (image, patch), 256 threads, thread = 6×6 tile of the 96×96 output.
-// Emits the hi/lo bf16 planes token_proj consumes and, optionally, fp32 G for the caller.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gram96_kernel(const float* __restrict__ chan, bf16* __restrict__ g_hi,
-                                                     bf16* __restrict__ g_lo, float* __restrict__ g_f32) {
-    __shared__ float sP[25][97];
-    const int b = blockIdx.x / 9, k = blockIdx.x % 9, py = k / 3, px = k % 3;
-    for (int e = threadIdx.x; e < 25 * 96; e += 256) {
-        const int pi = e / 96, ch = e % 96;
-        const int y = min(py * 5 + pi / 5, 13), x = min(px * 5 + pi % 5, 13);
-        sP[pi][ch] = chan[(((size_t)b * 14 + y) * 14 + x) * 96 + ch];
-    }
-    __syncthreads();
-    const int ti = (threadIdx.x >> 4) * 6, tj = (threadIdx.x & 15) * 6;
-    float acc[6][6] = {};
-#pragma unroll 5
-    for (int q = 0; q < 25; ++q) {
-        float a[6], c[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) { a[i] = sP[q][ti + i]; c[i] = sP[q][tj + i]; }
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-#pragma unroll
-            for (int j = 0; j < 6; ++j) acc[i][j] = fmaf(a[i], c[j], acc[i][j]);
-    }
-    const size_t tokbase = (size_t)blockIdx.x * 9216;
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        const size_t o = tokbase + (size_t)(ti + i) * 96 + tj;
-        uint32_t hi[3], lo[3];
-#pragma unroll
-        for (int j = 0; j < 3; ++j) tc::split_bf16x2(acc[i][2 * j] * 0.04f, acc[i][2 * j + 1] * 0.04f, hi[j], lo[j]);
-        // 12-byte runs, 4-byte aligned
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            *reinterpret_cast<uint32_t*>(g_hi + o + 2 * j) = hi[j];
-            *reinterpret_cast<uint32_t*>(g_lo + o + 2 * j) = lo[j];
-        }
-        if (g_f32) {
-#pragma unroll
-            for (int j = 0; j < 6; ++j) g_f32[o + j] = acc[i][j] * 0.04f;
-        }
     }
 }
 
@@ -385,8 +339,16 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
     if (taps && taps->chan)
         PMG_CUDA_OK(cudaMemcpyAsync(taps->chan, Ff(w.chan), (size_t)P * 96 * 4, cudaMemcpyDeviceToDevice, st), "tap chan");
     // patches + Gram (:185-188)
-    gram96_kernel<<<T, 256, 0, st>>>(Ff(w.chan), Hb(w.g_hi), Hb(w.g_lo), gram);
-    PMG_LAUNCH_OK("gram96");
+    {
+        static bool attr_set = false;
+        if (!attr_set) {
+            PMG_CUDA_OK(cudaFuncSetAttribute(tc::gram96_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GRAM_SMEM), "gram smem attr");
+            attr_set = true;
+        }
+        const int grid = T < tc::num_sms() ? T : tc::num_sms();
+        tc::gram96_tc_kernel<<<grid, tc::GRAM_THREADS, tc::GRAM_SMEM, st>>>(Ff(w.chan), Hb(w.g_hi), Hb(w.g_lo), gram, T);
+        PMG_LAUNCH_OK("gram96_tc");
+    }
     PMG_MARK(tm, "gram");
     // token_proj (:192-193): split-K partial sums, reduced (+bias) by tok_ln_kernel
     const size_t pstride = (size_t)T * 192;

@@ -23,6 +23,15 @@ inline EncodeTiledFn encode_fn() {
     return fn;
 }
 
+inline int num_sms() {
+    static int n = [] {
+        int dev = 0, v = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+        return v > 0 ? v : 148;
+    }();
+    return n;
+}
+
 // bf16 row-major [rows, cols] (cols contiguous, row pitch = pitch_elems), box = box_rows × 64 cols,
 // 128-byte swizzle; out-of-bounds rows/cols read as zero.
 inline int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
@@ -60,7 +69,9 @@ int launch_gemm_t(const void* A_hi, const void* A_lo, int lda, const void* B, in
         PMG_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "gemm smem attr");
         attr_set = true;
     }
-    dim3 grid((p.M + GEMM_BM - 1) / GEMM_BM, eff_splits, p.N / BN);
+    if (p.N > GEMM_MAX_N) return PMG_ERR_BAD_SHAPE;
+    const int total_tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * eff_splits * (p.N / BN);
+    const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
     gemm_kernel<BN, NA><<<grid, GEMM_THREADS, smem, st>>>(ta_hi, ta_lo, tb, p);
     PMG_LAUNCH_OK("tc gemm");
     return PMG_OK;
