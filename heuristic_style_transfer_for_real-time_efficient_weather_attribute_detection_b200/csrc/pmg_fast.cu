@@ -196,18 +196,21 @@ __global__ void __launch_bounds__(128) tok_ln_kernel(const float* __restrict__ p
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) attn9_kernel(const float* __restrict__ qkv, bf16* __restrict__ o_hi,
                                                     bf16* __restrict__ o_lo) {
-    __shared__ float s[9 * 576];
-    __shared__ float sp[4][9][9];
+    constexpr int LD = 580;                 // 576 + 4: token rows land in different banks (576 ≡ 0 mod 32)
+    __shared__ __align__(16) float s[9 * LD];
+    __shared__ float sp[4][9][12];
     const int b = blockIdx.x;
-    for (int e = threadIdx.x; e < 9 * 576 / 4; e += 128)
-        reinterpret_cast<float4*>(s)[e] = reinterpret_cast<const float4*>(qkv + (size_t)b * 9 * 576)[e];
+    for (int e = threadIdx.x; e < 9 * 144; e += 128) {
+        const int t = e / 144, c4 = e % 144;
+        *reinterpret_cast<float4*>(s + t * LD + c4 * 4) = reinterpret_cast<const float4*>(qkv + ((size_t)b * 9 + t) * 576)[c4];
+    }
     __syncthreads();
     const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // scores: 81 (i,j) pairs per head over 32 lanes
     for (int e = lane; e < 81; e += 32) {
         const int i = e / 9, j = e % 9;
-        const float* q = s + i * 576 + h * 48;
-        const float* kk = s + j * 576 + 192 + h * 48;
+        const float* q = s + i * LD + h * 48;
+        const float* kk = s + j * LD + 192 + h * 48;
         float a = 0.f;
 #pragma unroll 8
         for (int c = 0; c < 48; ++c) a = fmaf(q[c], kk[c], a);
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(128) attn9_kernel(const float* __restrict__ qk
 #pragma unroll
         for (int j = 0; j < 9; ++j) {
             const float w = sp[h][i][j];
-            const float2 v = *reinterpret_cast<const float2*>(s + j * 576 + 384 + h * 48 + c);
+            const float2 v = *reinterpret_cast<const float2*>(s + j * LD + 384 + h * 48 + c);
             a0 = fmaf(w, v.x, a0); a1 = fmaf(w, v.y, a1);
         }
         uint32_t hi, lo;
@@ -345,8 +348,8 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
             PMG_CUDA_OK(cudaFuncSetAttribute(tc::gram96_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GRAM_SMEM), "gram smem attr");
             attr_set = true;
         }
-        const int grid = T < tc::num_sms() ? T : tc::num_sms();
-        tc::gram96_tc_kernel<<<grid, tc::GRAM_THREADS, tc::GRAM_SMEM, st>>>(Ff(w.chan), Hb(w.g_hi), Hb(w.g_lo), gram, T);
+        const int grid = B < tc::num_sms() ? B : tc::num_sms();
+        tc::gram96_tc_kernel<<<grid, tc::GRAM_THREADS, tc::GRAM_SMEM, st>>>(Ff(w.chan), Hb(w.g_hi), Hb(w.g_lo), gram, B);
         PMG_LAUNCH_OK("gram96_tc");
     }
     PMG_MARK(tm, "gram");

@@ -76,7 +76,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
     static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment for the 128B swizzle");
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // pointer arithmetic on the __shared__ array (not an integer round-trip) keeps the shared address space,
+    // so the epilogue's scale/shift reads compile to LDS instead of generic LD
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;     // [2]
@@ -196,11 +198,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
                 }
                 float v[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = fmaf(__uint_as_float(r[j]), s_scale[nb + j], s_shift[nb + j]);
-                    if (p.act == GACT_LEAKY) x = x >= 0.f ? x : 0.2f * x;
-                    else if (p.act == GACT_RELU) x = fmaxf(x, 0.f);
-                    v[j] = x;
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 sc = *reinterpret_cast<const float4*>(s_scale + nb + j);
+                    const float4 sh = *reinterpret_cast<const float4*>(s_shift + nb + j);
+                    v[j] = fmaf(__uint_as_float(r[j]), sc.x, sh.x);
+                    v[j + 1] = fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y);
+                    v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z);
+                    v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w);
+                }
+                if (p.act == GACT_LEAKY) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.2f * v[j]);     // LeakyReLU(0.2): max(x, 0.2x)
+                } else if (p.act == GACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
                 }
                 if (p.epi == EPI_F32) {
                     float* dst = p.out_f32 + (size_t)row * p.ldc + nb;
