@@ -348,8 +348,8 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
             PMG_CUDA_OK(cudaFuncSetAttribute(tc::gram96_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GRAM_SMEM), "gram smem attr");
             attr_set = true;
         }
-        const int grid = B < tc::num_sms() ? B : tc::num_sms();
-        tc::gram96_tc_kernel<<<grid, tc::GRAM_THREADS, tc::GRAM_SMEM, st>>>(Ff(w.chan), Hb(w.g_hi), Hb(w.g_lo), gram, B);
+        const int grid = T < tc::num_sms() ? T : tc::num_sms();
+        tc::gram96_tc_kernel<<<grid, tc::GRAM_THREADS, tc::GRAM_SMEM, st>>>(Ff(w.chan), Hb(w.g_hi), Hb(w.g_lo), gram, T);
         PMG_LAUNCH_OK("gram96_tc");
     }
     PMG_MARK(tm, "gram");

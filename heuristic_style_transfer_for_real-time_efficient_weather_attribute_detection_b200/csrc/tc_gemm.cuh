@@ -48,7 +48,7 @@ __host__ __device__ constexpr int gemm_stage_bytes() { return NA * GEMM_BM * GEM
 
 template <int BN, int NA>
 __host__ __device__ constexpr int gemm_stages() {
-    constexpr int budget = 196 * 1024;
+    constexpr int budget = 180 * 1024;
     constexpr int s = budget / gemm_stage_bytes<BN, NA>();
     return s > 8 ? 8 : s;
 }
@@ -57,7 +57,8 @@ constexpr int GEMM_MAX_N = 576;   // scale/shift staged in smem for the whole ou
 
 template <int BN, int NA>
 __host__ __device__ constexpr int gemm_smem_bytes() {
-    return gemm_stages<BN, NA>() * gemm_stage_bytes<BN, NA>() + 1024 /*align*/ + 256 /*barriers*/ + 2 * GEMM_MAX_N * 4;
+    return gemm_stages<BN, NA>() * gemm_stage_bytes<BN, NA>() + 1024 /*align*/ + 256 /*barriers*/ + 2 * GEMM_MAX_N * 4 +
+           8 * 4096 /*epilogue staging, 4 KB per epilogue warp*/;
 }
 
 // Persistent: CTA c processes tiles c, c+gridDim.x, …; tile = (split, n_tile, m_tile), m fastest.
@@ -86,6 +87,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
     float* s_scale = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);
     float* s_shift = s_scale + GEMM_MAX_N;
+    uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_shift + GEMM_MAX_N);      // 8 × 4 KB, 128-byte aligned
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
@@ -171,8 +173,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
             if ((lt & 1) != grp) continue;
             const int mt = tile % tiles_m, nt = (tile / tiles_m) % tiles_n, sp = tile / (tiles_m * tiles_n);
             const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
-            const int row = mt * GEMM_BM + q * 32 + lane;
-            const bool in_m = row < p.M;
             mbar_wait(&tmem_full_bar[as], aph);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + as * ACC_COLS + ((uint32_t)(q * 32) << 16);
@@ -186,52 +186,62 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
                 }
-                if (!in_m) continue;
                 const int nb = nt * BN + c0;
+                uint32_t w[32];
                 if (p.epi == EPI_PARTIAL) {
-                    float* dst = p.out_f32 + (size_t)sp * p.partial_stride + (size_t)row * p.ldc + nb;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(dst + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                          __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-                    continue;
-                }
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 sc = *reinterpret_cast<const float4*>(s_scale + nb + j);
-                    const float4 sh = *reinterpret_cast<const float4*>(s_shift + nb + j);
-                    v[j] = fmaf(__uint_as_float(r[j]), sc.x, sh.x);
-                    v[j + 1] = fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y);
-                    v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z);
-                    v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w);
-                }
-                if (p.act == GACT_LEAKY) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.2f * v[j]);     // LeakyReLU(0.2): max(x, 0.2x)
-                } else if (p.act == GACT_RELU) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                }
-                if (p.epi == EPI_F32) {
-                    float* dst = p.out_f32 + (size_t)row * p.ldc + nb;
-                    const float* rs = p.resid ? p.resid + (size_t)row * p.ldc + nb : nullptr;
+                    for (int j = 0; j < 32; ++j) w[j] = r[j];
+                } else {
+                    float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
-                        float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                        if (rs) { const float4 t = *reinterpret_cast<const float4*>(rs + j); o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w; }
-                        *reinterpret_cast<float4*>(dst + j) = o;
+                        const float4 sc = *reinterpret_cast<const float4*>(s_scale + nb + j);
+                        const float4 sh = *reinterpret_cast<const float4*>(s_shift + nb + j);
+                        v[j] = fmaf(__uint_as_float(r[j]), sc.x, sh.x);
+                        v[j + 1] = fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y);
+                        v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z);
+                        v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w);
                     }
-                } else {
-                    uint32_t hi[16], lo[16];
+                    if (p.act == GACT_LEAKY) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
-                    uint4* dh = reinterpret_cast<uint4*>(p.out_hi + (size_t)row * p.ldc + nb);
-                    uint4* dl = reinterpret_cast<uint4*>(p.out_lo + (size_t)row * p.ldc + nb);
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.2f * v[j]);     // LeakyReLU(0.2): max(x, 0.2x)
+                    } else if (p.act == GACT_RELU) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                        dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+                    }
+                    if (p.epi == EPI_F32) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v[j]);
+                    } else {
+                        // row slice = [hi 64 B | lo 64 B]
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], w[j], w[16 + j]);
+                    }
+                }
+                // park the row slice in the warp's swizzled staging tile, then store with 8 lanes per row
+                uint8_t* wbuf = s_stage + (warp - 2) * 4096;
+                __syncwarp();
+                stage_write_row(wbuf, lane, w);
+                __syncwarp();
+                const int row0 = mt * GEMM_BM + q * 32;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    int rr, cc;
+                    uint4 d = stage_read(wbuf, lane, i, rr, cc);
+                    const int grow = row0 + rr;
+                    if (grow >= p.M) continue;
+                    if (p.epi == EPI_SPLIT) {
+                        __nv_bfloat16* plane = cc < 4 ? p.out_hi : p.out_lo;
+                        *reinterpret_cast<uint4*>(plane + (size_t)grow * p.ldc + nb + (cc & 3) * 8) = d;
+                    } else {
+                        const size_t off = (size_t)grow * p.ldc + nb + cc * 4;
+                        float* dst = p.out_f32 + (p.epi == EPI_PARTIAL ? (size_t)sp * p.partial_stride : 0) + off;
+                        if (p.epi == EPI_F32 && p.resid) {
+                            const float4 t = *reinterpret_cast<const float4*>(p.resid + off);
+                            d.x = __float_as_uint(__uint_as_float(d.x) + t.x); d.y = __float_as_uint(__uint_as_float(d.y) + t.y);
+                            d.z = __float_as_uint(__uint_as_float(d.z) + t.z); d.w = __float_as_uint(__uint_as_float(d.w) + t.w);
+                        }
+                        *reinterpret_cast<uint4*>(dst) = d;
                     }
                 }
             }

@@ -161,4 +161,21 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
     lo = *reinterpret_cast<uint32_t*>(&l);
 }
 
+// ---------------------------------------------------------------- coalescing epilogue staging
+// A warp owns 32 accumulator rows (thread = row).  Writing each thread's row straight to global gives 32
+// scattered 16-byte pieces per store instruction (half-filled sectors, LSU-bound).  Instead each thread parks
+// its 128-byte row slice in a warp-private, chunk-swizzled 4 KB smem tile (conflict-free STS.128), and the warp
+// re-reads it so that 8 consecutive lanes hold one row's 128 contiguous bytes (conflict-free LDS.128):
+// instruction i covers rows 4i..4i+3.
+__device__ __forceinline__ void stage_write_row(uint8_t* wbuf, int lane, const uint32_t (&w)[32]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(wbuf + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+}
+__device__ __forceinline__ uint4 stage_read(const uint8_t* wbuf, int lane, int i, int& r, int& c) {
+    r = 4 * i + (lane >> 3);
+    c = lane & 7;
+    return *reinterpret_cast<const uint4*>(wbuf + r * 128 + ((c ^ (r & 7)) << 4));
+}
+
 }  // namespace tc
