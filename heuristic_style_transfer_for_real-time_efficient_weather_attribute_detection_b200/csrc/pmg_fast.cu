@@ -289,13 +289,15 @@ size_t fast_workspace_bytes(const Plan&, const Shape&, int B) { return fast_ws(B
 
 int fast_launch_count(const Plan& p, const Shape&, int) { return 5 + 1 + 1 + 1 + 6 * p.nl + (p.nl > 1 ? p.nl - 1 : 0) + 1; }
 
-static int gemm(int BN, int NA, const void* a_hi, const void* a_lo, int lda, const void* b, int M, int N, int K, int epi,
-                int act, int ldc, float* out_f32, bf16* out_hi, bf16* out_lo, const float* scale, const float* shift,
-                const float* resid, int splits, size_t pstride, cudaStream_t st, int k_cols = 0) {
+template <int BN, int NA, int EPI, int ACT>
+static int gemm(const void* a_hi, const void* a_lo, int lda, const void* b, int M, int N, int K, int ldc, float* out_f32,
+                bf16* out_hi, bf16* out_lo, const float* scale, const float* shift, const float* resid, int splits,
+                size_t pstride, cudaStream_t st, int k_cols = 0) {
     tc::GemmParams g{};
-    g.M = M; g.N = N; g.K = K; g.epi = epi; g.act = act; g.ldc = ldc; g.out_f32 = out_f32; g.out_hi = out_hi; g.out_lo = out_lo;
+    g.M = M; g.N = N; g.K = K; g.epi = EPI; g.act = ACT; g.ldc = ldc; g.out_f32 = out_f32; g.out_hi = out_hi; g.out_lo = out_lo;
     g.scale = scale; g.shift = shift; g.resid = resid; g.partial_stride = pstride;
-    return tc::launch_gemm(BN, NA, a_hi, a_lo, lda, b, k_cols > 0 ? k_cols : K, g, splits, st, k_cols);
+    const int kc = k_cols > 0 ? k_cols : K;
+    return tc::launch_gemm_t<BN, NA, EPI, ACT>(a_hi, a_lo, lda, b, kc, g, splits, kc, st);
 }
 
 int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const char* packed, const void* x, int x_dtype,
@@ -318,24 +320,29 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
         else im2col0_kernel<false><<<grid, 256, 0, st>>>(x, Hb(w.a0_hi), nullptr, B);
         PMG_LAUNCH_OK("im2col0");
         PMG_MARK(tm, "im2col0");
-        if ((rc = gemm(32, x_dtype == PMG_F32 ? 2 : 1, Hb(w.a0_hi), Hb(w.a0_lo), 48, Wb(f.w0), P * 16, 32, 64, tc::EPI_SPLIT,
-                       tc::GACT_LEAKY, 32, nullptr, Hb(w.act0_hi), Hb(w.act0_lo), Pf(L.conv_scale[0]), Pf(L.conv_shift[0]),
-                       nullptr, 1, 0, st, 48)))
-            return rc;
+        if (x_dtype == PMG_F32)
+            rc = gemm<32, 2, tc::EPI_SPLIT, tc::GACT_LEAKY>(Hb(w.a0_hi), Hb(w.a0_lo), 48, Wb(f.w0), P * 16, 32, 64, 32, nullptr,
+                                                            Hb(w.act0_hi), Hb(w.act0_lo), Pf(L.conv_scale[0]),
+                                                            Pf(L.conv_shift[0]), nullptr, 1, 0, st, 48);
+        else
+            rc = gemm<32, 1, tc::EPI_SPLIT, tc::GACT_LEAKY>(Hb(w.a0_hi), nullptr, 48, Wb(f.w0), P * 16, 32, 64, 32, nullptr,
+                                                            Hb(w.act0_hi), Hb(w.act0_lo), Pf(L.conv_scale[0]),
+                                                            Pf(L.conv_shift[0]), nullptr, 1, 0, st, 48);
+        if (rc) return rc;
         PMG_MARK(tm, "conv0");
     }
     // conv1 (:115-117, second strided layer)
-    if ((rc = gemm(64, 2, Hb(w.act0_hi), Hb(w.act0_lo), 512, Wb(f.w1), P, 64, 512, tc::EPI_SPLIT, tc::GACT_LEAKY, 64, nullptr,
+    if ((rc = gemm<64, 2, tc::EPI_SPLIT, tc::GACT_LEAKY>(Hb(w.act0_hi), Hb(w.act0_lo), 512, Wb(f.w1), P, 64, 512, 64, nullptr,
                    Hb(w.act1_hi), Hb(w.act1_lo), Pf(L.conv_scale[1]), Pf(L.conv_shift[1]), nullptr, 1, 0, st)))
         return rc;
     PMG_MARK(tm, "conv1");
     // conv2: final 1×1 (:124-128)
-    if ((rc = gemm(128, 2, Hb(w.act1_hi), Hb(w.act1_lo), 64, Wb(f.w2), P, 128, 64, tc::EPI_SPLIT, tc::GACT_LEAKY, 128, nullptr,
+    if ((rc = gemm<128, 2, tc::EPI_SPLIT, tc::GACT_LEAKY>(Hb(w.act1_hi), Hb(w.act1_lo), 64, Wb(f.w2), P, 128, 64, 128, nullptr,
                    Hb(w.act2_hi), Hb(w.act2_lo), Pf(L.conv_scale[2]), Pf(L.conv_shift[2]), nullptr, 1, 0, st)))
         return rc;
     PMG_MARK(tm, "conv2");
     // chan_proj (:136,182) → fp32 pixel-major (B,14,14,96)
-    if ((rc = gemm(96, 2, Hb(w.act2_hi), Hb(w.act2_lo), 128, Wb(f.w3), P, 96, 128, tc::EPI_F32, tc::GACT_NONE, 96, Ff(w.chan),
+    if ((rc = gemm<96, 2, tc::EPI_F32, tc::GACT_NONE>(Hb(w.act2_hi), Hb(w.act2_lo), 128, Wb(f.w3), P, 96, 128, 96, Ff(w.chan),
                    nullptr, nullptr, nullptr, nullptr, nullptr, 1, 0, st)))
         return rc;
     PMG_MARK(tm, "chan_proj");
@@ -355,7 +362,7 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
     PMG_MARK(tm, "gram");
     // token_proj (:192-193): split-K partial sums, reduced (+bias) by tok_ln_kernel
     const size_t pstride = (size_t)T * 192;
-    if ((rc = gemm(192, 2, Hb(w.g_hi), Hb(w.g_lo), 9216, Wb(f.wt), T, 192, 9216, tc::EPI_PARTIAL, tc::GACT_NONE, 192,
+    if ((rc = gemm<192, 2, tc::EPI_PARTIAL, tc::GACT_NONE>(Hb(w.g_hi), Hb(w.g_lo), 9216, Wb(f.wt), T, 192, 9216, 192,
                    Ff(w.partial), nullptr, nullptr, nullptr, nullptr, nullptr, w.splits, pstride, st)))
         return rc;
     PMG_MARK(tm, "token_proj");
@@ -377,21 +384,21 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
                                                        Hb(w.h_lo), T, 1);
             PMG_LAUNCH_OK("ln1");
         }
-        if ((rc = gemm(192, 2, Hb(w.h_hi), Hb(w.h_lo), 192, Wb(f.win[l]), T, 576, 192, tc::EPI_F32, tc::GACT_NONE, 576, Ff(w.qkv),
+        if ((rc = gemm<192, 2, tc::EPI_F32, tc::GACT_NONE>(Hb(w.h_hi), Hb(w.h_lo), 192, Wb(f.win[l]), T, 576, 192, 576, Ff(w.qkv),
                        nullptr, nullptr, nullptr, Pf(t.b_in), nullptr, 1, 0, st)))
             return rc;
         attn9_kernel<<<B, 128, 0, st>>>(Ff(w.qkv), Hb(w.h_hi), Hb(w.h_lo));
         PMG_LAUNCH_OK("attn9");
-        if ((rc = gemm(192, 2, Hb(w.h_hi), Hb(w.h_lo), 192, Wb(f.wo[l]), T, 192, 192, tc::EPI_F32, tc::GACT_NONE, 192, Ff(w.tok),
+        if ((rc = gemm<192, 2, tc::EPI_F32, tc::GACT_NONE>(Hb(w.h_hi), Hb(w.h_lo), 192, Wb(f.wo[l]), T, 192, 192, 192, Ff(w.tok),
                        nullptr, nullptr, nullptr, Pf(t.b_o), Ff(w.tok), 1, 0, st)))
             return rc;
         tok_ln_kernel<<<(T + 3) / 4, 128, 0, st>>>(nullptr, 0, 0, nullptr, Ff(w.tok), Pf(t.ln2w), Pf(t.ln2b), Hb(w.h_hi),
                                                    Hb(w.h_lo), T, 1);
         PMG_LAUNCH_OK("ln2");
-        if ((rc = gemm(192, 2, Hb(w.h_hi), Hb(w.h_lo), 192, Wb(f.wf1[l]), T, 384, 192, tc::EPI_SPLIT, tc::GACT_RELU, 384, nullptr,
+        if ((rc = gemm<192, 2, tc::EPI_SPLIT, tc::GACT_RELU>(Hb(w.h_hi), Hb(w.h_lo), 192, Wb(f.wf1[l]), T, 384, 192, 384, nullptr,
                        Hb(w.ffh_hi), Hb(w.ffh_lo), nullptr, Pf(t.b_1), nullptr, 1, 0, st)))
             return rc;
-        if ((rc = gemm(192, 2, Hb(w.ffh_hi), Hb(w.ffh_lo), 384, Wb(f.wf2[l]), T, 192, 384, tc::EPI_F32, tc::GACT_NONE, 192,
+        if ((rc = gemm<192, 2, tc::EPI_F32, tc::GACT_NONE>(Hb(w.ffh_hi), Hb(w.ffh_lo), 384, Wb(f.wf2[l]), T, 192, 384, 192,
                        Ff(w.tok), nullptr, nullptr, nullptr, Pf(t.b_2), Ff(w.tok), 1, 0, st)))
             return rc;
         PMG_MARK(tm, "encoder_layer");
@@ -417,5 +424,16 @@ extern "C" int pmg_tc_gemm(const void* a_hi, const void* a_lo, const void* b, in
     g.M = M; g.N = N; g.K = K; g.ldc = N; g.out_f32 = out;
     g.epi = splits > 1 ? tc::EPI_PARTIAL : tc::EPI_F32;
     g.partial_stride = (size_t)M * N;
-    return tc::launch_gemm(bn, a_lo ? 2 : 1, a_hi, a_lo, K, b, K, g, splits, reinterpret_cast<cudaStream_t>(stream));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define PMG_TG(BNV)                                                                                                        \
+    if (bn == BNV) {                                                                                                       \
+        if (splits > 1)                                                                                                    \
+            return a_lo ? tc::launch_gemm_t<BNV, 2, tc::EPI_PARTIAL, tc::GACT_NONE>(a_hi, a_lo, K, b, K, g, splits, K, st) \
+                        : tc::launch_gemm_t<BNV, 1, tc::EPI_PARTIAL, tc::GACT_NONE>(a_hi, a_lo, K, b, K, g, splits, K, st); \
+        return a_lo ? tc::launch_gemm_t<BNV, 2, tc::EPI_F32, tc::GACT_NONE>(a_hi, a_lo, K, b, K, g, splits, K, st)         \
+                    : tc::launch_gemm_t<BNV, 1, tc::EPI_F32, tc::GACT_NONE>(a_hi, a_lo, K, b, K, g, splits, K, st);        \
+    }
+    PMG_TG(32) PMG_TG(64) PMG_TG(96) PMG_TG(128) PMG_TG(192)
+#undef PMG_TG
+    return PMG_ERR_UNSUPPORTED;
 }

@@ -39,9 +39,18 @@ struct GemmParams {
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_THREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9 = two epilogue groups
+constexpr int GEMM_MAX_N = 576;     // scale/shift staged in smem for the whole output width
+
+// Work item = MT consecutive 128-row M-tiles sharing one TMEM accumulator stage (MT·BN columns): for narrow
+// outputs (conv0: N = 32, K = 48) this amortises the per-tile barrier round trips over 4 tiles.
+template <int BN>
+__host__ __device__ constexpr int gemm_mt() { return BN <= 32 ? 4 : BN <= 64 ? 2 : 1; }
 
 template <int BN>
-__host__ __device__ constexpr int gemm_tmem_cols() { return BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256; }
+__host__ __device__ constexpr int gemm_acc_cols() {
+    constexpr int c = BN * gemm_mt<BN>();
+    return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : 256;
+}
 
 template <int BN, int NA>
 __host__ __device__ constexpr int gemm_stage_bytes() { return NA * GEMM_BM * GEMM_BK * 2 + BN * GEMM_BK * 2; }
@@ -53,17 +62,15 @@ __host__ __device__ constexpr int gemm_stages() {
     return s > 8 ? 8 : s;
 }
 
-constexpr int GEMM_MAX_N = 576;   // scale/shift staged in smem for the whole output width
-
 template <int BN, int NA>
 __host__ __device__ constexpr int gemm_smem_bytes() {
     return gemm_stages<BN, NA>() * gemm_stage_bytes<BN, NA>() + 1024 /*align*/ + 256 /*barriers*/ + 2 * GEMM_MAX_N * 4 +
            8 * 4096 /*epilogue staging, 4 KB per epilogue warp*/;
 }
 
-// Persistent: CTA c processes tiles c, c+gridDim.x, …; tile = (split, n_tile, m_tile), m fastest.
-// Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
-template <int BN, int NA>
+// Persistent: CTA c processes work items c, c+gridDim.x, …; item = (split, n_tile, m_group), m fastest.
+// Two TMEM accumulator stages let the epilogue of item i overlap the MMAs of item i+1.
+template <int BN, int NA, int EPI, int ACT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
             const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -71,7 +78,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
     constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     constexpr int B_BYTES = BN * GEMM_BK * 2;
     constexpr int STAGE_BYTES = gemm_stage_bytes<BN, NA>();
-    constexpr int ACC_COLS = gemm_tmem_cols<BN>();
+    constexpr int MT = gemm_mt<BN>();
+    constexpr int ACC_COLS = gemm_acc_cols<BN>();
     constexpr int TMEM_COLS = 2 * ACC_COLS;
     static_assert(BN % 32 == 0 && BN >= 32 && BN <= 256, "UMMA N / epilogue chunking");
     static_assert(B_BYTES % 1024 == 0, "B stage must keep 1024-byte alignment for the 128B swizzle");
@@ -91,10 +99,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+    const int groups_m = (tiles_m + MT - 1) / MT;
     const int tiles_n = p.N / BN;
     const int total_kb = p.K / GEMM_BK;
     const int nsplit = (total_kb + p.kblocks_per_split - 1) / p.kblocks_per_split;
-    const int total_tiles = tiles_m * tiles_n * nsplit;
+    const int total_items = groups_m * tiles_n * nsplit;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA_hi);
@@ -105,9 +114,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
-    for (int i = threadIdx.x; i < p.N; i += GEMM_THREADS) {
-        s_scale[i] = p.scale ? p.scale[i] : 1.f;
-        s_shift[i] = p.shift ? p.shift[i] : 0.f;
+    if (EPI != EPI_PARTIAL) {
+        for (int i = threadIdx.x; i < p.N; i += GEMM_THREADS) {
+            s_scale[i] = p.scale ? p.scale[i] : 1.f;
+            s_shift[i] = p.shift ? p.shift[i] : 0.f;
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -118,18 +129,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int mt = tile % tiles_m, nt = (tile / tiles_m) % tiles_n, sp = tile / (tiles_m * tiles_n);
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+                const int mg = item % groups_m, nt = (item / groups_m) % tiles_n, sp = item / (groups_m * tiles_n);
                 const int kb0 = sp * p.kblocks_per_split, kb1 = min(total_kb, kb0 + p.kblocks_per_split);
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1);
-                    uint8_t* st = smem + s * STAGE_BYTES;
-                    mbar_expect_tx(&full_bar[s], STAGE_BYTES);
-                    tma_load_2d_hint(st, &tmA_hi, &full_bar[s], kb * GEMM_BK, mt * GEMM_BM, kEvictFirst);
-                    if (NA == 2) tma_load_2d_hint(st + A_BYTES, &tmA_lo, &full_bar[s], kb * GEMM_BK, mt * GEMM_BM, kEvictFirst);
-                    tma_load_2d_hint(st + NA * A_BYTES, &tmB, &full_bar[s], kb * GEMM_BK, nt * BN, kEvictLast);
+                for (int j = 0; j < MT; ++j) {
+                    const int mt = mg * MT + j;
+                    if (mt >= tiles_m) break;
+                    for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                        const int s = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        uint8_t* st = smem + s * STAGE_BYTES;
+                        mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                        tma_load_2d_hint(st, &tmA_hi, &full_bar[s], kb * GEMM_BK, mt * GEMM_BM, kEvictFirst);
+                        if (NA == 2) tma_load_2d_hint(st + A_BYTES, &tmA_lo, &full_bar[s], kb * GEMM_BK, mt * GEMM_BM, kEvictFirst);
+                        tma_load_2d_hint(st + NA * A_BYTES, &tmB, &full_bar[s], kb * GEMM_BK, nt * BN, kEvictLast);
+                    }
                 }
             }
         }
@@ -137,111 +152,126 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0, 0);
-            uint32_t it = 0, lt = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-                const int sp = tile / (tiles_m * tiles_n);
+            uint32_t it = 0, li = 0;
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
+                const int mg = item % groups_m, sp = item / (groups_m * tiles_n);
                 const int kb0 = sp * p.kblocks_per_split, kb1 = min(total_kb, kb0 + p.kblocks_per_split);
-                const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
-                mbar_wait(&tmem_empty_bar[as], aph ^ 1);     // epilogue has drained this accumulator
+                const uint32_t as = li & 1, aph = (li >> 1) & 1;
+                mbar_wait(&tmem_empty_bar[as], aph ^ 1);     // epilogue has drained this accumulator stage
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * ACC_COLS;
-                for (int kb = kb0; kb < kb1; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&full_bar[s], ph);
-                    tc_fence_after();
-                    const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES);
-                    const uint32_t b_ad = a_hi + NA * A_BYTES;
+                for (int j = 0; j < MT; ++j) {
+                    if (mg * MT + j >= tiles_m) break;
+                    const uint32_t d_tmem = tmem_base + as * ACC_COLS + j * BN;
+                    for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                        const int s = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait(&full_bar[s], ph);
+                        tc_fence_after();
+                        const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES);
+                        const uint32_t b_ad = a_hi + NA * A_BYTES;
 #pragma unroll
-                    for (int k = 0; k < GEMM_BK / 16; ++k) {
-                        const uint64_t bd = make_desc_k_sw128(b_ad + k * 32);
-                        umma_bf16(d_tmem, make_desc_k_sw128(a_hi + k * 32), bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-                        if (NA == 2) umma_bf16(d_tmem, make_desc_k_sw128(a_hi + A_BYTES + k * 32), bd, idesc, 1u);
+                        for (int k = 0; k < GEMM_BK / 16; ++k) {
+                            const uint64_t bd = make_desc_k_sw128(b_ad + k * 32);
+                            umma_bf16(d_tmem, make_desc_k_sw128(a_hi + k * 32), bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                            if (NA == 2) umma_bf16(d_tmem, make_desc_k_sw128(a_hi + A_BYTES + k * 32), bd, idesc, 1u);
+                        }
+                        umma_commit(&empty_bar[s]);          // frees the smem stage when these MMAs have read it
                     }
-                    umma_commit(&empty_bar[s]);          // frees the smem stage when these MMAs have read it
                 }
-                umma_commit(&tmem_full_bar[as]);         // accumulator complete
+                umma_commit(&tmem_full_bar[as]);             // accumulator stage complete
             }
         }
     } else {
-        // ===== epilogue: group g = (warp-2)/4 drains accumulator stage g (local tiles lt ≡ g mod 2), so two
-        // tiles' epilogues are in flight per CTA; TMEM lane quarter = warp % 4 =====
+        // ===== epilogue: group g = (warp-2)/4 drains accumulator stage g (items li ≡ g mod 2), so two
+        // items' epilogues are in flight per CTA; TMEM lane quarter = warp % 4 =====
         const int q = warp & 3;
         const uint32_t grp = (uint32_t)(warp - 2) >> 2;
-        uint32_t lt = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
-            if ((lt & 1) != grp) continue;
-            const int mt = tile % tiles_m, nt = (tile / tiles_m) % tiles_n, sp = tile / (tiles_m * tiles_n);
-            const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
-            mbar_wait(&tmem_full_bar[as], aph);
+        uint8_t* wbuf = s_stage + (warp - 2) * 4096;
+        // staged-store geometry is per-lane constant: 8 lanes per row, lane&7 = 16-byte chunk of the 128-byte slice
+        const int sr = lane >> 3, sc = lane & 7;
+        uint32_t li = 0;
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
+            if ((li & 1) != grp) continue;
+            const int mg = item % groups_m, nt = (item / groups_m) % tiles_n, sp = item / (groups_m * tiles_n);
+            const uint32_t aph = (li >> 1) & 1;
+            mbar_wait(&tmem_full_bar[grp], aph);
             tc_fence_after();
-            const uint32_t t_addr = tmem_base + as * ACC_COLS + ((uint32_t)(q * 32) << 16);
+            const uint32_t t_addr = tmem_base + grp * ACC_COLS + ((uint32_t)(q * 32) << 16);
+            const int mt_cnt = min(MT, tiles_m - mg * MT);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(t_addr + (uint32_t)c0, r);
-                tmem_ld_wait();
-                if (c0 + 32 >= BN) {                     // last chunk read: hand the accumulator back
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
-                }
-                const int nb = nt * BN + c0;
-                uint32_t w[32];
-                if (p.epi == EPI_PARTIAL) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) w[j] = r[j];
-                } else {
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 sc = *reinterpret_cast<const float4*>(s_scale + nb + j);
-                        const float4 sh = *reinterpret_cast<const float4*>(s_shift + nb + j);
-                        v[j] = fmaf(__uint_as_float(r[j]), sc.x, sh.x);
-                        v[j + 1] = fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y);
-                        v[j + 2] = fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z);
-                        v[j + 3] = fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w);
+            for (int j = 0; j < mt_cnt; ++j) {
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(t_addr + (uint32_t)(j * BN + c0), r);
+                    tmem_ld_wait();
+                    if (j == mt_cnt - 1 && c0 + 32 >= BN) {   // last read of this stage: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tmem_empty_bar[grp]);
                     }
-                    if (p.act == GACT_LEAKY) {
+                    const int nb = nt * BN + c0;
+                    uint32_t w[32];
+                    if (EPI == EPI_PARTIAL) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.2f * v[j]);     // LeakyReLU(0.2): max(x, 0.2x)
-                    } else if (p.act == GACT_RELU) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-                    }
-                    if (p.epi == EPI_F32) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v[j]);
+                        for (int i = 0; i < 32; ++i) w[i] = r[i];
                     } else {
-                        // row slice = [hi 64 B | lo 64 B]
+                        float v[32];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], w[j], w[16 + j]);
-                    }
-                }
-                // park the row slice in the warp's swizzled staging tile, then store with 8 lanes per row
-                uint8_t* wbuf = s_stage + (warp - 2) * 4096;
-                __syncwarp();
-                stage_write_row(wbuf, lane, w);
-                __syncwarp();
-                const int row0 = mt * GEMM_BM + q * 32;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    int rr, cc;
-                    uint4 d = stage_read(wbuf, lane, i, rr, cc);
-                    const int grow = row0 + rr;
-                    if (grow >= p.M) continue;
-                    if (p.epi == EPI_SPLIT) {
-                        __nv_bfloat16* plane = cc < 4 ? p.out_hi : p.out_lo;
-                        *reinterpret_cast<uint4*>(plane + (size_t)grow * p.ldc + nb + (cc & 3) * 8) = d;
-                    } else {
-                        const size_t off = (size_t)grow * p.ldc + nb + cc * 4;
-                        float* dst = p.out_f32 + (p.epi == EPI_PARTIAL ? (size_t)sp * p.partial_stride : 0) + off;
-                        if (p.epi == EPI_F32 && p.resid) {
-                            const float4 t = *reinterpret_cast<const float4*>(p.resid + off);
-                            d.x = __float_as_uint(__uint_as_float(d.x) + t.x); d.y = __float_as_uint(__uint_as_float(d.y) + t.y);
-                            d.z = __float_as_uint(__uint_as_float(d.z) + t.z); d.w = __float_as_uint(__uint_as_float(d.w) + t.w);
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 sc4 = *reinterpret_cast<const float4*>(s_scale + nb + i);
+                            const float4 sh4 = *reinterpret_cast<const float4*>(s_shift + nb + i);
+                            v[i] = fmaf(__uint_as_float(r[i]), sc4.x, sh4.x);
+                            v[i + 1] = fmaf(__uint_as_float(r[i + 1]), sc4.y, sh4.y);
+                            v[i + 2] = fmaf(__uint_as_float(r[i + 2]), sc4.z, sh4.z);
+                            v[i + 3] = fmaf(__uint_as_float(r[i + 3]), sc4.w, sh4.w);
                         }
-                        *reinterpret_cast<uint4*>(dst) = d;
+                        if (ACT == GACT_LEAKY) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.2f * v[i]);     // LeakyReLU(0.2) = max(x, 0.2x)
+                        } else if (ACT == GACT_RELU) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.f);
+                        }
+                        if (EPI == EPI_F32) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) w[i] = __float_as_uint(v[i]);
+                        } else {                                 // row slice = [hi 64 B | lo 64 B]
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) split_bf16x2(v[2 * i], v[2 * i + 1], w[i], w[16 + i]);
+                        }
+                    }
+                    // park the row slice in the warp's swizzled staging tile, then store with 8 lanes per row
+                    __syncwarp();
+                    stage_write_row(wbuf, lane, w);
+                    __syncwarp();
+                    const int row0 = (mg * MT + j) * GEMM_BM + q * 32 + sr;    // + 4·i per store instruction
+                    const int rows_left = p.M - row0;                          // row 4i valid ⇔ 4i < rows_left
+                    if (EPI == EPI_SPLIT) {
+                        __nv_bfloat16* dst = (sc < 4 ? p.out_hi : p.out_lo) + (size_t)row0 * p.ldc + nb + (sc & 3) * 8;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rr = 4 * i + sr;
+                            const uint4 d = *reinterpret_cast<const uint4*>(wbuf + rr * 128 + ((sc ^ (rr & 7)) << 4));
+                            if (4 * i < rows_left) *reinterpret_cast<uint4*>(dst + (size_t)(4 * i) * p.ldc) = d;
+                        }
+                    } else {
+                        const size_t off = (size_t)row0 * p.ldc + nb + sc * 4;
+                        float* dst = p.out_f32 + (EPI == EPI_PARTIAL ? (size_t)sp * p.partial_stride : 0) + off;
+                        const float* rs = (EPI == EPI_F32 && p.resid) ? p.resid + off : nullptr;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int rr = 4 * i + sr;
+                            uint4 d = *reinterpret_cast<const uint4*>(wbuf + rr * 128 + ((sc ^ (rr & 7)) << 4));
+                            if (4 * i < rows_left) {
+                                if (rs) {
+                                    const float4 t = *reinterpret_cast<const float4*>(rs + (size_t)(4 * i) * p.ldc);
+                                    d.x = __float_as_uint(__uint_as_float(d.x) + t.x); d.y = __float_as_uint(__uint_as_float(d.y) + t.y);
+                                    d.z = __float_as_uint(__uint_as_float(d.z) + t.z); d.w = __float_as_uint(__uint_as_float(d.w) + t.w);
+                                }
+                                *reinterpret_cast<uint4*>(dst + (size_t)(4 * i) * p.ldc) = d;
+                            }
+                        }
                     }
                 }
             }

@@ -51,10 +51,11 @@ inline int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint6
 
 // A: [M, K] bf16 planes (lo may be null ⇒ single plane), pitch lda; B: [N, K] bf16, pitch ldb.
 // k_cols = columns that really exist in memory (≤ K); TMA zero-fills [k_cols, K) — used for conv0's K = 48.
-template <int BN, int NA>
+template <int BN, int NA, int EPI, int ACT>
 int launch_gemm_t(const void* A_hi, const void* A_lo, int lda, const void* B, int ldb, GemmParams p, int splits,
                   int k_cols, cudaStream_t st) {
-    if (p.K % GEMM_BK || p.N % BN || p.M < 1 || splits < 1 || k_cols > p.K || k_cols < 1) return PMG_ERR_BAD_SHAPE;
+    if (p.K % GEMM_BK || p.N % BN || p.M < 1 || splits < 1 || k_cols > p.K || k_cols < 1 || p.N > GEMM_MAX_N)
+        return PMG_ERR_BAD_SHAPE;
     CUtensorMap ta_hi, ta_lo, tb;
     int rc;
     if ((rc = make_tmap_bf16(&ta_hi, A_hi, p.M, k_cols, lda, GEMM_BM))) return rc;
@@ -66,13 +67,13 @@ int launch_gemm_t(const void* A_hi, const void* A_lo, int lda, const void* B, in
     constexpr int smem = gemm_smem_bytes<BN, NA>();
     static bool attr_set = false;   // idempotent; racing threads set the same value
     if (!attr_set) {
-        PMG_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "gemm smem attr");
+        PMG_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, NA, EPI, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "gemm smem attr");
         attr_set = true;
     }
-    if (p.N > GEMM_MAX_N) return PMG_ERR_BAD_SHAPE;
-    const int total_tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * eff_splits * (p.N / BN);
-    const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-    gemm_kernel<BN, NA><<<grid, GEMM_THREADS, smem, st>>>(ta_hi, ta_lo, tb, p);
+    const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+    const int items = ((tiles_m + gemm_mt<BN>() - 1) / gemm_mt<BN>()) * eff_splits * (p.N / BN);
+    const int grid = items < num_sms() ? items : num_sms();
+    gemm_kernel<BN, NA, EPI, ACT><<<grid, GEMM_THREADS, smem, st>>>(ta_hi, ta_lo, tb, p);
     PMG_LAUNCH_OK("tc gemm");
     return PMG_OK;
 }
@@ -82,21 +83,6 @@ inline int effective_splits(int K, int splits) {
     const int total_kb = K / GEMM_BK;
     const int per = (total_kb + splits - 1) / splits;
     return (total_kb + per - 1) / per;
-}
-
-inline int launch_gemm(int BN, int NA, const void* A_hi, const void* A_lo, int lda, const void* B, int ldb,
-                       const GemmParams& p, int splits, cudaStream_t st, int k_cols = 0) {
-    if (k_cols <= 0) k_cols = p.K;
-#define PMG_GEMM_CASE(bn)                                                                                 \
-    if (BN == bn) return NA == 2 ? launch_gemm_t<bn, 2>(A_hi, A_lo, lda, B, ldb, p, splits, k_cols, st)   \
-                                 : launch_gemm_t<bn, 1>(A_hi, A_lo, lda, B, ldb, p, splits, k_cols, st);
-    PMG_GEMM_CASE(32)
-    PMG_GEMM_CASE(64)
-    PMG_GEMM_CASE(96)
-    PMG_GEMM_CASE(128)
-    PMG_GEMM_CASE(192)
-#undef PMG_GEMM_CASE
-    return PMG_ERR_UNSUPPORTED;
 }
 
 }  // namespace tc
