@@ -29,7 +29,7 @@ using bf16 = __nv_bfloat16;
 // layout of the fast section of the packed weights (bf16, [N][K] K-contiguous = UMMA "K-major" B operand)
 // ------------------------------------------------------------------------------------------------
 struct FastW {
-    size_t w0, w1, w2, w3, wt;          // conv0 [32][48], conv1 [64][512] (K = (sy,sx,c)), conv2 [128][64], chan [96][128], token [192][9216]
+    size_t w0, w1, w2, w3, wt;          // conv0 [32][64] (K 48 zero-padded to 64), conv1 [64][512] (K = (sy,sx,c)), conv2 [128][64], chan [96][128], token [192][9216]
     size_t win[8], wo[8], wf1[8], wf2[8];
     size_t total;
 };
@@ -38,7 +38,7 @@ static FastW fast_w(const Plan& p) {
     FastW f{};
     size_t o = 0;
     auto take = [&](size_t n) { size_t r = o; o = align256(o + n * sizeof(bf16)); return r; };
-    f.w0 = take(32 * 48); f.w1 = take(64 * 512); f.w2 = take(128 * 64); f.w3 = take(96 * 128);
+    f.w0 = take(32 * 64); f.w1 = take(64 * 512); f.w2 = take(128 * 64); f.w3 = take(96 * 128);
     f.wt = take((size_t)192 * 9216);
     for (int l = 0; l < p.nl && l < 8; ++l) {
         f.win[l] = take(576 * 192); f.wo[l] = take(192 * 192); f.wf1[l] = take(384 * 192); f.wf2[l] = take(192 * 384);
@@ -72,6 +72,14 @@ __global__ void pack_w1_kernel(const float* __restrict__ in, bf16* __restrict__ 
     out[i] = __float2bfloat16_rn(in[(co * 32 + c) * 16 + s]);
 }
 
+// conv0 weight (32, 3, 4, 4) → [32][64]: k = c*16+ky*4+kx for k < 48, zero for the 16 pad columns
+__global__ void pack_w0_kernel(const float* __restrict__ in, bf16* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 32 * 64) return;
+    const int co = i / 64, k = i % 64;
+    out[i] = __float2bfloat16_rn(k < 48 ? in[co * 48 + k] : 0.f);
+}
+
 int pack_fast(const Plan& p, const PackedLayout& L, const float* const* prm, char* packed, cudaStream_t st) {
     if (!is_committed(p)) return PMG_OK;
     const FastW f = fast_w(p);
@@ -81,7 +89,7 @@ int pack_fast(const Plan& p, const PackedLayout& L, const float* const* prm, cha
         size_t g = (n + 255) / 256;
         cvt_bf16_kernel<<<(int)(g > 2048 ? 2048 : g), 256, 0, st>>>(src, Bp(off), n);
     };
-    cvt(prm[0], f.w0, 32 * 48);                                   // (32,3,4,4) == [32][c*16+ky*4+kx]
+    pack_w0_kernel<<<8, 256, 0, st>>>(prm[0], Bp(f.w0));           // (32,3,4,4) == [32][c*16+ky*4+kx], K padded to 64
     pack_w1_kernel<<<(64 * 512 + 255) / 256, 256, 0, st>>>(prm[5], Bp(f.w1));
     cvt(prm[10], f.w2, 128 * 64);
     cvt(prm[15], f.w3, 96 * 128);
@@ -99,7 +107,7 @@ int pack_fast(const Plan& p, const PackedLayout& L, const float* const* prm, cha
 }
 
 // ------------------------------------------------------------------------------------------------
-// im2col for conv0: x (B,3,224,224) NCHW → A0 [B·3136][48] bf16, row r = (b·196 + py·14 + px)·16 + sy·4 + sx,
+// im2col for conv0: x (B,3,224,224) NCHW → A0 [B·3136][64] bf16 (cols 48..63 zero), row r = (b·196 + py·14 + px)·16 + sy·4 + sx,
 // col = c·16 + ky·4 + kx  (pixel y = 16py+4sy+ky, x = 16px+4sx+kx).  One thread = one 16-byte chunk
 // (8 bf16 = two kernel rows ky, ky+1 of one channel), so a warp writes 512 contiguous bytes.
 // fp32 input is split into hi/lo planes; bf16 input is copied.
@@ -107,10 +115,15 @@ int pack_fast(const Plan& p, const PackedLayout& L, const float* const* prm, cha
 template <bool F32IN>
 __global__ void __launch_bounds__(256) im2col0_kernel(const void* __restrict__ x, bf16* __restrict__ a_hi,
                                                       bf16* __restrict__ a_lo, int B) {
-    const size_t total = (size_t)B * 3136 * 6;
+    const size_t total = (size_t)B * 3136 * 8;
     for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-        const size_t r = t / 6;
-        const int j = (int)(t % 6);
+        const size_t r = t >> 3;
+        const int j = (int)(t & 7);
+        if (j >= 6) {                                   // K padding 48 → 64: TMA rows stay 128-byte, fully in bounds
+            *reinterpret_cast<uint4*>(a_hi + r * 64 + j * 8) = make_uint4(0, 0, 0, 0);
+            if (F32IN) *reinterpret_cast<uint4*>(a_lo + r * 64 + j * 8) = make_uint4(0, 0, 0, 0);
+            continue;
+        }
         const int s = (int)(r & 15);
         const size_t bp = r >> 4;
         const int pix = (int)(bp % 196);
@@ -125,14 +138,14 @@ __global__ void __launch_bounds__(256) im2col0_kernel(const void* __restrict__ x
             const float4 r1 = *reinterpret_cast<const float4*>(xf + src + 224);
             tc::split_bf16x2(r0.x, r0.y, hi[0], lo[0]); tc::split_bf16x2(r0.z, r0.w, hi[1], lo[1]);
             tc::split_bf16x2(r1.x, r1.y, hi[2], lo[2]); tc::split_bf16x2(r1.z, r1.w, hi[3], lo[3]);
-            *reinterpret_cast<uint4*>(a_lo + r * 48 + j * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4*>(a_lo + r * 64 + j * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         } else {
             const bf16* xb = reinterpret_cast<const bf16*>(x);
             const uint2 r0 = *reinterpret_cast<const uint2*>(xb + src);
             const uint2 r1 = *reinterpret_cast<const uint2*>(xb + src + 224);
             hi[0] = r0.x; hi[1] = r0.y; hi[2] = r1.x; hi[3] = r1.y;
         }
-        *reinterpret_cast<uint4*>(a_hi + r * 48 + j * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(a_hi + r * 64 + j * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     }
 }
 
@@ -269,7 +282,7 @@ static FastWs fast_ws(int B) {
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = align256(o + bytes); return r; };
     const size_t P = (size_t)B * 196, T = (size_t)B * 9;
-    w.a0_hi = take(P * 16 * 48 * 2); w.a0_lo = take(P * 16 * 48 * 2);
+    w.a0_hi = take(P * 16 * 64 * 2); w.a0_lo = take(P * 16 * 64 * 2);
     w.act0_hi = take(P * 512 * 2); w.act0_lo = take(P * 512 * 2);
     w.act1_hi = take(P * 64 * 2); w.act1_lo = take(P * 64 * 2);
     w.act2_hi = take(P * 128 * 2); w.act2_lo = take(P * 128 * 2);
@@ -314,20 +327,20 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
     PMG_MARK(tm, "start");
     // conv0 (:115-117) = im2col + GEMM [B·3136,48]×[48,32], BN+LeakyReLU epilogue → act0 planes == conv1's A
     {
-        const size_t chunks = (size_t)B * 3136 * 6;
+        const size_t chunks = (size_t)B * 3136 * 8;
         const int grid = (int)((chunks + 255) / 256 > 148 * 16 ? 148 * 16 : (chunks + 255) / 256);
         if (x_dtype == PMG_F32) im2col0_kernel<true><<<grid, 256, 0, st>>>(x, Hb(w.a0_hi), Hb(w.a0_lo), B);
         else im2col0_kernel<false><<<grid, 256, 0, st>>>(x, Hb(w.a0_hi), nullptr, B);
         PMG_LAUNCH_OK("im2col0");
         PMG_MARK(tm, "im2col0");
         if (x_dtype == PMG_F32)
-            rc = gemm<32, 2, tc::EPI_SPLIT, tc::GACT_LEAKY>(Hb(w.a0_hi), Hb(w.a0_lo), 48, Wb(f.w0), P * 16, 32, 64, 32, nullptr,
+            rc = gemm<32, 2, tc::EPI_SPLIT, tc::GACT_LEAKY>(Hb(w.a0_hi), Hb(w.a0_lo), 64, Wb(f.w0), P * 16, 32, 64, 32, nullptr,
                                                             Hb(w.act0_hi), Hb(w.act0_lo), Pf(L.conv_scale[0]),
-                                                            Pf(L.conv_shift[0]), nullptr, 1, 0, st, 48);
+                                                            Pf(L.conv_shift[0]), nullptr, 1, 0, st);
         else
-            rc = gemm<32, 1, tc::EPI_SPLIT, tc::GACT_LEAKY>(Hb(w.a0_hi), nullptr, 48, Wb(f.w0), P * 16, 32, 64, 32, nullptr,
+            rc = gemm<32, 1, tc::EPI_SPLIT, tc::GACT_LEAKY>(Hb(w.a0_hi), nullptr, 64, Wb(f.w0), P * 16, 32, 64, 32, nullptr,
                                                             Hb(w.act0_hi), Hb(w.act0_lo), Pf(L.conv_scale[0]),
-                                                            Pf(L.conv_shift[0]), nullptr, 1, 0, st, 48);
+                                                            Pf(L.conv_shift[0]), nullptr, 1, 0, st);
         if (rc) return rc;
         PMG_MARK(tm, "conv0");
     }
