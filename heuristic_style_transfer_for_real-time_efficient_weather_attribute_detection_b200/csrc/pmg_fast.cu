@@ -31,6 +31,7 @@ using bf16 = __nv_bfloat16;
 struct FastW {
     size_t w0, w1, w2, w3, wt;          // conv0 [32][64] (K 48 zero-padded to 64), conv1 [64][512] (K = (sy,sx,c)), conv2 [128][64], chan [96][128], token [192][9216]
     size_t win[8], wo[8], wf1[8], wf2[8];
+    size_t wq;                           // [64][192]: rows 0..ntask-1 task queries, then the ncls_total classifier rows, zero pad
     size_t total;
 };
 
@@ -43,6 +44,7 @@ static FastW fast_w(const Plan& p) {
     for (int l = 0; l < p.nl && l < 8; ++l) {
         f.win[l] = take(576 * 192); f.wo[l] = take(192 * 192); f.wf1[l] = take(384 * 192); f.wf2[l] = take(192 * 384);
     }
+    f.wq = take(64 * 192);
     f.total = o;
     return f;
 }
@@ -50,7 +52,7 @@ static FastW fast_w(const Plan& p) {
 static bool is_committed(const Plan& p) {
     return p.ok && p.n_layers == 3 && p.layer[0].cin == 3 && p.layer[0].cout == 32 && p.layer[0].k == 4 &&
            p.layer[1].cout == 64 && p.layer[1].k == 4 && p.layer[2].cout == 128 && p.layer[2].k == 1 && p.Cr == 96 &&
-           p.d == 192 && p.nh == 4 && p.pdiv == 3 && p.nl <= 8;
+           p.d == 192 && p.nh == 4 && p.pdiv == 3 && p.nl <= 8 && p.ntask + p.ncls_total <= 64;
 }
 
 size_t fast_section_bytes(const Plan& p) { return is_committed(p) ? fast_w(p).total : 0; }
@@ -101,6 +103,15 @@ int pack_fast(const Plan& p, const PackedLayout& L, const float* const* prm, cha
         cvt(prm[i + 4], f.wf1[l], 384 * 192);
         cvt(prm[i + 6], f.wf2[l], 192 * 384);
         i += 12;
+    }
+    // heads as one GEMM operand: [queries | classifier rows] (models_PMG.py:45,153-155)
+    PMG_CUDA_OK(cudaMemsetAsync(Bp(f.wq), 0, 64 * 192 * sizeof(bf16), st), "wq memset");
+    for (int t = 0; t < p.ntask; ++t) cvt(prm[i + t], f.wq + (size_t)t * 192 * sizeof(bf16), 192);
+    i += p.ntask;
+    for (int t = 0; t < p.ntask; ++t) {
+        const int n = p.cls_off[t + 1] - p.cls_off[t];
+        cvt(prm[i], f.wq + (size_t)(p.ntask + p.cls_off[t]) * 192 * sizeof(bf16), (size_t)n * 192);
+        i += 2;
     }
     PMG_LAUNCH_OK("pack_fast");
     return PMG_OK;
@@ -181,6 +192,17 @@ __global__ void __launch_bounds__(128) tok_ln_kernel(const float* __restrict__ p
         }
     }
     if (!do_ln) return;
+    if (do_ln == 2) {                       // raw residual stream as hi/lo planes (operand of the heads GEMM)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int c = 2 * lane + 64 * j;
+            uint32_t hi, lo;
+            tc::split_bf16x2(v[2 * j], v[2 * j + 1], hi, lo);
+            *reinterpret_cast<uint32_t*>(h_hi + (size_t)row * 192 + c) = hi;
+            *reinterpret_cast<uint32_t*>(h_lo + (size_t)row * 192 + c) = lo;
+        }
+        return;
+    }
     float s = v[0] + v[1] + v[2] + v[3] + v[4] + v[5];
 #pragma unroll
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -261,11 +283,42 @@ __global__ void __launch_bounds__(128) attn9_kernel(const float* __restrict__ qk
 }
 
 // ------------------------------------------------------------------------------------------------
+// Task pooling + heads, finishing step (models_PMG.py:47-57,198).  The heads GEMM produced, per token n,
+//   sc[n][t]          = tok_n · q_t                 (t < ntask)         — the pooling scores
+//   sc[n][ntask + c]  = W_c · tok_n                 (c < ncls_total)    — every class projected per token
+// and  logits[c] = Σ_n softmax_n(sc[:,t(c)]) · sc[n][ntask+c] + b_c  because the head is linear in the pooled token.
+// One thread per (image, class); 9 tokens.
+// ------------------------------------------------------------------------------------------------
+struct FinishArgs {
+    const float* sc; const float* bias; float* logits;
+    int B, ntask, ncls_total;
+    unsigned char task_of[64];
+};
+
+__global__ void __launch_bounds__(256) pool_finish_kernel(const FinishArgs a) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.B * a.ncls_total) return;
+    const int b = idx / a.ncls_total, c = idx % a.ncls_total, t = a.task_of[c];
+    const float* s = a.sc + (size_t)b * 9 * 64;
+    float sv[9], mx = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < 9; ++n) { sv[n] = s[n * 64 + t]; mx = fmaxf(mx, sv[n]); }
+    float den = 0.f, acc = 0.f;
+#pragma unroll
+    for (int n = 0; n < 9; ++n) {
+        const float e = expf(sv[n] - mx);
+        den += e;
+        acc = fmaf(e, s[n * 64 + a.ntask + c], acc);
+    }
+    a.logits[idx] = acc / den + a.bias[c];
+}
+
+// ------------------------------------------------------------------------------------------------
 // workspace
 // ------------------------------------------------------------------------------------------------
 struct FastWs {
     size_t a0_hi, a0_lo, act0_hi, act0_lo, act1_hi, act1_lo, act2_hi, act2_lo, chan, g_hi, g_lo, partial, tok,
-        h_hi, h_lo, qkv, ffh_hi, ffh_lo, total;
+        h_hi, h_lo, qkv, ffh_hi, ffh_lo, sc, total;
     int splits;
 };
 
@@ -294,13 +347,14 @@ static FastWs fast_ws(int B) {
     w.h_hi = take(T * 192 * 2); w.h_lo = take(T * 192 * 2);
     w.qkv = take(T * 576 * 4);
     w.ffh_hi = take(T * 384 * 2); w.ffh_lo = take(T * 384 * 2);
+    w.sc = take(T * 64 * 4);
     w.total = o;
     return w;
 }
 
 size_t fast_workspace_bytes(const Plan&, const Shape&, int B) { return fast_ws(B).total; }
 
-int fast_launch_count(const Plan& p, const Shape&, int) { return 5 + 1 + 1 + 1 + 6 * p.nl + (p.nl > 1 ? p.nl - 1 : 0) + 1; }
+int fast_launch_count(const Plan& p, const Shape&, int) { return 5 + 1 + 1 + 1 + 6 * p.nl + (p.nl > 1 ? p.nl - 1 : 0) + 3; }
 
 template <int BN, int NA, int EPI, int ACT>
 static int gemm(const void* a_hi, const void* a_lo, int lda, const void* b, int M, int N, int K, int ldc, float* out_f32,
@@ -418,9 +472,22 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
     }
     if (taps && taps->tokens_out)
         PMG_CUDA_OK(cudaMemcpyAsync(taps->tokens_out, Ff(w.tok), (size_t)T * 192 * 4, cudaMemcpyDeviceToDevice, st), "tap tok out");
-    rc = launch_pool_heads(p, L, packed, Ff(w.tok), B, 9, logits, st);
+    // task attention pooling + heads (:197-198): one [T,192]×[192,64] tensor-core GEMM + a finishing kernel
+    tok_ln_kernel<<<(T + 3) / 4, 128, 0, st>>>(nullptr, 0, 0, nullptr, Ff(w.tok), nullptr, nullptr, Hb(w.h_hi), Hb(w.h_lo), T, 2);
+    PMG_LAUNCH_OK("tok split");
+    if ((rc = gemm<64, 2, tc::EPI_F32, tc::GACT_NONE>(Hb(w.h_hi), Hb(w.h_lo), 192, Wb(f.wq), T, 64, 192, 64, Ff(w.sc), nullptr,
+                                                      nullptr, nullptr, nullptr, nullptr, 1, 0, st)))
+        return rc;
+    {
+        FinishArgs a;
+        a.sc = Ff(w.sc); a.bias = Pf(L.cls_b); a.logits = logits; a.B = B; a.ntask = p.ntask; a.ncls_total = p.ncls_total;
+        for (int t = 0; t < p.ntask; ++t)
+            for (int c = p.cls_off[t]; c < p.cls_off[t + 1]; ++c) a.task_of[c] = (unsigned char)t;
+        pool_finish_kernel<<<(B * p.ncls_total + 255) / 256, 256, 0, st>>>(a);
+        PMG_LAUNCH_OK("pool_finish");
+    }
     PMG_MARK(tm, "pool_heads");
-    return rc;
+    return PMG_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

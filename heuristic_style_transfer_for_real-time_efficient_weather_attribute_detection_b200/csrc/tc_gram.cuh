@@ -20,10 +20,10 @@
 
 namespace tc {
 
-constexpr int GRAM_THREADS = 224;     // warps 0-2 loaders, 3 MMA, 4-6 epilogue
+constexpr int GRAM_THREADS = 512;     // warps 0-2 loaders, 3 MMA, 4-15 epilogue: (lane quarter w%4 < 3) × (32-col chunk (w-4)/4)
 constexpr int GRAM_STAGES = 3;
 constexpr int GRAM_PLANE = 128 * 128; // bytes: 128 rows × 128 B (64 pixel slots, 32 used)
-constexpr int GRAM_SMEM = GRAM_STAGES * 2 * GRAM_PLANE + 1024 + 256 + 3 * 4096 /*epilogue staging*/;
+constexpr int GRAM_SMEM = GRAM_STAGES * 2 * GRAM_PLANE + 1024 + 256 + 12 * 4096 /*epilogue staging*/;
 
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram96_tc_kernel(const float* __restrict__ chan, __nv_bfloat16* __restrict__ g_hi, __nv_bfloat16* __restrict__ g_lo,
@@ -35,12 +35,12 @@ gram96_tc_kernel(const float* __restrict__ chan, __nv_bfloat16* __restrict__ g_h
     uint64_t* tmem_full_bar = empty_bar + GRAM_STAGES;   // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-    uint8_t* s_stage = smem + GRAM_STAGES * 2 * GRAM_PLANE + 256;             // 3 × 4 KB
+    uint8_t* s_stage = smem + GRAM_STAGES * 2 * GRAM_PLANE + 256;             // 12 × 4 KB
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < GRAM_STAGES; ++s) { mbar_init(&full_bar[s], 96); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 3); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 9); }
         fence_barrier_init();
     }
     if (warp == 3) tmem_alloc(tmem_slot, 256);
@@ -119,45 +119,42 @@ gram96_tc_kernel(const float* __restrict__ chan, __nv_bfloat16* __restrict__ g_h
             }
         }
     } else {
-        // ===== epilogue: warps 4,5,6 ↔ TMEM lane quarters 0,1,2 (rows 0..95) =====
+        // ===== epilogue: 9 warps, warp w ↔ TMEM lane quarter q = w%4 (rows 32q..32q+31, q < 3) and the
+        // 32-column chunk (w-4)/4; one warp per (quarter, chunk) keeps three times as many warps in flight =====
         const int q = warp & 3;
-        const int row = q * 32 + lane;
-        uint32_t it = 0;
-        for (int tok = blockIdx.x; tok < n_tokens; tok += gridDim.x, ++it) {
-            const uint32_t as = it & 1, aph = (it >> 1) & 1;
-            mbar_wait(&tmem_full_bar[as], aph);
-            tc_fence_after();
-            const uint32_t t_addr = tmem_base + as * 128 + ((uint32_t)(q * 32) << 16);
-            const size_t o = (size_t)tok * 9216 + (size_t)row * 96;
-#pragma unroll 1
-            for (int c0 = 0; c0 < 96; c0 += 32) {
+        if (q < 3) {
+            const int c0 = ((warp - 4) >> 2) * 32;
+            uint8_t* wbuf = s_stage + (warp - 4) * 4096;
+            const int sr = lane >> 3, sc = lane & 7;
+            uint32_t it = 0;
+            for (int tok = blockIdx.x; tok < n_tokens; tok += gridDim.x, ++it) {
+                const uint32_t as = it & 1, aph = (it >> 1) & 1;
+                mbar_wait(&tmem_full_bar[as], aph);
+                tc_fence_after();
                 uint32_t r[32];
-                tmem_ld_32x32b_x32(t_addr + (uint32_t)c0, r);
+                tmem_ld_32x32b_x32(tmem_base + as * 128 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
                 tmem_ld_wait();
-                if (c0 == 64) {
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
-                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
                 uint32_t w[32];
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
                     split_bf16x2(__uint_as_float(r[2 * j]) * 0.04f, __uint_as_float(r[2 * j + 1]) * 0.04f, w[j], w[16 + j]);
                 // row slice [hi 64 B | lo 64 B] → warp-private swizzled staging → 8 lanes per row, coalesced
-                uint8_t* wbuf = s_stage + q * 4096;
                 __syncwarp();
                 stage_write_row(wbuf, lane, w);
                 __syncwarp();
-                const size_t tbase = (size_t)tok * 9216 + (size_t)(q * 32) * 96 + c0;
+                const size_t tbase = (size_t)tok * 9216 + (size_t)(q * 32 + sr) * 96 + c0 + (sc & 3) * 8;
+                __nv_bfloat16* dst = (sc < 4 ? g_hi : g_lo) + tbase;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    int rr, cc;
-                    const uint4 d = stage_read(wbuf, lane, i, rr, cc);
-                    __nv_bfloat16* plane = cc < 4 ? g_hi : g_lo;
-                    *reinterpret_cast<uint4*>(plane + tbase + (size_t)rr * 96 + (cc & 3) * 8) = d;
+                    const int rr = 4 * i + sr;
+                    *reinterpret_cast<uint4*>(dst + (size_t)(4 * i) * 96) =
+                        *reinterpret_cast<const uint4*>(wbuf + rr * 128 + ((sc ^ (rr & 7)) << 4));
                 }
                 if (g_f32) {
-                    float4* df = reinterpret_cast<float4*>(g_f32 + o + c0);
+                    float4* df = reinterpret_cast<float4*>(g_f32 + (size_t)tok * 9216 + (size_t)(q * 32 + lane) * 96 + c0);
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         df[j] = make_float4(__uint_as_float(r[4 * j]) * 0.04f, __uint_as_float(r[4 * j + 1]) * 0.04f,
