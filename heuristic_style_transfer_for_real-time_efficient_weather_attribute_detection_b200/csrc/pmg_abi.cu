@@ -105,7 +105,7 @@ int pmg_forward_launch_count(const pmg_config* cfg, int B, int H, int W, unsigne
     if (!p.ok || B < 1) return -1;
     const Shape s = make_shape(p, H, W);
     if (!s.ok) return -1;
-    return use_fast(p, s, flags) ? fast_launch_count(p, s, B) : generic_launch_count(p);
+    return use_fast(p, s, flags) ? fast_launch_count(p, s, B, flags) : generic_launch_count(p);
 }
 
 static int forward_impl(const pmg_config* cfg, const void* packed, const void* x, int x_dtype, int B, int H, int W,
@@ -127,7 +127,7 @@ static int forward_impl(const pmg_config* cfg, const void* packed, const void* x
     if (workspace_bytes < need) return PMG_ERR_WORKSPACE;
     if (fast)
         return fast_forward(p, s, L, reinterpret_cast<const char*>(packed), x, x_dtype, B, logits, gram, taps,
-                            reinterpret_cast<char*>(workspace), st, tm);
+                            reinterpret_cast<char*>(workspace), st, tm, flags);
     return generic_forward(p, s, L, reinterpret_cast<const char*>(packed), x, x_dtype, B, logits, gram, taps,
                            reinterpret_cast<char*>(workspace), st, tm);
 }

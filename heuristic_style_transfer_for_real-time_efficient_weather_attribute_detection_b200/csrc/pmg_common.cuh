@@ -174,8 +174,8 @@ bool fast_supported(const Plan& p, const Shape& s);
 size_t fast_workspace_bytes(const Plan& p, const Shape& s, int B);
 int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const char* packed, const void* x,
                  int x_dtype, int B, float* logits, float* gram, const pmg_taps* taps, char* ws,
-                 cudaStream_t st, StageTimer* tm);
-int fast_launch_count(const Plan& p, const Shape& s, int B);
+                 cudaStream_t st, StageTimer* tm, unsigned flags);
+int fast_launch_count(const Plan& p, const Shape& s, int B, unsigned flags);
 int pack_fast(const Plan& p, const PackedLayout& L, const float* const* prm, char* packed, cudaStream_t st);
 
 }  // namespace pmg

@@ -17,6 +17,7 @@
 #include "pmg_common.cuh"
 #include "tc_host.cuh"
 #include "tc_gram.cuh"
+#include "tc_front.cuh"
 
 namespace pmg {
 
@@ -31,6 +32,7 @@ using bf16 = __nv_bfloat16;
 struct FastW {
     size_t w0, w1, w2, w3, wt;          // conv0 [32][64] (K 48 zero-padded to 64), conv1 [64][512] (K = (sy,sx,c)), conv2 [128][64], chan [96][128], token [192][9216]
     size_t win[8], wo[8], wf1[8], wf2[8];
+    size_t w0x, w1x;                     // fused front end: block-sparse conv0 [128][192], conv1 as (sy,kb) blocks [512][64]
     size_t wq;                           // [64][192]: rows 0..ntask-1 task queries, then the ncls_total classifier rows, zero pad
     size_t total;
 };
@@ -45,6 +47,7 @@ static FastW fast_w(const Plan& p) {
         f.win[l] = take(576 * 192); f.wo[l] = take(192 * 192); f.wf1[l] = take(384 * 192); f.wf2[l] = take(192 * 384);
     }
     f.wq = take(64 * 192);
+    f.w0x = take(128 * 192); f.w1x = take(512 * 64);
     f.total = o;
     return f;
 }
@@ -82,6 +85,23 @@ __global__ void pack_w0_kernel(const float* __restrict__ in, bf16* __restrict__ 
     out[i] = __float2bfloat16_rn(k < 48 ? in[co * 48 + k] : 0.f);
 }
 
+// fused front end, conv0 weight block-sparse over the column offset sx:
+//   [n = sx*32 + co][k = (c*4 + ky)*16 + sxp*4 + kx] = (sxp == sx) ? w0[co][c][ky][kx] : 0
+__global__ void pack_w0x_kernel(const float* __restrict__ in, bf16* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 128 * 192) return;
+    const int n = i / 192, k = i % 192, sx = n >> 5, co = n & 31, cky = k >> 4, sxp = (k >> 2) & 3, kx = k & 3;
+    out[i] = __float2bfloat16_rn(sxp == sx ? in[(co * 12 + cky) * 4 + kx] : 0.f);
+}
+// fused front end, conv1 weight as 8 blocks (sy, kb): [blk*64 + n][col = (sx&1)*32 + c] = w1[n][c][sy][sx], sx = kb*2 + col/32
+__global__ void pack_w1x_kernel(const float* __restrict__ in, bf16* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 512 * 64) return;
+    const int row = i >> 6, col = i & 63, blk = row >> 6, n = row & 63, sy = blk >> 1, kb = blk & 1;
+    const int sx = kb * 2 + (col >> 5), c = col & 31;
+    out[i] = __float2bfloat16_rn(in[((n * 32 + c) * 4 + sy) * 4 + sx]);
+}
+
 int pack_fast(const Plan& p, const PackedLayout& L, const float* const* prm, char* packed, cudaStream_t st) {
     if (!is_committed(p)) return PMG_OK;
     const FastW f = fast_w(p);
@@ -93,6 +113,8 @@ int pack_fast(const Plan& p, const PackedLayout& L, const float* const* prm, cha
     };
     pack_w0_kernel<<<8, 256, 0, st>>>(prm[0], Bp(f.w0));           // (32,3,4,4) == [32][c*16+ky*4+kx], K padded to 64
     pack_w1_kernel<<<(64 * 512 + 255) / 256, 256, 0, st>>>(prm[5], Bp(f.w1));
+    pack_w0x_kernel<<<(128 * 192 + 255) / 256, 256, 0, st>>>(prm[0], Bp(f.w0x));
+    pack_w1x_kernel<<<(512 * 64 + 255) / 256, 256, 0, st>>>(prm[5], Bp(f.w1x));
     cvt(prm[10], f.w2, 128 * 64);
     cvt(prm[15], f.w3, 96 * 128);
     cvt(prm[16], f.wt, (size_t)192 * 9216);
@@ -354,7 +376,10 @@ static FastWs fast_ws(int B) {
 
 size_t fast_workspace_bytes(const Plan&, const Shape&, int B) { return fast_ws(B).total; }
 
-int fast_launch_count(const Plan& p, const Shape&, int) { return 5 + 1 + 1 + 1 + 6 * p.nl + (p.nl > 1 ? p.nl - 1 : 0) + 3; }
+// bf16 input: fused front kernel (1 launch) instead of im2col + conv0 + conv1 (3 launches)
+int fast_launch_count(const Plan& p, const Shape&, int, unsigned flags) {
+    return ((flags & PMG_FLAG_NO_FUSED_FRONT) ? 3 : 1) + 2 + 1 + 1 + 1 + 6 * p.nl + (p.nl > 1 ? p.nl - 1 : 0) + 3;
+}
 
 template <int BN, int NA, int EPI, int ACT>
 static int gemm(const void* a_hi, const void* a_lo, int lda, const void* b, int M, int N, int K, int ldc, float* out_f32,
@@ -368,7 +393,8 @@ static int gemm(const void* a_hi, const void* a_lo, int lda, const void* b, int 
 }
 
 int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const char* packed, const void* x, int x_dtype,
-                 int B, float* logits, float* gram, const pmg_taps* taps, char* ws, cudaStream_t st, StageTimer* tm) {
+                 int B, float* logits, float* gram, const pmg_taps* taps, char* ws, cudaStream_t st, StageTimer* tm,
+                 unsigned flags) {
     const FastWs w = fast_ws(B);
     const FastW f = fast_w(p);
     const char* fb = packed + L.fast;
@@ -379,6 +405,26 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
     const int P = B * 196, T = B * 9;
     int rc;
     PMG_MARK(tm, "start");
+    const bool fused_front = (x_dtype == PMG_BF16) && !(flags & PMG_FLAG_NO_FUSED_FRONT);
+    if (fused_front) {
+        // conv0 + conv1 (+ both BN + LeakyReLU) in one TMA-fed tcgen05 kernel (tc_front.cuh)
+        CUtensorMap tx, tw0, tw1;
+        if ((rc = tc::make_tmap_image5d(&tx, x, B))) return rc;
+        if ((rc = tc::make_tmap_bf16(&tw0, Wb(f.w0x), 128, 192, 192, 128))) return rc;
+        if ((rc = tc::make_tmap_bf16(&tw1, Wb(f.w1x), 512, 64, 64, 64))) return rc;
+        static bool attr_set = false;
+        if (!attr_set) {
+            PMG_CUDA_OK(cudaFuncSetAttribute(tc::front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FRONT_SMEM), "front smem attr");
+            attr_set = true;
+        }
+        tc::FrontParams fp;
+        fp.scale0 = Pf(L.conv_scale[0]); fp.shift0 = Pf(L.conv_shift[0]); fp.scale1 = Pf(L.conv_scale[1]); fp.shift1 = Pf(L.conv_shift[1]);
+        fp.act1_hi = Hb(w.act1_hi); fp.act1_lo = Hb(w.act1_lo); fp.B = B;
+        const int grid = 2 * B < tc::num_sms() ? 2 * B : tc::num_sms();
+        tc::front_kernel<<<grid, tc::FRONT_THREADS, tc::FRONT_SMEM, st>>>(tx, tw0, tw1, fp);
+        PMG_LAUNCH_OK("front_kernel");
+        PMG_MARK(tm, "front_conv0_conv1");
+    } else {
     // conv0 (:115-117) = im2col + GEMM [B·3136,48]×[48,32], BN+LeakyReLU epilogue → act0 planes == conv1's A
     {
         const size_t chunks = (size_t)B * 3136 * 8;
@@ -403,6 +449,7 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
                    Hb(w.act1_hi), Hb(w.act1_lo), Pf(L.conv_scale[1]), Pf(L.conv_shift[1]), nullptr, 1, 0, st)))
         return rc;
     PMG_MARK(tm, "conv1");
+    }
     // conv2: final 1×1 (:124-128)
     if ((rc = gemm<128, 2, tc::EPI_SPLIT, tc::GACT_LEAKY>(Hb(w.act1_hi), Hb(w.act1_lo), 64, Wb(f.w2), P, 128, 64, 128, nullptr,
                    Hb(w.act2_hi), Hb(w.act2_lo), Pf(L.conv_scale[2]), Pf(L.conv_shift[2]), nullptr, 1, 0, st)))

@@ -1,0 +1,265 @@
+// tc_front.cuh — fused PatchGAN front end: conv0 (k4 s4, 3→32) + BN + LeakyReLU + conv1 (k4 s4, 32→64) + BN +
+// LeakyReLU in ONE persistent tcgen05 kernel; the 56×56×32 activation never leaves the SM.
+// Reference: models_PMG.py:113-121 (the two strided layers of feature_extractor).
+//
+// Tile = 98 conv1 pixels (7 rows × 14 cols of the 14×14 map) of one image, 2 tiles per image; UMMA M = 128
+// (rows 98..127 are don't-care).  For each of the 4 row offsets sy of conv1's 4×4 window:
+//
+//   * TMA (5-D tensor map over the NCHW bf16 image, dims x16|px|y16|py|b·c, box 16×14×1×7×1, SWIZZLE_32B)
+//     drops, per (channel c, kernel row ky), a [98 pixels × 16 input columns] slab straight into smem in the
+//     K-major 32-byte-swizzled UMMA operand layout: no im2col, no register staging, every box fully in bounds.
+//   * conv0 as a GEMM over those slabs:  D0[pixel, (sx,co)] = Σ_{c,ky} A[pixel, 16 cols] · W0'[(sx,co), (c,ky,16 cols)]
+//     with W0' the conv0 weight laid out block-sparse over the 4 column offsets sx (each output column group sx
+//     only sees its own 4 of the 16 input columns).  12 MMAs (M128 N128 K16) per sy; the 4× zero padding is
+//     free: the tensor pipe is far from being the bottleneck of this layer.
+//   * epilogue 0 (8 warps): TMEM → BN scale/shift → LeakyReLU → hi/lo bf16 split → written as conv1's A operand
+//     (K-major, 128-byte swizzle) for the K slice (sy, sx, c).
+//   * conv1 accumulates that K slice:  D1[pixel, 64] += A1(hi) · W1[sy] + A1(lo) · W1[sy]   (16 MMAs, M128 N64 K16).
+//
+// After the 4th slice, epilogue 1 applies BN + LeakyReLU and stores act1 as hi/lo bf16 planes [B·196, 64].
+// Both weight tensors stay resident in smem for the life of the CTA.  D0 is double-buffered in TMEM so the
+// conv0 MMAs of slice sy+1 run under epilogue 0 of slice sy.
+#pragma once
+
+#include "tc_prims.cuh"
+
+namespace tc {
+
+constexpr int FRONT_THREADS = 320;                 // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int FR_W0_BYTES = 3 * 128 * 128;         // 48 KB: 3 K-blocks × [128 rows × 128 B]
+constexpr int FR_W1_BYTES = 8 * 64 * 128;          // 64 KB: (sy, kb) × [64 rows × 128 B]
+constexpr int FR_A0_SLOT = 4096;                   // one TMA box (98 rows × 32 B = 3136 B) per 4 KB slot
+constexpr int FR_A0_STAGE = 4 * FR_A0_SLOT;        // one channel: 4 kernel rows
+constexpr int FR_A0_STAGES = 3;
+constexpr int FR_A1_BYTES = 2 * 2 * 128 * 128;     // 64 KB: [plane hi/lo][kb][128 rows × 128 B]
+constexpr int FR_BOX_BYTES = 98 * 32;
+constexpr int FR_OFF_W1 = FR_W0_BYTES;
+constexpr int FR_OFF_A0 = FR_OFF_W1 + FR_W1_BYTES;
+constexpr int FR_OFF_A1 = FR_OFF_A0 + FR_A0_STAGES * FR_A0_STAGE;
+constexpr int FR_OFF_BAR = FR_OFF_A1 + FR_A1_BYTES;
+constexpr int FR_OFF_PRM = FR_OFF_BAR + 256;
+constexpr int FRONT_SMEM = FR_OFF_PRM + (32 + 32 + 64 + 64) * 4 + 1024;
+
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1,
+                                            int32_t c2, int32_t c3, int32_t c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+          "r"(c3), "r"(c4)
+        : "memory");
+}
+
+// K-major operand whose rows are 32 bytes (16 bf16 = one UMMA K step), 32-byte swizzle, 8-row groups 256 B apart
+__device__ __forceinline__ uint64_t make_desc_k_sw32(uint32_t saddr) { return make_smem_desc(saddr, 16, 256, LAYOUT_SW32); }
+
+struct FrontParams {
+    const float* scale0; const float* shift0;    // [32]  BN(eval) of conv0 folded
+    const float* scale1; const float* shift1;    // [64]
+    __nv_bfloat16* act1_hi; __nv_bfloat16* act1_lo;   // [B·196, 64]
+    int B;
+};
+
+__global__ void __launch_bounds__(FRONT_THREADS, 1)
+front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW0,
+             const __grid_constant__ CUtensorMap tmW1, const FrontParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sW0 = smem;
+    uint8_t* sW1 = smem + FR_OFF_W1;
+    uint8_t* sA0 = smem + FR_OFF_A0;
+    uint8_t* sA1 = smem + FR_OFF_A1;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FR_OFF_BAR);
+    uint64_t* a0_full = bars;            // [3]
+    uint64_t* a0_empty = bars + 3;       // [3]
+    uint64_t* d0_full = bars + 6;        // [2]
+    uint64_t* d0_empty = bars + 8;       // [2]
+    uint64_t* a1_ready = bars + 10;
+    uint64_t* a1_free = bars + 11;
+    uint64_t* d1_full = bars + 12;
+    uint64_t* d1_empty = bars + 13;
+    uint64_t* w_bar = bars + 14;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+    float* s0 = reinterpret_cast<float*>(smem + FR_OFF_PRM);
+    float* h0 = s0 + 32;
+    float* s1 = h0 + 32;
+    float* h1 = s1 + 64;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = 2 * p.B;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmX); prefetch_tmap(&tmW0); prefetch_tmap(&tmW1);
+        for (int i = 0; i < 3; ++i) { mbar_init(&a0_full[i], 1); mbar_init(&a0_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&d0_full[i], 1); mbar_init(&d0_empty[i], 8); }
+        mbar_init(a1_ready, 8); mbar_init(a1_free, 1); mbar_init(d1_full, 1); mbar_init(d1_empty, 8); mbar_init(w_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (threadIdx.x < 32) { s0[threadIdx.x] = p.scale0[threadIdx.x]; h0[threadIdx.x] = p.shift0[threadIdx.x]; }
+    if (threadIdx.x >= 64 && threadIdx.x < 128) { s1[threadIdx.x - 64] = p.scale1[threadIdx.x - 64]; h1[threadIdx.x - 64] = p.shift1[threadIdx.x - 64]; }
+    // A0 slot tails (rows 98..127) and A1 are read by the MMAs before/without ever being written for the
+    // don't-care rows: clear once so no NaN bit patterns circulate
+    for (int i = threadIdx.x; i < (FR_A0_STAGES * FR_A0_STAGE + FR_A1_BYTES) / 16; i += FRONT_THREADS)
+        reinterpret_cast<uint4*>(sA0)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tD0 = tmem_base, tD1 = tmem_base + 256;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            mbar_expect_tx(w_bar, FR_W0_BYTES + FR_W1_BYTES);
+            for (int i = 0; i < 3; ++i) tma_load_2d(sW0 + i * 16384, &tmW0, w_bar, i * 64, 0);
+            for (int i = 0; i < 8; ++i) tma_load_2d(sW1 + i * 8192, &tmW1, w_bar, 0, i * 64);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int b = tile >> 1, py0 = (tile & 1) * 7;
+                for (int sy = 0; sy < 4; ++sy)
+                    for (int c = 0; c < 3; ++c, ++it) {
+                        const int s = it % FR_A0_STAGES;
+                        const uint32_t ph = (it / FR_A0_STAGES) & 1;
+                        mbar_wait(&a0_empty[s], ph ^ 1);
+                        mbar_expect_tx(&a0_full[s], 4 * FR_BOX_BYTES);
+#pragma unroll
+                        for (int ky = 0; ky < 4; ++ky)
+                            tma_load_5d(sA0 + s * FR_A0_STAGE + ky * FR_A0_SLOT, &tmX, &a0_full[s], 0, 0, sy * 4 + ky, py0, b * 3 + c);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc0 = make_idesc_bf16(128, 128, 0, 0);
+            constexpr uint32_t idesc1 = make_idesc_bf16(128, 64, 0, 0);
+            const uint32_t aW0 = smem_u32(sW0), aW1 = smem_u32(sW1), aA0 = smem_u32(sA0), aA1 = smem_u32(sA1);
+            mbar_wait(w_bar, 0);
+            uint32_t it = 0, g = 0, lt = 0;
+            auto mma1 = [&](uint32_t gg) {
+                const uint32_t sy = gg & 3;
+                mbar_wait(a1_ready, gg & 1);
+                if (sy == 0) mbar_wait(d1_empty, ((gg >> 2) & 1) ^ 1);
+                tc_fence_after();
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t bd = make_desc_k_sw128(aW1 + (sy * 2 + kb) * 8192 + k * 32);
+                        umma_bf16(tD1, make_desc_k_sw128(aA1 + kb * 16384 + k * 32), bd, idesc1, (sy > 0 || kb > 0 || k > 0) ? 1u : 0u);
+                        umma_bf16(tD1, make_desc_k_sw128(aA1 + 32768 + kb * 16384 + k * 32), bd, idesc1, 1u);
+                    }
+                umma_commit(a1_free);
+            };
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+                for (int sy = 0; sy < 4; ++sy, ++g) {
+                    const uint32_t as = g & 1, aph = (g >> 1) & 1;
+                    mbar_wait(&d0_empty[as], aph ^ 1);
+                    tc_fence_after();
+                    for (int c = 0; c < 3; ++c, ++it) {
+                        const int s = it % FR_A0_STAGES;
+                        const uint32_t ph = (it / FR_A0_STAGES) & 1;
+                        mbar_wait(&a0_full[s], ph);
+                        tc_fence_after();
+#pragma unroll
+                        for (int ky = 0; ky < 4; ++ky) {
+                            const int kk = c * 4 + ky;
+                            umma_bf16(tD0 + as * 128, make_desc_k_sw32(aA0 + s * FR_A0_STAGE + ky * FR_A0_SLOT),
+                                      make_desc_k_sw128(aW0 + (kk >> 2) * 16384 + (kk & 3) * 32), idesc0, (c > 0 || ky > 0) ? 1u : 0u);
+                        }
+                        umma_commit(&a0_empty[s]);
+                    }
+                    umma_commit(&d0_full[as]);
+                    if (sy >= 1) mma1(g - 1);
+                }
+                mma1(g - 1);
+                umma_commit(d1_full);
+            }
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        const int q = warp & 3;                       // TMEM lane quarter
+        const int half = (warp - 2) >> 2;             // 0: D0 columns 0..63 (sx 0,1 → K block 0), 1: 64..127 (sx 2,3 → K block 1)
+        const int m = q * 32 + lane;                  // tile row = conv1 pixel index inside the tile
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        uint8_t* a1row = sA1 + half * 16384 + m * 128;
+        uint32_t g = 0, lt = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+            for (int sy = 0; sy < 4; ++sy, ++g) {
+                const uint32_t as = g & 1, aph = (g >> 1) & 1;
+                mbar_wait(&d0_full[as], aph);
+                tc_fence_after();
+                uint32_t H[2][16], L[2][16];
+#pragma unroll
+                for (int ck = 0; ck < 2; ++ck) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(tD0 + as * 128 + lane_addr + (uint32_t)(half * 64 + ck * 32), r);
+                    tmem_ld_wait();
+                    if (ck == 1) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&d0_empty[as]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float v0 = fmaf(__uint_as_float(r[2 * j]), s0[2 * j], h0[2 * j]);
+                        float v1 = fmaf(__uint_as_float(r[2 * j + 1]), s0[2 * j + 1], h0[2 * j + 1]);
+                        v0 = fmaxf(v0, 0.2f * v0);
+                        v1 = fmaxf(v1, 0.2f * v1);
+                        split_bf16x2(v0, v1, H[ck][j], L[ck][j]);
+                    }
+                }
+                if (g > 0) mbar_wait(a1_free, (g - 1) & 1);        // conv1 MMAs of the previous slice have read A1
+#pragma unroll
+                for (int ck = 0; ck < 2; ++ck)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int sw = ((ck * 4 + j) ^ (m & 7)) << 4;
+                        *reinterpret_cast<uint4*>(a1row + sw) = make_uint4(H[ck][4 * j], H[ck][4 * j + 1], H[ck][4 * j + 2], H[ck][4 * j + 3]);
+                        *reinterpret_cast<uint4*>(a1row + 32768 + sw) = make_uint4(L[ck][4 * j], L[ck][4 * j + 1], L[ck][4 * j + 2], L[ck][4 * j + 3]);
+                    }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a1_ready);
+            }
+            // ---- epilogue 1: act1 = LeakyReLU(BN(D1)), this warp's 32 of the 64 channels ----
+            mbar_wait(d1_full, lt & 1);
+            tc_fence_after();
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(tD1 + lane_addr + (uint32_t)(half * 32), r);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(d1_empty);
+            if (m < 98) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int c = half * 32 + 2 * j;
+                    float v0 = fmaf(__uint_as_float(r[2 * j]), s1[c], h1[c]);
+                    float v1 = fmaf(__uint_as_float(r[2 * j + 1]), s1[c + 1], h1[c + 1]);
+                    v0 = fmaxf(v0, 0.2f * v0);
+                    v1 = fmaxf(v1, 0.2f * v1);
+                    split_bf16x2(v0, v1, hi[j], lo[j]);
+                }
+                const size_t o = ((size_t)(tile >> 1) * 196 + (tile & 1) * 98 + m) * 64 + half * 32;
+                uint4* dh = reinterpret_cast<uint4*>(p.act1_hi + o);
+                uint4* dl = reinterpret_cast<uint4*>(p.act1_lo + o);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                    dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace tc

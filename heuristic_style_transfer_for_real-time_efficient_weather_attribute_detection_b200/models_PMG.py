@@ -139,6 +139,7 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
         self._ws: Optional[torch.Tensor] = None
         self._lock = threading.Lock()
         self.force_generic = False      # tests: route through the shape-generic kernels
+        self.fused_front = True         # fast path: TMA-fed fused conv0+conv1 kernel (bf16 input); False = im2col + GEMMs
 
     # kernel-side state is rebuilt on demand; keep it out of pickles / deepcopies
     def __getstate__(self):
@@ -252,7 +253,7 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
                          "tokens_in": torch.empty((B, np_, d), dtype=torch.float32, device=x.device),
                          "tokens_out": torch.empty((B, np_, d), dtype=torch.float32, device=x.device)}
                 tp = _lib.PmgTaps(extra["chan"].data_ptr(), extra["tokens_in"].data_ptr(), extra["tokens_out"].data_ptr())
-            flags = _lib.PMG_FLAG_FORCE_GENERIC if self.force_generic else 0
+            flags = self._flags()
             rc = _lib.lib.pmg_forward(cfgp, packed.data_ptr(), x.data_ptr(), dt, B, H, W, logits.data_ptr(),
                                       gram.data_ptr() if gram is not None else None,
                                       ctypes.byref(tp) if tp is not None else None,
@@ -284,6 +285,10 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
         """Test hook: (packed logits, gram, {chan, tokens_in, tokens_out})."""
         return self._run(x, want_gram=True, taps=True)
 
+    def _flags(self) -> int:
+        return ((_lib.PMG_FLAG_FORCE_GENERIC if self.force_generic else 0)
+                | (0 if self.fused_front else _lib.PMG_FLAG_NO_FUSED_FRONT))
+
     def launches_per_forward(self, B: int, H: int = 224, W: int = 224) -> int:
-        flags = _lib.PMG_FLAG_FORCE_GENERIC if self.force_generic else 0
+        flags = self._flags()
         return _lib.lib.pmg_forward_launch_count(ctypes.byref(self._cfg), B, H, W, flags)
