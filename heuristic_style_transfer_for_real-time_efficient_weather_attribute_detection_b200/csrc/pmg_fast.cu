@@ -148,6 +148,8 @@ int pack_fast(const Plan& p, const PackedLayout& L, const float* const* prm, cha
 template <bool F32IN>
 __global__ void __launch_bounds__(256) im2col0_kernel(const void* __restrict__ x, bf16* __restrict__ a_hi,
                                                       bf16* __restrict__ a_lo, int B) {
+    tc::pdl_wait();
+    tc::pdl_trigger();
     const size_t total = (size_t)B * 3136 * 8;
     for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
         const size_t r = t >> 3;
@@ -191,6 +193,8 @@ __global__ void __launch_bounds__(128) tok_ln_kernel(const float* __restrict__ p
                                                      const float* __restrict__ bias, float* __restrict__ tok,
                                                      const float* __restrict__ lnw, const float* __restrict__ lnb,
                                                      bf16* __restrict__ h_hi, bf16* __restrict__ h_lo, int T, int do_ln) {
+    tc::pdl_wait();
+    tc::pdl_trigger();
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= T) return;
     float v[6];
@@ -256,6 +260,8 @@ __global__ void __launch_bounds__(128) attn9_kernel(const float* __restrict__ qk
     constexpr int LD = 580;                 // 576 + 4: token rows land in different banks (576 ≡ 0 mod 32)
     __shared__ __align__(16) float s[9 * LD];
     __shared__ float sp[4][9][12];
+    tc::pdl_wait();
+    tc::pdl_trigger();
     const int b = blockIdx.x;
     for (int e = threadIdx.x; e < 9 * 144; e += 128) {
         const int t = e / 144, c4 = e % 144;
@@ -318,6 +324,8 @@ struct FinishArgs {
 };
 
 __global__ void __launch_bounds__(256) pool_finish_kernel(const FinishArgs a) {
+    tc::pdl_wait();
+    tc::pdl_trigger();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= a.B * a.ncls_total) return;
     const int b = idx / a.ncls_total, c = idx % a.ncls_total, t = a.task_of[c];
@@ -421,17 +429,17 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
         fp.scale0 = Pf(L.conv_scale[0]); fp.shift0 = Pf(L.conv_shift[0]); fp.scale1 = Pf(L.conv_scale[1]); fp.shift1 = Pf(L.conv_shift[1]);
         fp.act1_hi = Hb(w.act1_hi); fp.act1_lo = Hb(w.act1_lo); fp.B = B;
         const int grid = 2 * B < tc::num_sms() ? 2 * B : tc::num_sms();
-        tc::front_kernel<<<grid, tc::FRONT_THREADS, tc::FRONT_SMEM, st>>>(tx, tw0, tw1, fp);
-        PMG_LAUNCH_OK("front_kernel");
+        PMG_CUDA_OK(tc::launch_pdl(tc::front_kernel, dim3(grid), dim3(tc::FRONT_THREADS), tc::FRONT_SMEM, st, tx, tw0, tw1, fp), "front_kernel");
         PMG_MARK(tm, "front_conv0_conv1");
     } else {
     // conv0 (:115-117) = im2col + GEMM [B·3136,48]×[48,32], BN+LeakyReLU epilogue → act0 planes == conv1's A
     {
         const size_t chunks = (size_t)B * 3136 * 8;
         const int grid = (int)((chunks + 255) / 256 > 148 * 16 ? 148 * 16 : (chunks + 255) / 256);
-        if (x_dtype == PMG_F32) im2col0_kernel<true><<<grid, 256, 0, st>>>(x, Hb(w.a0_hi), Hb(w.a0_lo), B);
-        else im2col0_kernel<false><<<grid, 256, 0, st>>>(x, Hb(w.a0_hi), nullptr, B);
-        PMG_LAUNCH_OK("im2col0");
+        if (x_dtype == PMG_F32)
+            PMG_CUDA_OK(tc::launch_pdl(im2col0_kernel<true>, dim3(grid), dim3(256), 0, st, x, Hb(w.a0_hi), Hb(w.a0_lo), B), "im2col0");
+        else
+            PMG_CUDA_OK(tc::launch_pdl(im2col0_kernel<false>, dim3(grid), dim3(256), 0, st, x, Hb(w.a0_hi), (bf16*)nullptr, B), "im2col0");
         PMG_MARK(tm, "im2col0");
         if (x_dtype == PMG_F32)
             rc = gemm<32, 2, tc::EPI_SPLIT, tc::GACT_LEAKY>(Hb(w.a0_hi), Hb(w.a0_lo), 64, Wb(f.w0), P * 16, 32, 64, 32, nullptr,
@@ -470,8 +478,8 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
             attr_set = true;
         }
         const int grid = T < tc::num_sms() ? T : tc::num_sms();
-        tc::gram96_tc_kernel<<<grid, tc::GRAM_THREADS, tc::GRAM_SMEM, st>>>(Ff(w.chan), Hb(w.g_hi), Hb(w.g_lo), gram, T);
-        PMG_LAUNCH_OK("gram96_tc");
+        PMG_CUDA_OK(tc::launch_pdl(tc::gram96_tc_kernel, dim3(grid), dim3(tc::GRAM_THREADS), tc::GRAM_SMEM, st,
+                                   (const float*)Ff(w.chan), Hb(w.g_hi), Hb(w.g_lo), gram, T), "gram96_tc");
     }
     PMG_MARK(tm, "gram");
     // token_proj (:192-193): split-K partial sums, reduced (+bias) by tok_ln_kernel
@@ -482,10 +490,9 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
     PMG_MARK(tm, "token_proj");
     {
         const TfLayerOff* t0 = p.nl > 0 ? &L.tf[0] : nullptr;
-        tok_ln_kernel<<<(T + 3) / 4, 128, 0, st>>>(Ff(w.partial), w.splits, pstride, Pf(L.tok_b), Ff(w.tok),
-                                                   t0 ? Pf(t0->ln1w) : nullptr, t0 ? Pf(t0->ln1b) : nullptr, Hb(w.h_hi),
-                                                   Hb(w.h_lo), T, t0 ? 1 : 0);
-        PMG_LAUNCH_OK("tok_ln");
+        PMG_CUDA_OK(tc::launch_pdl(tok_ln_kernel, dim3((T + 3) / 4), dim3(128), 0, st, (const float*)Ff(w.partial), w.splits, pstride,
+                                   Pf(L.tok_b), Ff(w.tok), t0 ? Pf(t0->ln1w) : (const float*)nullptr,
+                                   t0 ? Pf(t0->ln1b) : (const float*)nullptr, Hb(w.h_hi), Hb(w.h_lo), T, t0 ? 1 : 0), "tok_ln");
         PMG_MARK(tm, "tok_reduce_ln");
     }
     if (taps && taps->tokens_in)
@@ -494,21 +501,18 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
     for (int l = 0; l < p.nl; ++l) {
         const TfLayerOff& t = L.tf[l];
         if (l > 0) {
-            tok_ln_kernel<<<(T + 3) / 4, 128, 0, st>>>(nullptr, 0, 0, nullptr, Ff(w.tok), Pf(t.ln1w), Pf(t.ln1b), Hb(w.h_hi),
-                                                       Hb(w.h_lo), T, 1);
-            PMG_LAUNCH_OK("ln1");
+            PMG_CUDA_OK(tc::launch_pdl(tok_ln_kernel, dim3((T + 3) / 4), dim3(128), 0, st, (const float*)nullptr, 0, (size_t)0,
+                                       (const float*)nullptr, Ff(w.tok), Pf(t.ln1w), Pf(t.ln1b), Hb(w.h_hi), Hb(w.h_lo), T, 1), "ln1");
         }
         if ((rc = gemm<192, 2, tc::EPI_F32, tc::GACT_NONE>(Hb(w.h_hi), Hb(w.h_lo), 192, Wb(f.win[l]), T, 576, 192, 576, Ff(w.qkv),
                        nullptr, nullptr, nullptr, Pf(t.b_in), nullptr, 1, 0, st)))
             return rc;
-        attn9_kernel<<<B, 128, 0, st>>>(Ff(w.qkv), Hb(w.h_hi), Hb(w.h_lo));
-        PMG_LAUNCH_OK("attn9");
+        PMG_CUDA_OK(tc::launch_pdl(attn9_kernel, dim3(B), dim3(128), 0, st, (const float*)Ff(w.qkv), Hb(w.h_hi), Hb(w.h_lo)), "attn9");
         if ((rc = gemm<192, 2, tc::EPI_F32, tc::GACT_NONE>(Hb(w.h_hi), Hb(w.h_lo), 192, Wb(f.wo[l]), T, 192, 192, 192, Ff(w.tok),
                        nullptr, nullptr, nullptr, Pf(t.b_o), Ff(w.tok), 1, 0, st)))
             return rc;
-        tok_ln_kernel<<<(T + 3) / 4, 128, 0, st>>>(nullptr, 0, 0, nullptr, Ff(w.tok), Pf(t.ln2w), Pf(t.ln2b), Hb(w.h_hi),
-                                                   Hb(w.h_lo), T, 1);
-        PMG_LAUNCH_OK("ln2");
+        PMG_CUDA_OK(tc::launch_pdl(tok_ln_kernel, dim3((T + 3) / 4), dim3(128), 0, st, (const float*)nullptr, 0, (size_t)0,
+                                   (const float*)nullptr, Ff(w.tok), Pf(t.ln2w), Pf(t.ln2b), Hb(w.h_hi), Hb(w.h_lo), T, 1), "ln2");
         if ((rc = gemm<192, 2, tc::EPI_SPLIT, tc::GACT_RELU>(Hb(w.h_hi), Hb(w.h_lo), 192, Wb(f.wf1[l]), T, 384, 192, 384, nullptr,
                        Hb(w.ffh_hi), Hb(w.ffh_lo), nullptr, Pf(t.b_1), nullptr, 1, 0, st)))
             return rc;
@@ -520,8 +524,9 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
     if (taps && taps->tokens_out)
         PMG_CUDA_OK(cudaMemcpyAsync(taps->tokens_out, Ff(w.tok), (size_t)T * 192 * 4, cudaMemcpyDeviceToDevice, st), "tap tok out");
     // task attention pooling + heads (:197-198): one [T,192]×[192,64] tensor-core GEMM + a finishing kernel
-    tok_ln_kernel<<<(T + 3) / 4, 128, 0, st>>>(nullptr, 0, 0, nullptr, Ff(w.tok), nullptr, nullptr, Hb(w.h_hi), Hb(w.h_lo), T, 2);
-    PMG_LAUNCH_OK("tok split");
+    PMG_CUDA_OK(tc::launch_pdl(tok_ln_kernel, dim3((T + 3) / 4), dim3(128), 0, st, (const float*)nullptr, 0, (size_t)0,
+                               (const float*)nullptr, Ff(w.tok), (const float*)nullptr, (const float*)nullptr, Hb(w.h_hi),
+                               Hb(w.h_lo), T, 2), "tok split");
     if ((rc = gemm<64, 2, tc::EPI_F32, tc::GACT_NONE>(Hb(w.h_hi), Hb(w.h_lo), 192, Wb(f.wq), T, 64, 192, 64, Ff(w.sc), nullptr,
                                                       nullptr, nullptr, nullptr, nullptr, 1, 0, st)))
         return rc;
@@ -530,8 +535,7 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
         a.sc = Ff(w.sc); a.bias = Pf(L.cls_b); a.logits = logits; a.B = B; a.ntask = p.ntask; a.ncls_total = p.ncls_total;
         for (int t = 0; t < p.ntask; ++t)
             for (int c = p.cls_off[t]; c < p.cls_off[t + 1]; ++c) a.task_of[c] = (unsigned char)t;
-        pool_finish_kernel<<<(B * p.ncls_total + 255) / 256, 256, 0, st>>>(a);
-        PMG_LAUNCH_OK("pool_finish");
+        PMG_CUDA_OK(tc::launch_pdl(pool_finish_kernel, dim3((B * p.ncls_total + 255) / 256), dim3(256), 0, st, a), "pool_finish");
     }
     PMG_MARK(tm, "pool_heads");
     return PMG_OK;

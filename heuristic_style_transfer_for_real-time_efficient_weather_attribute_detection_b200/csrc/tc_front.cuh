@@ -107,6 +107,7 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tD0 = tmem_base, tD1 = tmem_base + 256;
+    pdl_trigger();
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -114,6 +115,7 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             mbar_expect_tx(w_bar, FR_W0_BYTES + FR_W1_BYTES);
             for (int i = 0; i < 3; ++i) tma_load_2d(sW0 + i * 16384, &tmW0, w_bar, i * 64, 0);
             for (int i = 0; i < 8; ++i) tma_load_2d(sW1 + i * 8192, &tmW1, w_bar, 0, i * 64);
+            pdl_wait();      // weights are constants; everything below may depend on earlier kernels
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int b = tile >> 1, py0 = (tile & 1) * 7;
@@ -185,6 +187,7 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         uint8_t* a1row = sA1 + half * 16384 + m * 128;
         uint32_t g = 0, lt = 0;
+        pdl_wait();          // act1 planes are still being read by the previous forward's conv2 until it completes
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
             for (int sy = 0; sy < 4; ++sy, ++g) {
                 const uint32_t as = g & 1, aph = (g >> 1) & 1;

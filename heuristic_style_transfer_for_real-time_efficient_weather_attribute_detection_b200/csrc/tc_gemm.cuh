@@ -124,6 +124,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();          // A (and resid) come from the previous kernel
 
     if (warp == 0) {
         // ===== TMA producer =====

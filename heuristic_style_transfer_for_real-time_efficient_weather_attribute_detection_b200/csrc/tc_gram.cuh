@@ -55,6 +55,8 @@ gram96_tc_kernel(const float* __restrict__ chan, __nv_bfloat16* __restrict__ g_h
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+    pdl_wait();          // chan comes from the previous kernel
 
     if (warp < 3) {
         // ===== loaders: thread = channel =====

@@ -23,6 +23,19 @@ inline EncodeTiledFn encode_fn() {
     return fn;
 }
 
+// launch with programmatic dependent launch enabled (the kernel must call tc::pdl_wait() before touching
+// data produced by earlier kernels in the stream)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int num_sms() {
     static int n = [] {
         int dev = 0, v = 148;
@@ -90,8 +103,7 @@ int launch_gemm_t(const void* A_hi, const void* A_lo, int lda, const void* B, in
     const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
     const int items = ((tiles_m + gemm_mt<BN>() - 1) / gemm_mt<BN>()) * eff_splits * (p.N / BN);
     const int grid = items < num_sms() ? items : num_sms();
-    gemm_kernel<BN, NA, EPI, ACT><<<grid, GEMM_THREADS, smem, st>>>(ta_hi, ta_lo, tb, p);
-    PMG_LAUNCH_OK("tc gemm");
+    PMG_CUDA_OK(launch_pdl(gemm_kernel<BN, NA, EPI, ACT>, dim3(grid), dim3(GEMM_THREADS), smem, st, ta_hi, ta_lo, tb, p), "tc gemm");
     return PMG_OK;
 }
 

@@ -22,6 +22,14 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every fast-path kernel is launched with programmaticStreamSerialization: its prologue (barrier init, TMEM
+// allocation, tensor-map prefetch, weight staging) overlaps the tail of the previous kernel; pdl_wait() blocks
+// until the previous grid has completed and its writes are visible, so it must precede the first read of any
+// activation.  pdl_trigger() lets the next kernel in the stream start ITS prologue.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
