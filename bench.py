@@ -165,7 +165,7 @@ def main():
     import torch.distributed as dist
     import pmg_b200
     from pmg_b200 import _lib
-    from pmg_b200.runner import HostPipeline, gather_logits
+    from pmg_b200.runner import HostPipeline, gather_logits_async
     from oracle import synth   # seeded synthetic checkpoint generator (test infra; weights only, not compute)
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path); use --impl reference for the CPU arm"
@@ -187,12 +187,24 @@ def main():
     x = torch.randn(B, 3, 224, 224, device=dev, generator=gen).to(torch.bfloat16)
     GB = B * world
 
+    pending = [None]
+
     def step():
+        # forward of this step runs under the (async) logits all-gather of the previous one; every gather is
+        # waited for inside the timed region
         with torch.no_grad():
             lg = model.forward_packed(x)
             if world > 1:
-                lg = gather_logits(lg, GB)
+                nxt = gather_logits_async(lg, GB)
+                if pending[0] is not None:
+                    pending[0].result()
+                pending[0] = nxt
         return lg
+
+    def drain():
+        if pending[0] is not None:
+            pending[0].result()
+            pending[0] = None
 
     def fence():
         if world > 1:
@@ -201,12 +213,14 @@ def main():
 
     for _ in range(W):
         step()
+    drain()
     fence()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         out = step()
+    drain()
     e1.record()
     fence()
     ms = e0.elapsed_time(e1)

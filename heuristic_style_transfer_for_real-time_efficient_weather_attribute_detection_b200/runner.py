@@ -18,6 +18,37 @@ def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+class PendingGather:
+    """Handle of an in-flight logits all-gather: ``result()`` waits for the collective and returns the
+    (global_batch, L) tensor.  Lets the next micro-batch's forward run under the gather."""
+
+    def __init__(self, work, out, sizes, mx):
+        self.work, self.out, self.sizes, self.mx = work, out, sizes, mx
+
+    def result(self) -> torch.Tensor:
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+        if all(hi - lo == self.mx for lo, hi in self.sizes):
+            return self.out
+        return torch.cat([self.out[r * self.mx: r * self.mx + (hi - lo)] for r, (lo, hi) in enumerate(self.sizes)], dim=0)
+
+
+def gather_logits_async(local: torch.Tensor, global_batch: int, group=None) -> PendingGather:
+    """Same single collective as gather_logits, issued with async_op=True."""
+    world = dist.get_world_size(group)
+    L = local.shape[1]
+    sizes = [shard_bounds(global_batch, world, r) for r in range(world)]
+    mx = max(hi - lo for lo, hi in sizes)
+    send = local
+    if local.shape[0] != mx:
+        send = local.new_zeros((mx, L))
+        send[: local.shape[0]] = local
+    out = local.new_empty((world * mx, L))
+    work = dist.all_gather_into_tensor(out, send.contiguous(), group=group, async_op=True)
+    return PendingGather(work, out, sizes, mx)
+
+
 def gather_logits(local: torch.Tensor, global_batch: int, group=None) -> torch.Tensor:
     """All-gather ragged (B_local, L) shards into (global_batch, L) on every rank with ONE collective:
     shards are padded to the largest shard so a single all_gather_into_tensor moves them."""
@@ -51,6 +82,11 @@ class ShardedPMG:
     @torch.no_grad()
     def infer(self, x_local: torch.Tensor, global_batch: int) -> torch.Tensor:
         return gather_logits(self.infer_local(x_local), global_batch, self.group)
+
+    @torch.no_grad()
+    def infer_async(self, x_local: torch.Tensor, global_batch: int) -> PendingGather:
+        """Forward of the local shard + non-blocking gather; call ``.result()`` when the logits are needed."""
+        return gather_logits_async(self.infer_local(x_local), global_batch, self.group)
 
     def split(self, logits: torch.Tensor) -> Dict[str, torch.Tensor]:
         return self.model._split(logits)

@@ -49,3 +49,29 @@ def test_gather_logits_world2_gloo(n):
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def _worker_async(rank, world, port, n, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pmg_b200.runner import gather_logits_async, shard_bounds
+    full = torch.arange(n * 52, dtype=torch.float32).reshape(n, 52)
+    lo, hi = shard_bounds(n, world, rank)
+    h1 = gather_logits_async(full[lo:hi].clone(), n)
+    h2 = gather_logits_async(full[lo:hi].clone() * 2, n)      # two gathers in flight
+    ok = bool(torch.equal(h1.result(), full)) and bool(torch.equal(h2.result(), full * 2))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_gather_logits_async_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_async, args=(r, 2, port, 9, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
