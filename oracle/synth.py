@@ -164,3 +164,41 @@ def images(seed: int, batch: int, h: int = 224, w: int = 224, c: int = 3) -> np.
     xx = (np.arange(w) * gw // w)
     field = coarse[:, :, yy][:, :, :, xx]
     return round_bf16((1.1 * field + 0.6 * noise).astype(np.float32))
+
+
+# --------------------------------------------------------------------------------------
+# PM contract (reference: Models/models_PM.py:91-157, test_PM.py:153-164, hyperparameters_PM.json)
+# --------------------------------------------------------------------------------------
+PM_HPARAMS = {"ndf": 64, "norm": "instance", "patch_size": 73, "attn_tau": 0.7, "attn_use_se": False,
+              "attn_softmax_spatial": True}
+
+
+def pm_trunk_plan(input_nc: int, ndf: int, patch_size: float):
+    """[(cin, cout, stride)] of the k=4, pad=1 trunk convs — layer-count loop of models_PM.py:121-139."""
+    plan, cin, nf, rf = [], input_nc, ndf, float(patch_size)
+    while rf > 4 and nf <= 512:
+        plan.append((cin, nf, 2))
+        cin, nf, rf = nf, nf * 2, rf / 2
+    plan.append((cin, nf, 1))
+    return plan
+
+
+def pm_state_dict(seed: int = 0, hparams: dict | None = None, tasks: dict | None = None, input_nc: int = 3):
+    """Synthetic PM state_dict in the reference's key layout (InstanceNorm2d(affine=True) has no running stats)."""
+    hp = dict(PM_HPARAMS if hparams is None else hparams)
+    tasks = dict(PMG_TASKS if tasks is None else tasks)
+    sd = {}
+    idx = 0
+    for (cin, cout, _s) in pm_trunk_plan(input_nc, hp["ndf"], hp["patch_size"]):
+        fan = cin * 16
+        sd[f"trunk.{idx}.weight"] = _t(f"pm.t{idx}.w", seed, (cout, cin, 4, 4), std=1.4 / np.sqrt(fan))
+        sd[f"trunk.{idx}.bias"] = _t(f"pm.t{idx}.b", seed, (cout,), std=0.1)
+        sd[f"trunk.{idx + 1}.weight"] = _t(f"pm.t{idx}.g", seed, (cout,), kind="uniform", lo=0.6, hi=1.4)
+        sd[f"trunk.{idx + 1}.bias"] = _t(f"pm.t{idx}.be", seed, (cout,), std=0.2)
+        idx += 3
+        c_last = cout
+    for t, n in tasks.items():
+        sd[f"task_heads.{t}.attn_conv.weight"] = _t(f"pm.{t}.aw", seed, (1, c_last, 1, 1), std=2.0 / np.sqrt(c_last))
+        sd[f"task_heads.{t}.attn_conv.bias"] = _t(f"pm.{t}.ab", seed, (1,), std=0.1)
+        sd[f"task_heads.{t}.cls_conv.weight"] = _t(f"pm.{t}.cw", seed, (n, c_last, 1, 1), std=1.0 / np.sqrt(c_last))
+    return sd

@@ -120,5 +120,56 @@ def main():
         json.dump({"hparams": small_hp, "tasks": small_tasks}, f, indent=1)
 
 
+def run_pm_case(name, hp, tasks_n, seed, batch, h, w):
+    from Models.models_PM import MultiTaskPatchGAN, load_model_weights   # reference
+    model = MultiTaskPatchGAN(tasks_dict=tasks_n, input_nc=3, ndf=hp["ndf"], norm=hp["norm"], patch_size=hp["patch_size"],
+                              device="cpu", attn_tau=hp["attn_tau"], attn_use_se=hp["attn_use_se"],
+                              attn_softmax_spatial=hp["attn_softmax_spatial"])
+    sd_np = synth.pm_state_dict(seed, hp, tasks_n)
+    assert list(model.state_dict().keys()) == list(sd_np.keys()), "synthetic PM key order != reference"
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "best_model_PM.pth")
+        torch.save({k: torch.from_numpy(np.array(v)) for k, v in sd_np.items()}, p)
+        load_model_weights(model, p, torch.device("cpu"), strict=True)
+    model.eval()
+    x = torch.from_numpy(synth.images(seed, batch, h, w))
+    with torch.no_grad():
+        full = model(x, return_full=True)
+        feats = model.trunk(x)
+    logits = torch.cat([full[t]["logits"] for t in tasks_n], dim=1).numpy()
+    attn = torch.stack([full[t]["attn"][:, 0] for t in tasks_n], dim=1).numpy()        # (B, T, H, W)
+    f = feats.numpy().astype(np.float64)
+    np.savez_compressed(os.path.join(HERE, f"{name}.npz"), logits=logits.astype(np.float32), attn=attn.astype(np.float32),
+                        feats_stats=np.array([f.mean(), np.abs(f).mean(), np.sqrt((f ** 2).mean())]),
+                        feats_img0_ch0=feats[0, 0].numpy().astype(np.float32),
+                        feats_fro=np.sqrt((f ** 2).sum(axis=(1, 2, 3))), meta=np.array([seed, batch, h, w], dtype=np.int64))
+    print(f"{name}: logits {logits.shape} |max| {np.abs(logits).max():.3f} feats {tuple(feats.shape)}")
+    return model
+
+
+def main_pm():
+    with open(os.path.join(REF, "build_classifiers/Tasks.json")) as f:
+        tasks_lists = json.load(f)
+    tasks_n = {t: len(v) for t, v in tasks_lists.items()}
+    with open(os.path.join(REF, "Model_weights/PM/hyperparameters_PM.json")) as f:
+        cfg = json.load(f)
+    hp = {"ndf": 64, "norm": "instance", "patch_size": cfg["patch_size"], "attn_tau": cfg["attn_tau"],
+          "attn_use_se": cfg["attn_use_se"], "attn_softmax_spatial": cfg["attn_softmax_spatial"]}   # test_PM.py:146-164
+    model = run_pm_case("pm_b2_224", hp, tasks_n, seed=4, batch=2, h=224, w=224)
+    contract = {"source": "generated from /root/reference Model_weights/PM/hyperparameters_PM.json + test_PM.py:153-164 + Tasks.json",
+                "hparams": hp, "tasks": tasks_lists,
+                "state_dict": [[k, list(v.shape), str(v.dtype)] for k, v in model.state_dict().items()],
+                "n_params": int(sum(p.numel() for p in model.parameters()))}
+    with open(os.path.join(HERE, "pm_contract.json"), "w") as f:
+        json.dump(contract, f, indent=1)
+    small = {"ndf": 16, "norm": "instance", "patch_size": 16, "attn_tau": 0.5, "attn_use_se": False, "attn_softmax_spatial": True}
+    run_pm_case("pm_small_b3_40x52", small, {"alpha": 3, "beta": 2}, seed=6, batch=3, h=40, w=52)
+    with open(os.path.join(HERE, "pm_small_contract.json"), "w") as f:
+        json.dump({"hparams": small, "tasks": {"alpha": ["a", "b", "c"], "beta": ["x", "y"]}}, f, indent=1)
+
+
 if __name__ == "__main__":
+    if "--pm-only" not in sys.argv:
+        main()
+    main_pm()
     main()
