@@ -11,9 +11,11 @@ package without it raises ImportError.  There is no CPU or eager-PyTorch fallbac
 """
 from . import _lib                      # noqa: F401  (fails loudly if the .so is missing)
 from . import models_PMG                # noqa: F401
+from . import models_PM                 # noqa: F401
 from .models_PMG import MultiTaskPatchGANGramModelNonOverlapV2  # noqa: F401
+from .models_PM import MultiTaskPatchGAN  # noqa: F401
 from .compat import install_as_reference_models  # noqa: F401
 from . import gram as gram              # noqa: F401
 from . import runner as runner          # noqa: F401
 
-__all__ = ["MultiTaskPatchGANGramModelNonOverlapV2", "install_as_reference_models", "gram", "runner"]
+__all__ = ["MultiTaskPatchGANGramModelNonOverlapV2", "MultiTaskPatchGAN", "install_as_reference_models", "gram", "runner"]

@@ -25,6 +25,11 @@ class PmgTaps(C.Structure):
     _fields_ = [("chan", C.c_void_p), ("tokens_in", C.c_void_p), ("tokens_out", C.c_void_p)]
 
 
+class PmConfig(C.Structure):
+    _fields_ = [("input_nc", C.c_int32), ("ndf", C.c_int32), ("patch_size", C.c_float), ("n_tasks", C.c_int32),
+                ("ncls", C.c_int32 * PMG_MAX_TASKS), ("attn_tau", C.c_float), ("ablate_attention", C.c_int32)]
+
+
 class PmgStageTime(C.Structure):
     _fields_ = [("name", C.c_char_p), ("ms", C.c_float)]
 
@@ -37,6 +42,7 @@ EXPORTS = [
     "pmg_abi_version", "pmg_status_string", "pmg_last_cuda_error", "pmg_param_count", "pmg_packed_bytes",
     "pmg_pack_weights", "pmg_workspace_bytes", "pmg_logits_per_image", "pmg_forward_launch_count",
     "pmg_forward", "pmg_forward_profile", "pmg_gram_batched", "pmg_tc_gemm",
+    "pm_param_count", "pm_packed_bytes", "pm_pack_weights", "pm_workspace_bytes", "pm_feature_shape", "pm_forward",
 ]
 
 
@@ -75,6 +81,20 @@ def _load() -> C.CDLL:
     lib.pmg_tc_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_void_p, C.c_void_p]
     lib.pmg_tc_gemm.restype = C.c_int
+    pcfg = C.POINTER(PmConfig)
+    lib.pm_param_count.argtypes = [pcfg]
+    lib.pm_param_count.restype = C.c_int
+    lib.pm_packed_bytes.argtypes = [pcfg]
+    lib.pm_packed_bytes.restype = C.c_size_t
+    lib.pm_pack_weights.argtypes = [pcfg, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.pm_pack_weights.restype = C.c_int
+    lib.pm_workspace_bytes.argtypes = [pcfg, C.c_int, C.c_int, C.c_int]
+    lib.pm_workspace_bytes.restype = C.c_size_t
+    lib.pm_feature_shape.argtypes = [pcfg, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.pm_feature_shape.restype = C.c_int
+    lib.pm_forward.argtypes = [pcfg, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p]
+    lib.pm_forward.restype = C.c_int
     if lib.pmg_abi_version() != 1:
         raise ImportError("libpmg_b200.so ABI version mismatch — rebuild")
     return lib
@@ -88,6 +108,18 @@ def check(status: int, what: str) -> None:
         msg = lib.pmg_status_string(status).decode()
         cuda = lib.pmg_last_cuda_error().decode()
         raise PmgError(f"{what}: {msg}" + (f" [{cuda}]" if status == 5 and cuda else ""))
+
+
+def make_pm_config(input_nc, ndf, patch_size, ncls_list, attn_tau, ablate) -> PmConfig:
+    if len(ncls_list) > PMG_MAX_TASKS:
+        raise PmgError(f"at most {PMG_MAX_TASKS} tasks are supported")
+    cfg = PmConfig()
+    cfg.input_nc, cfg.ndf, cfg.patch_size = input_nc, ndf, float(patch_size)
+    cfg.n_tasks = len(ncls_list)
+    for i, n in enumerate(ncls_list):
+        cfg.ncls[i] = int(n)
+    cfg.attn_tau, cfg.ablate_attention = float(attn_tau), int(bool(ablate))
+    return cfg
 
 
 def make_config(input_nc, ndf, patch_size, patch_div, gram_channels, d_model, transformer_layers,

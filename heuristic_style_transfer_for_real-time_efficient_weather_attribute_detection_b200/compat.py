@@ -19,7 +19,7 @@ import types
 
 
 def install_as_reference_models() -> None:
-    from . import models_PMG
+    from . import models_PM, models_PMG
     pkg = sys.modules.get("Models")
     if pkg is None:
         try:
@@ -30,6 +30,8 @@ def install_as_reference_models() -> None:
             sys.modules["Models"] = pkg
     sys.modules["Models.models_PMG"] = models_PMG
     setattr(pkg, "models_PMG", models_PMG)
+    sys.modules["Models.models_PM"] = models_PM            # test_PM.py:16-21 imports MultiTaskPatchGAN & helpers
+    setattr(pkg, "models_PM", models_PM)
 
 
 def main(argv=None) -> int:

@@ -1,0 +1,455 @@
+// pm_path.cu — PM model (MultiTaskPatchGAN) eval forward on B200.
+// Reference: /root/reference/Models/models_PM.py:91-194 (trunk :114-141, heads :27-76, forward :159-194).
+//
+// Every trunk layer is  Conv2d(k4, s2|s1, p1, bias) → InstanceNorm2d(affine, per-sample stats) → LeakyReLU(0.2):
+//   im2col (hi/lo bf16 planes, zero padding folded in)  →  tc::gemm_kernel (tcgen05, fp32 accumulate, + bias)
+//   →  instnorm kernel (fp32 two-pass statistics per (sample, channel), affine, LeakyReLU, hi/lo split)
+// The 12 task heads (attn_conv 1×1 → spatial softmax(a/τ) → cls_conv 1×1 → attention-weighted sum) are one
+// tensor-core GEMM  feats[B·HW, C] × [attn rows | cls rows]ᵀ  (N = 64) plus a warp-shuffle finishing kernel
+// (softmax over the HW positions, weighted sum of the per-position class projections): cls_conv is linear, so
+// Σ_p A_p (W·f_p) == W·(Σ_p A_p f_p) and no (B, K, H, W) map is materialised.
+#include "pmg_common.cuh"
+#include "tc_host.cuh"
+
+namespace pmg {
+
+using bf16 = __nv_bfloat16;
+constexpr int PM_MAX_LAYERS = 8;
+constexpr int PM_CHUNK = 128;          // images per internal pass (bounds the im2col workspace)
+constexpr float kInEps = 1e-5f;        // nn.InstanceNorm2d default
+
+struct PmLayer { int cin, cout, stride, K, Kp; };   // K = cin*16, Kp = K rounded up to 64
+
+struct PmPlan {
+    int n_layers = 0;
+    PmLayer layer[PM_MAX_LAYERS];
+    int C = 0, ntask = 0, ncls_total = 0;
+    int cls_off[PMG_MAX_TASKS + 1];
+    bool ok = false;
+};
+
+static PmPlan pm_plan(const pm_config* c) {
+    PmPlan p;
+    if (!c || c->input_nc < 1 || c->ndf < 32 || c->ndf % 32 || c->n_tasks < 1 || c->n_tasks > PMG_MAX_TASKS || !(c->attn_tau > 0.f))
+        return p;
+    int cin = c->input_nc, nf = c->ndf;
+    float rf = c->patch_size;
+    auto add = [&](int ci, int co, int st) {
+        PmLayer& l = p.layer[p.n_layers++];
+        l.cin = ci; l.cout = co; l.stride = st; l.K = ci * 16; l.Kp = (l.K + 63) / 64 * 64;
+    };
+    while (rf > 4.f && nf <= 512) {                       // models_PM.py:121-132
+        if (p.n_layers >= PM_MAX_LAYERS - 1) return p;
+        add(cin, nf, 2);
+        cin = nf; nf *= 2; rf /= 2.f;
+    }
+    add(cin, nf, 1);                                      // :134-139
+    p.C = nf;
+    p.ntask = c->n_tasks;
+    int off = 0;
+    for (int t = 0; t < c->n_tasks; ++t) {
+        if (c->ncls[t] < 1 || c->ncls[t] > 8) return p;     // finishing kernel keeps ≤ 8 class accumulators per task
+        p.cls_off[t] = off; off += c->ncls[t];
+    }
+    p.cls_off[c->n_tasks] = off;
+    p.ncls_total = off;
+    if (p.ntask + p.ncls_total > 64) return p;            // heads GEMM is one N = 64 tile
+    p.ok = true;
+    return p;
+}
+
+struct PmShape { int h[PM_MAX_LAYERS + 1], w[PM_MAX_LAYERS + 1]; bool ok = false; };
+
+static PmShape pm_shape(const PmPlan& p, int H, int W) {
+    PmShape s;
+    s.h[0] = H; s.w[0] = W;
+    for (int l = 0; l < p.n_layers; ++l) {
+        s.h[l + 1] = (s.h[l] + 2 - 4) / p.layer[l].stride + 1;
+        s.w[l + 1] = (s.w[l] + 2 - 4) / p.layer[l].stride + 1;
+        if (s.h[l] + 2 < 4 || s.w[l] + 2 < 4 || s.h[l + 1] < 1 || s.w[l + 1] < 1) return s;
+    }
+    s.ok = true;
+    return s;
+}
+
+struct PmPacked {
+    size_t w[PM_MAX_LAYERS], bias[PM_MAX_LAYERS], gamma[PM_MAX_LAYERS], beta[PM_MAX_LAYERS];
+    size_t wh, bh;      // heads: [64][C] bf16, bias [64] fp32 (attn biases in the first ntask slots)
+    size_t total;
+};
+
+static PmPacked pm_packed(const PmPlan& p) {
+    PmPacked L{};
+    size_t o = 256;
+    auto take = [&](size_t bytes) { size_t r = o; o = align256(o + bytes); return r; };
+    for (int l = 0; l < p.n_layers; ++l) {
+        L.w[l] = take((size_t)p.layer[l].cout * p.layer[l].Kp * 2);
+        L.bias[l] = take(p.layer[l].cout * 4); L.gamma[l] = take(p.layer[l].cout * 4); L.beta[l] = take(p.layer[l].cout * 4);
+    }
+    L.wh = take((size_t)64 * p.C * 2);
+    L.bh = take(64 * 4);
+    L.total = o;
+    return L;
+}
+
+// ------------------------------------------------------------------------------------------------ packing
+// layer 0: [co][k = c*16+ky*4+kx] (torch order), zero-padded to Kp;  layers ≥ 1: [co][k = (ky*4+kx)*cin + c]
+__global__ void pm_pack_conv_kernel(const float* __restrict__ in, bf16* __restrict__ out, int cout, int cin, int Kp, int nhwc) {
+    const size_t total = (size_t)cout * Kp;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int co = (int)(i / Kp), k = (int)(i % Kp);
+        float v = 0.f;
+        if (k < cin * 16) {
+            if (nhwc) { const int kk = k / cin, c = k % cin; v = in[((size_t)co * cin + c) * 16 + kk]; }
+            else v = in[(size_t)co * cin * 16 + k];
+        }
+        out[i] = __float2bfloat16_rn(v);
+    }
+}
+__global__ void pm_copy_kernel(const float* __restrict__ in, float* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+__global__ void pm_cvt_kernel(const float* __restrict__ in, bf16* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ im2col
+// first layer: x (B,Cin,H,W) NCHW fp32|bf16 → A planes [B·Ho·Wo][Kp], k = c*16 + ky*4 + kx, pad 1
+template <bool F32IN>
+__global__ void __launch_bounds__(256) pm_im2col_first_kernel(const void* __restrict__ x, bf16* __restrict__ a_hi,
+                                                              bf16* __restrict__ a_lo, int B, int Cin, int H, int W, int Ho,
+                                                              int Wo, int stride, int Kp) {
+    const int chunks = Kp / 8;
+    const size_t total = (size_t)B * Ho * Wo * chunks;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = t / chunks;
+        const int j = (int)(t % chunks);
+        const int xo = (int)(r % Wo), yo = (int)((r / Wo) % Ho);
+        const size_t b = r / ((size_t)Wo * Ho);
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = j * 8 + e, c = k >> 4, ky = (k >> 2) & 3, kx = k & 3;
+            const int y = yo * stride - 1 + ky, xx = xo * stride - 1 + kx;
+            float val = 0.f;
+            if (c < Cin && y >= 0 && y < H && xx >= 0 && xx < W) {
+                const size_t idx = ((b * Cin + c) * H + y) * W + xx;
+                val = F32IN ? reinterpret_cast<const float*>(x)[idx] : __bfloat162float(reinterpret_cast<const bf16*>(x)[idx]);
+            }
+            v[e] = val;
+        }
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) tc::split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+        *reinterpret_cast<uint4*>(a_hi + r * Kp + j * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(a_lo + r * Kp + j * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// deeper layers: activation planes (B,H,W,C) bf16 → A planes [B·Ho·Wo][16·C], k = (ky*4+kx)*C + c; 16-byte copies
+__global__ void __launch_bounds__(256) pm_im2col_kernel(const bf16* __restrict__ in_hi, const bf16* __restrict__ in_lo,
+                                                        bf16* __restrict__ a_hi, bf16* __restrict__ a_lo, int B, int C, int H,
+                                                        int W, int Ho, int Wo, int stride) {
+    const int c8 = C / 8;
+    const size_t total = (size_t)B * Ho * Wo * 16 * c8;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        const int cc = (int)(t % c8);
+        const int kk = (int)((t / c8) & 15);
+        const size_t r = t / ((size_t)c8 * 16);
+        const int xo = (int)(r % Wo), yo = (int)((r / Wo) % Ho);
+        const size_t b = r / ((size_t)Wo * Ho);
+        const int y = yo * stride - 1 + (kk >> 2), xx = xo * stride - 1 + (kk & 3);
+        uint4 vh = make_uint4(0, 0, 0, 0), vl = vh;
+        if (y >= 0 && y < H && xx >= 0 && xx < W) {
+            const size_t src = ((b * H + y) * W + xx) * C + cc * 8;
+            vh = *reinterpret_cast<const uint4*>(in_hi + src);
+            vl = *reinterpret_cast<const uint4*>(in_lo + src);
+        }
+        const size_t dst = r * (size_t)(16 * C) + (size_t)kk * C + cc * 8;
+        *reinterpret_cast<uint4*>(a_hi + dst) = vh;
+        *reinterpret_cast<uint4*>(a_lo + dst) = vl;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ InstanceNorm
+// conv (B, HW, C) fp32 → LeakyReLU(IN(conv)) as hi/lo planes (and fp32 on request).  Block = (sample, 32 channels),
+// lane = channel, 8 warps stride over the pixels; statistics in two passes (mean, then centred second moment).
+__global__ void __launch_bounds__(256) pm_instnorm_kernel(const float* __restrict__ conv, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, bf16* __restrict__ o_hi,
+                                                          bf16* __restrict__ o_lo, float* __restrict__ o_f32, int HW, int C) {
+    __shared__ float red[8][33];
+    __shared__ float s_mean[32], s_rstd[32];
+    const int b = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* src = conv + (size_t)b * HW * C + c;
+    float s = 0.f;
+    for (int p = warp; p < HW; p += 8) s += src[(size_t)p * C];
+    red[warp][lane] = s;
+    __syncthreads();
+    if (warp == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][lane];
+        s_mean[lane] = t / (float)HW;
+    }
+    __syncthreads();
+    const float mu = s_mean[lane];
+    float q = 0.f;
+    for (int p = warp; p < HW; p += 8) { const float d = src[(size_t)p * C] - mu; q = fmaf(d, d, q); }
+    red[warp][lane] = q;
+    __syncthreads();
+    if (warp == 0) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][lane];
+        s_rstd[lane] = 1.f / sqrtf(t / (float)HW + kInEps);
+    }
+    __syncthreads();
+    const float sc = s_rstd[lane] * gamma[c], sh = beta[c] - mu * sc;
+    for (int p = warp; p < HW; p += 8) {
+        float v = fmaf(src[(size_t)p * C], sc, sh);
+        v = fmaxf(v, 0.2f * v);
+        const size_t o = ((size_t)b * HW + p) * C + c;
+        const bf16 h = __float2bfloat16_rn(v);
+        o_hi[o] = h;
+        o_lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+        if (o_f32) o_f32[o] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ heads finish
+// sc (B·HW, 64): col t < ntask = attention logit a_t (bias added), col ntask + c = cls_conv projection of class c.
+// One warp per (sample, task): A = softmax_p(a/τ) (or uniform), logits_c = Σ_p A_p·proj_c(p) / (ΣA + 1e-6).
+struct PmFinishArgs {
+    const float* sc; float* logits; float* attn;
+    int B, HW, ntask, ncls_total, ablate;
+    float inv_tau;
+    int cls_off[PMG_MAX_TASKS + 1];
+};
+
+__global__ void __launch_bounds__(128) pm_heads_finish_kernel(const PmFinishArgs a) {
+    const int wid = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (wid >= a.B * a.ntask) return;
+    const int b = wid / a.ntask, t = wid % a.ntask;
+    const float* s = a.sc + (size_t)b * a.HW * 64;
+    float mx = -INFINITY;
+    if (!a.ablate)
+        for (int p = lane; p < a.HW; p += 32) mx = fmaxf(mx, s[(size_t)p * 64 + t] * a.inv_tau);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const int c0 = a.cls_off[t], nc = a.cls_off[t + 1] - c0;
+    float den = 0.f, acc[8] = {};
+    for (int p = lane; p < a.HW; p += 32) {
+        const float e = a.ablate ? 1.f : expf(s[(size_t)p * 64 + t] * a.inv_tau - mx);
+        den += e;
+        for (int k = 0; k < nc && k < 8; ++k) acc[k] = fmaf(e, s[(size_t)p * 64 + a.ntask + c0 + k], acc[k]);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        den += __shfl_xor_sync(0xffffffffu, den, o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    }
+    // A = e/den sums to 1; the reference divides Σ(M·A) by (ΣA + 1e-6) for the softmax variant (models_PM.py:73-75)
+    // and uses plain Σ(M·A) with A = 1/HW for the ablation (:60-63)
+    const float norm = a.ablate ? 1.f / (float)a.HW : 1.f / (den * (1.f + 1e-6f));
+    if (lane == 0)
+        for (int k = 0; k < nc && k < 8; ++k) a.logits[(size_t)b * a.ncls_total + c0 + k] = acc[k] * norm;
+    if (a.attn) {
+        float* dst = a.attn + ((size_t)b * a.ntask + t) * a.HW;
+        for (int p = lane; p < a.HW; p += 32)
+            dst[p] = a.ablate ? 1.f / (float)a.HW : expf(s[(size_t)p * 64 + t] * a.inv_tau - mx) / den;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ workspace
+struct PmWs { size_t a_hi, a_lo, conv, act_hi[2], act_lo[2], sc, feats, total; };
+
+static PmWs pm_ws(const PmPlan& p, const PmShape& s, int Bc) {
+    PmWs w{};
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t r = o; o = align256(o + bytes); return r; };
+    size_t amax = 0, cmax = 0;
+    for (int l = 0; l < p.n_layers; ++l) {
+        const size_t rows = (size_t)Bc * s.h[l + 1] * s.w[l + 1];
+        amax = max(amax, rows * p.layer[l].Kp);
+        cmax = max(cmax, rows * p.layer[l].cout);
+    }
+    w.a_hi = take(amax * 2); w.a_lo = take(amax * 2);
+    w.conv = take(cmax * 4);
+    for (int i = 0; i < 2; ++i) { w.act_hi[i] = take(cmax * 2); w.act_lo[i] = take(cmax * 2); }
+    w.sc = take((size_t)Bc * s.h[p.n_layers] * s.w[p.n_layers] * 64 * 4);
+    w.total = o;
+    return w;
+}
+
+template <int BN>
+static int pm_gemm(const void* a_hi, const void* a_lo, int Kp, const void* wgt, int M, int N, float* out, const float* bias,
+                   cudaStream_t st) {
+    tc::GemmParams g{};
+    g.M = M; g.N = N; g.K = Kp; g.epi = tc::EPI_F32; g.act = tc::GACT_NONE; g.ldc = N; g.out_f32 = out; g.shift = bias;
+    return tc::launch_gemm_t<BN, 2, tc::EPI_F32, tc::GACT_NONE>(a_hi, a_lo, Kp, wgt, Kp, g, 1, Kp, st);
+}
+
+// N may exceed GEMM_MAX_N (scale/shift staging): run column panels of ≤ 512
+static int pm_conv_gemm(const void* a_hi, const void* a_lo, int Kp, const bf16* wgt, int M, int N, float* out, const float* bias,
+                        cudaStream_t st) {
+    for (int n0 = 0; n0 < N; n0 += 512) {
+        const int nn = min(512, N - n0);
+        tc::GemmParams g{};
+        g.M = M; g.N = nn; g.K = Kp; g.epi = tc::EPI_F32; g.act = tc::GACT_NONE; g.ldc = N; g.out_f32 = out + n0; g.shift = bias + n0;
+        int rc;
+        if (nn % 128 == 0) rc = tc::launch_gemm_t<128, 2, tc::EPI_F32, tc::GACT_NONE>(a_hi, a_lo, Kp, wgt + (size_t)n0 * Kp, Kp, g, 1, Kp, st);
+        else if (nn % 64 == 0) rc = tc::launch_gemm_t<64, 2, tc::EPI_F32, tc::GACT_NONE>(a_hi, a_lo, Kp, wgt + (size_t)n0 * Kp, Kp, g, 1, Kp, st);
+        else if (nn % 32 == 0) rc = tc::launch_gemm_t<32, 2, tc::EPI_F32, tc::GACT_NONE>(a_hi, a_lo, Kp, wgt + (size_t)n0 * Kp, Kp, g, 1, Kp, st);
+        else rc = PMG_ERR_UNSUPPORTED;
+        if (rc) return rc;
+    }
+    return PMG_OK;
+}
+
+static int grid1d(size_t n) { size_t g = (n + 255) / 256; return (int)(g > 148 * 32 ? 148 * 32 : (g < 1 ? 1 : g)); }
+
+}  // namespace pmg
+
+using namespace pmg;
+
+extern "C" {
+
+int pm_param_count(const pm_config* cfg) {
+    const PmPlan p = pm_plan(cfg);
+    return p.ok ? 4 * p.n_layers + 3 * p.ntask : -1;
+}
+
+size_t pm_packed_bytes(const pm_config* cfg) {
+    const PmPlan p = pm_plan(cfg);
+    return p.ok ? pm_packed(p).total : 0;
+}
+
+int pm_feature_shape(const pm_config* cfg, int H, int W, int* Hf, int* Wf, int* C) {
+    const PmPlan p = pm_plan(cfg);
+    if (!p.ok || !Hf || !Wf || !C) return PMG_ERR_BAD_ARG;
+    const PmShape s = pm_shape(p, H, W);
+    if (!s.ok) return PMG_ERR_BAD_SHAPE;
+    *Hf = s.h[p.n_layers]; *Wf = s.w[p.n_layers]; *C = p.C;
+    return PMG_OK;
+}
+
+int pm_pack_weights(const pm_config* cfg, const float* const* prm, int n_params, void* packed, size_t packed_bytes,
+                    pmg_stream_t stream) {
+    const PmPlan p = pm_plan(cfg);
+    if (!p.ok || !prm || !packed) return PMG_ERR_BAD_ARG;
+    if (n_params != 4 * p.n_layers + 3 * p.ntask) return PMG_ERR_BAD_ARG;
+    for (int i = 0; i < n_params; ++i)
+        if (!prm[i]) return PMG_ERR_BAD_ARG;
+    const PmPacked L = pm_packed(p);
+    if (packed_bytes < L.total) return PMG_ERR_WORKSPACE;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    char* base = reinterpret_cast<char*>(packed);
+    int i = 0;
+    for (int l = 0; l < p.n_layers; ++l) {
+        const PmLayer& y = p.layer[l];
+        pm_pack_conv_kernel<<<grid1d((size_t)y.cout * y.Kp), 256, 0, st>>>(prm[i], reinterpret_cast<bf16*>(base + L.w[l]), y.cout, y.cin, y.Kp, l > 0);
+        pm_copy_kernel<<<(y.cout + 255) / 256, 256, 0, st>>>(prm[i + 1], reinterpret_cast<float*>(base + L.bias[l]), y.cout);
+        pm_copy_kernel<<<(y.cout + 255) / 256, 256, 0, st>>>(prm[i + 2], reinterpret_cast<float*>(base + L.gamma[l]), y.cout);
+        pm_copy_kernel<<<(y.cout + 255) / 256, 256, 0, st>>>(prm[i + 3], reinterpret_cast<float*>(base + L.beta[l]), y.cout);
+        i += 4;
+    }
+    PMG_CUDA_OK(cudaMemsetAsync(base + L.wh, 0, (size_t)64 * p.C * 2, st), "pm wh memset");
+    PMG_CUDA_OK(cudaMemsetAsync(base + L.bh, 0, 64 * 4, st), "pm bh memset");
+    bf16* wh = reinterpret_cast<bf16*>(base + L.wh);
+    float* bh = reinterpret_cast<float*>(base + L.bh);
+    for (int t = 0; t < p.ntask; ++t) {
+        const int n = p.cls_off[t + 1] - p.cls_off[t];
+        pm_cvt_kernel<<<(p.C + 255) / 256, 256, 0, st>>>(prm[i], wh + (size_t)t * p.C, p.C);
+        pm_copy_kernel<<<1, 32, 0, st>>>(prm[i + 1], bh + t, 1);
+        pm_cvt_kernel<<<(n * p.C + 255) / 256, 256, 0, st>>>(prm[i + 2], wh + (size_t)(p.ntask + p.cls_off[t]) * p.C, n * p.C);
+        i += 3;
+    }
+    PMG_LAUNCH_OK("pm_pack");
+    return PMG_OK;
+}
+
+size_t pm_workspace_bytes(const pm_config* cfg, int B, int H, int W) {
+    const PmPlan p = pm_plan(cfg);
+    if (!p.ok || B < 1) return 0;
+    const PmShape s = pm_shape(p, H, W);
+    if (!s.ok) return 0;
+    return pm_ws(p, s, B < PM_CHUNK ? B : PM_CHUNK).total;
+}
+
+int pm_forward(const pm_config* cfg, const void* packed, const void* x, int x_dtype, int B, int H, int W, float* logits,
+               float* attn, float* feats, void* workspace, size_t workspace_bytes, unsigned flags, pmg_stream_t stream) {
+    (void)flags;
+    const PmPlan p = pm_plan(cfg);
+    if (!p.ok || !packed || !x || !logits || !workspace) return PMG_ERR_BAD_ARG;
+    if (x_dtype != PMG_F32 && x_dtype != PMG_BF16) return PMG_ERR_BAD_ARG;
+    if (B < 1) return PMG_ERR_BAD_SHAPE;
+    const PmShape s = pm_shape(p, H, W);
+    if (!s.ok) return PMG_ERR_BAD_SHAPE;
+    {
+        int dev = 0, major = 0;
+        PMG_CUDA_OK(cudaGetDevice(&dev), "getdevice");
+        PMG_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev), "attr");
+        if (major != 10) return PMG_ERR_ARCH;
+    }
+    const int Bc_max = B < PM_CHUNK ? B : PM_CHUNK;
+    const PmWs w = pm_ws(p, s, Bc_max);
+    if (workspace_bytes < w.total) return PMG_ERR_WORKSPACE;
+    const PmPacked L = pm_packed(p);
+    const char* pk = reinterpret_cast<const char*>(packed);
+    char* ws = reinterpret_cast<char*>(workspace);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    auto Hb = [&](size_t off) { return reinterpret_cast<bf16*>(ws + off); };
+    const int Hf = s.h[p.n_layers], Wf = s.w[p.n_layers], HWf = Hf * Wf;
+    const size_t img_elems = (size_t)cfg->input_nc * H * W;
+    for (int b0 = 0; b0 < B; b0 += PM_CHUNK) {
+        const int Bc = min(PM_CHUNK, B - b0);
+        const char* xb = reinterpret_cast<const char*>(x) + (size_t)b0 * img_elems * (x_dtype == PMG_F32 ? 4 : 2);
+        int rc;
+        for (int l = 0; l < p.n_layers; ++l) {
+            const PmLayer& y = p.layer[l];
+            const int Ho = s.h[l + 1], Wo = s.w[l + 1];
+            const int rows = Bc * Ho * Wo;
+            if (l == 0) {
+                const size_t n = (size_t)rows * (y.Kp / 8);
+                if (x_dtype == PMG_F32)
+                    pm_im2col_first_kernel<true><<<grid1d(n), 256, 0, st>>>(xb, Hb(w.a_hi), Hb(w.a_lo), Bc, y.cin, H, W, Ho, Wo, y.stride, y.Kp);
+                else
+                    pm_im2col_first_kernel<false><<<grid1d(n), 256, 0, st>>>(xb, Hb(w.a_hi), Hb(w.a_lo), Bc, y.cin, H, W, Ho, Wo, y.stride, y.Kp);
+            } else {
+                const size_t n = (size_t)rows * 16 * (y.cin / 8);
+                pm_im2col_kernel<<<grid1d(n), 256, 0, st>>>(Hb(w.act_hi[(l - 1) & 1]), Hb(w.act_lo[(l - 1) & 1]), Hb(w.a_hi), Hb(w.a_lo), Bc,
+                                                            y.cin, s.h[l], s.w[l], Ho, Wo, y.stride);
+            }
+            PMG_LAUNCH_OK("pm im2col");
+            float* conv = reinterpret_cast<float*>(ws + w.conv);
+            if ((rc = pm_conv_gemm(Hb(w.a_hi), Hb(w.a_lo), y.Kp, reinterpret_cast<const bf16*>(pk + L.w[l]), rows, y.cout, conv,
+                                   reinterpret_cast<const float*>(pk + L.bias[l]), st)))
+                return rc;
+            const bool last = l == p.n_layers - 1;
+            pm_instnorm_kernel<<<dim3(y.cout / 32, Bc), 256, 0, st>>>(conv, reinterpret_cast<const float*>(pk + L.gamma[l]),
+                                                                      reinterpret_cast<const float*>(pk + L.beta[l]), Hb(w.act_hi[l & 1]),
+                                                                      Hb(w.act_lo[l & 1]),
+                                                                      (last && feats) ? feats + (size_t)b0 * HWf * p.C : nullptr,
+                                                                      Ho * Wo, y.cout);
+            PMG_LAUNCH_OK("pm instnorm");
+        }
+        const int lf = (p.n_layers - 1) & 1;
+        float* sc = reinterpret_cast<float*>(ws + w.sc);
+        if ((rc = pm_gemm<64>(Hb(w.act_hi[lf]), Hb(w.act_lo[lf]), p.C, pk + L.wh, Bc * HWf, 64, sc,
+                              reinterpret_cast<const float*>(pk + L.bh), st)))
+            return rc;
+        PmFinishArgs a;
+        a.sc = sc; a.logits = logits + (size_t)b0 * p.ncls_total; a.attn = attn ? attn + (size_t)b0 * p.ntask * HWf : nullptr;
+        a.B = Bc; a.HW = HWf; a.ntask = p.ntask; a.ncls_total = p.ncls_total; a.ablate = cfg->ablate_attention;
+        a.inv_tau = 1.f / cfg->attn_tau;
+        for (int t = 0; t <= p.ntask; ++t) a.cls_off[t] = p.cls_off[t];
+        pm_heads_finish_kernel<<<(Bc * p.ntask + 3) / 4, 128, 0, st>>>(a);
+        PMG_LAUNCH_OK("pm heads finish");
+    }
+    return PMG_OK;
+}
+
+}  // extern "C"

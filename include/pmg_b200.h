@@ -134,6 +134,40 @@ int pmg_forward_profile(const pmg_config* cfg, const void* packed, const void* x
 int pmg_gram_batched(const void* F, int f_dtype, int B, int C, int HW, float scale, float* G,
                      pmg_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * PM model (PatchGAN multi-task, no Gram branch) — BASELINE.json configs[3].
+ * Reference boundary: Models/models_PM.py:79-194 class MultiTaskPatchGAN (forward :159-194,
+ * TaskHeadImproved.forward :54-76); built by test_PM.py:153-164 with ndf=64, norm="instance".
+ * Supported: norm="instance", attn_use_se=false, attn_softmax_spatial=true (the committed
+ * hyperparameters_PM.json); anything else is rejected by the host module at construction.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct pm_config {
+    int32_t input_nc;            /* 3 */
+    int32_t ndf;                 /* 64; must be a multiple of 32 */
+    float patch_size;            /* 73: drives the layer-count loop (models_PM.py:121-132) */
+    int32_t n_tasks;
+    int32_t ncls[PMG_MAX_TASKS]; /* classes per task, tasks_dict order */
+    float attn_tau;              /* 0.7 */
+    int32_t ablate_attention;    /* 1 = uniform attention (GAP), models_PM.py:59-63 */
+} pm_config;
+
+/* Parameter order for pm_pack_weights (fp32, torch layouts, = reference state_dict order):
+ *   per trunk conv: conv.weight (Cout,Cin,4,4), conv.bias, instnorm.weight, instnorm.bias
+ *   per task:       attn_conv.weight (1,C,1,1), attn_conv.bias (1), cls_conv.weight (ncls,C,1,1) */
+int pm_param_count(const pm_config* cfg);
+size_t pm_packed_bytes(const pm_config* cfg);
+int pm_pack_weights(const pm_config* cfg, const float* const* params, int n_params, void* packed,
+                    size_t packed_bytes, pmg_stream_t stream);
+size_t pm_workspace_bytes(const pm_config* cfg, int B, int H, int W);
+/* spatial size (Hf, Wf) and channel count C of the trunk output for an H×W input; returns pmg_status */
+int pm_feature_shape(const pm_config* cfg, int H, int W, int* Hf, int* Wf, int* C);
+/* The forward pass — replaces MultiTaskPatchGAN.forward (models_PM.py:159-194).
+ *   logits (B, sum(ncls)) fp32, task-major columns; attn optional (B, n_tasks, Hf, Wf) fp32 = the per-task
+ *   spatial attention A of return_full=True; feats optional (B, Hf, Wf, C) fp32 pixel-major trunk output. */
+int pm_forward(const pm_config* cfg, const void* packed, const void* x, int x_dtype, int B, int H, int W,
+               float* logits, float* attn, float* feats, void* workspace, size_t workspace_bytes,
+               unsigned flags, pmg_stream_t stream);
+
 /* Building block of the fast path, exported for unit tests and micro-benchmarks: one tcgen05 + TMA GEMM
  *   out[M,N] (fp32) = (a_hi[M,K] + a_lo[M,K]) · b[N,K]^T      bf16 row-major operands, a_lo may be null
  * bn = N-tile (32, 64, 96, 128 or 192; N % bn == 0), K % 64 == 0.  splits > 1 writes split-K partial sums

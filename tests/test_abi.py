@@ -12,7 +12,7 @@ from helpers import ROOT, load_contract
 def _declared_functions():
     src = open(os.path.join(ROOT, "include", "pmg_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(pmg_[a-z_0-9]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(pmg?_[a-z_0-9]+)\s*\(", src)))
 
 
 def test_header_symbols_exported():
