@@ -162,7 +162,7 @@ def main_pm():
                 "n_params": int(sum(p.numel() for p in model.parameters()))}
     with open(os.path.join(HERE, "pm_contract.json"), "w") as f:
         json.dump(contract, f, indent=1)
-    small = {"ndf": 16, "norm": "instance", "patch_size": 16, "attn_tau": 0.5, "attn_use_se": False, "attn_softmax_spatial": True}
+    small = {"ndf": 32, "norm": "instance", "patch_size": 16, "attn_tau": 0.5, "attn_use_se": False, "attn_softmax_spatial": True}
     run_pm_case("pm_small_b3_40x52", small, {"alpha": 3, "beta": 2}, seed=6, batch=3, h=40, w=52)
     with open(os.path.join(HERE, "pm_small_contract.json"), "w") as f:
         json.dump({"hparams": small, "tasks": {"alpha": ["a", "b", "c"], "beta": ["x", "y"]}}, f, indent=1)
