@@ -58,9 +58,13 @@ gram96_tc_kernel(const float* __restrict__ chan, __nv_bfloat16* __restrict__ g_h
     pdl_trigger();
     pdl_wait();          // chan comes from the previous kernel
 
-    if (warp < 3) {
-        // ===== loaders: thread = channel =====
-        const int ch = threadIdx.x;
+    const bool loader_a = warp < 3;                               // tokens with even local index
+    const bool loader_b = warp >= 4 && (warp & 3) == 3;          // warps 7, 11, 15 (no TMEM rows to drain): odd tokens
+    if (loader_a || loader_b) {
+        // ===== loaders: two groups of 96 threads (thread = channel) alternate tokens, so two tokens' global
+        // loads are in flight per CTA =====
+        const int grp = loader_a ? 0 : 1;
+        const int ch = loader_a ? threadIdx.x : ((warp - 7) >> 2) * 32 + lane;
         float v[25];
         auto load_token = [&](int tok) {
             const int b = tok / 9, k = tok % 9, py = k / 3, px = k % 3;
@@ -71,10 +75,10 @@ gram96_tc_kernel(const float* __restrict__ chan, __nv_bfloat16* __restrict__ g_h
                 v[n] = __ldg(src + (y * 14 + x) * 96);
             }
         };
-        int tok = blockIdx.x;
+        const int step = 2 * gridDim.x;
+        int tok = blockIdx.x + grp * gridDim.x;
         if (tok < n_tokens) load_token(tok);
-        uint32_t it = 0;
-        for (; tok < n_tokens; tok += gridDim.x, ++it) {
+        for (uint32_t it = grp; tok < n_tokens; tok += step, it += 2) {
             const int s = it % GRAM_STAGES;
             const uint32_t ph = (it / GRAM_STAGES) & 1;
             uint32_t hi[16], lo[16];
@@ -82,8 +86,7 @@ gram96_tc_kernel(const float* __restrict__ chan, __nv_bfloat16* __restrict__ g_h
             for (int j = 0; j < 12; ++j) split_bf16x2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
             split_bf16x2(v[24], 0.f, hi[12], lo[12]);
             hi[13] = hi[14] = hi[15] = 0; lo[13] = lo[14] = lo[15] = 0;
-            const int nxt = tok + gridDim.x;
-            if (nxt < n_tokens) load_token(nxt);          // prefetch while waiting for the stage
+            if (tok + step < n_tokens) load_token(tok + step);   // prefetch this group's next token
             mbar_wait(&empty_bar[s], ph ^ 1);
             uint8_t* ph_base = smem + s * 2 * GRAM_PLANE + ch * 128;
 #pragma unroll
@@ -124,7 +127,7 @@ gram96_tc_kernel(const float* __restrict__ chan, __nv_bfloat16* __restrict__ g_h
         // ===== epilogue: 9 warps, warp w ↔ TMEM lane quarter q = w%4 (rows 32q..32q+31, q < 3) and the
         // 32-column chunk (w-4)/4; one warp per (quarter, chunk) keeps three times as many warps in flight =====
         const int q = warp & 3;
-        if (q < 3) {
+        {
             const int c0 = ((warp - 4) >> 2) * 32;
             uint8_t* wbuf = s_stage + (warp - 4) * 4096;
             const int sr = lane >> 3, sc = lane & 7;
