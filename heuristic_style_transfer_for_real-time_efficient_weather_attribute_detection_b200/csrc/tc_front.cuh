@@ -12,7 +12,7 @@
 //     with W0' the conv0 weight laid out block-sparse over the 4 column offsets sx (each output column group sx
 //     only sees its own 4 of the 16 input columns).  12 MMAs (M128 N128 K16) per sy; the 4× zero padding is
 //     free: the tensor pipe is far from being the bottleneck of this layer.
-//   * epilogue 0 (8 warps): TMEM → BN scale/shift → LeakyReLU → hi/lo bf16 split → written as conv1's A operand
+//   * epilogue 0 (16 warps): TMEM → BN scale/shift → LeakyReLU → hi/lo bf16 split → written as conv1's A operand
 //     (K-major, 128-byte swizzle) for the K slice (sy, sx, c).
 //   * conv1 accumulates that K slice:  D1[pixel, 64] += A1(hi) · W1[sy] + A1(lo) · W1[sy]   (16 MMAs, M128 N64 K16).
 //
@@ -25,7 +25,7 @@
 
 namespace tc {
 
-constexpr int FRONT_THREADS = 320;                 // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int FRONT_THREADS = 576;                 // warp 0 TMA, warp 1 MMA, warps 2-17 epilogue (lane quarter × 32-column group)
 constexpr int FR_W0_BYTES = 3 * 128 * 128;         // 48 KB: 3 K-blocks × [128 rows × 128 B]
 constexpr int FR_W1_BYTES = 8 * 64 * 128;          // 64 KB: (sy, kb) × [64 rows × 128 B]
 constexpr int FR_A0_SLOT = 4096;                   // one TMA box (98 rows × 32 B = 3136 B) per 4 KB slot
@@ -90,8 +90,8 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     if (threadIdx.x == 0) {
         prefetch_tmap(&tmX); prefetch_tmap(&tmW0); prefetch_tmap(&tmW1);
         for (int i = 0; i < 3; ++i) { mbar_init(&a0_full[i], 1); mbar_init(&a0_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&d0_full[i], 1); mbar_init(&d0_empty[i], 8); }
-        mbar_init(a1_ready, 8); mbar_init(a1_free, 1); mbar_init(d1_full, 1); mbar_init(d1_empty, 8); mbar_init(w_bar, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&d0_full[i], 1); mbar_init(&d0_empty[i], 16); }
+        mbar_init(a1_ready, 16); mbar_init(a1_free, 1); mbar_init(d1_full, 1); mbar_init(d1_empty, 16); mbar_init(w_bar, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -181,11 +181,12 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         }
     } else {
         // ===================== epilogue warps =====================
-        const int q = warp & 3;                       // TMEM lane quarter
-        const int half = (warp - 2) >> 2;             // 0: D0 columns 0..63 (sx 0,1 → K block 0), 1: 64..127 (sx 2,3 → K block 1)
+        // 16 warps: TMEM lane quarter q = warp % 4, 32-column group cg = (warp-2)/4 = conv0 column offset sx
+        const int q = warp & 3;
+        const int cg = (warp - 2) >> 2;               // sx: D0 columns cg*32 .. +31 → K block cg/2, 64-byte half cg%2
         const int m = q * 32 + lane;                  // tile row = conv1 pixel index inside the tile
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        uint8_t* a1row = sA1 + half * 16384 + m * 128;
+        uint8_t* a1row = sA1 + (cg >> 1) * 16384 + m * 128;
         uint32_t g = 0, lt = 0;
         pdl_wait();          // act1 planes are still being read by the previous forward's conv2 until it completes
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
@@ -193,67 +194,58 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                 const uint32_t as = g & 1, aph = (g >> 1) & 1;
                 mbar_wait(&d0_full[as], aph);
                 tc_fence_after();
-                uint32_t H[2][16], L[2][16];
+                uint32_t r[32], H[16], L[16];
+                tmem_ld_32x32b_x32(tD0 + as * 128 + lane_addr + (uint32_t)(cg * 32), r);
+                tmem_ld_wait();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d0_empty[as]);
 #pragma unroll
-                for (int ck = 0; ck < 2; ++ck) {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(tD0 + as * 128 + lane_addr + (uint32_t)(half * 64 + ck * 32), r);
-                    tmem_ld_wait();
-                    if (ck == 1) {
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&d0_empty[as]);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float v0 = fmaf(__uint_as_float(r[2 * j]), s0[2 * j], h0[2 * j]);
-                        float v1 = fmaf(__uint_as_float(r[2 * j + 1]), s0[2 * j + 1], h0[2 * j + 1]);
-                        v0 = fmaxf(v0, 0.2f * v0);
-                        v1 = fmaxf(v1, 0.2f * v1);
-                        split_bf16x2(v0, v1, H[ck][j], L[ck][j]);
-                    }
+                for (int j = 0; j < 8; ++j) {
+                    const float4 sc = *reinterpret_cast<const float4*>(s0 + 4 * j);
+                    const float4 sh = *reinterpret_cast<const float4*>(h0 + 4 * j);
+                    float v0 = fmaf(__uint_as_float(r[4 * j]), sc.x, sh.x), v1 = fmaf(__uint_as_float(r[4 * j + 1]), sc.y, sh.y);
+                    float v2 = fmaf(__uint_as_float(r[4 * j + 2]), sc.z, sh.z), v3 = fmaf(__uint_as_float(r[4 * j + 3]), sc.w, sh.w);
+                    v0 = fmaxf(v0, 0.2f * v0); v1 = fmaxf(v1, 0.2f * v1); v2 = fmaxf(v2, 0.2f * v2); v3 = fmaxf(v3, 0.2f * v3);
+                    split_bf16x2(v0, v1, H[2 * j], L[2 * j]);
+                    split_bf16x2(v2, v3, H[2 * j + 1], L[2 * j + 1]);
                 }
                 if (g > 0) mbar_wait(a1_free, (g - 1) & 1);        // conv1 MMAs of the previous slice have read A1
 #pragma unroll
-                for (int ck = 0; ck < 2; ++ck)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int sw = ((ck * 4 + j) ^ (m & 7)) << 4;
-                        *reinterpret_cast<uint4*>(a1row + sw) = make_uint4(H[ck][4 * j], H[ck][4 * j + 1], H[ck][4 * j + 2], H[ck][4 * j + 3]);
-                        *reinterpret_cast<uint4*>(a1row + 32768 + sw) = make_uint4(L[ck][4 * j], L[ck][4 * j + 1], L[ck][4 * j + 2], L[ck][4 * j + 3]);
-                    }
+                for (int j = 0; j < 4; ++j) {
+                    const int sw = (((cg & 1) * 4 + j) ^ (m & 7)) << 4;
+                    *reinterpret_cast<uint4*>(a1row + sw) = make_uint4(H[4 * j], H[4 * j + 1], H[4 * j + 2], H[4 * j + 3]);
+                    *reinterpret_cast<uint4*>(a1row + 32768 + sw) = make_uint4(L[4 * j], L[4 * j + 1], L[4 * j + 2], L[4 * j + 3]);
+                }
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a1_ready);
             }
-            // ---- epilogue 1: act1 = LeakyReLU(BN(D1)), this warp's 32 of the 64 channels ----
+            // ---- epilogue 1: act1 = LeakyReLU(BN(D1)), this warp's 16 of the 64 channels ----
             mbar_wait(d1_full, lt & 1);
             tc_fence_after();
-            uint32_t r[32];
-            tmem_ld_32x32b_x32(tD1 + lane_addr + (uint32_t)(half * 32), r);
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(tD1 + lane_addr + (uint32_t)(cg * 16), r);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(d1_empty);
             if (m < 98) {
-                uint32_t hi[16], lo[16];
+                uint32_t hi[8], lo[8];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int c = half * 32 + 2 * j;
+                for (int j = 0; j < 8; ++j) {
+                    const int c = cg * 16 + 2 * j;
                     float v0 = fmaf(__uint_as_float(r[2 * j]), s1[c], h1[c]);
                     float v1 = fmaf(__uint_as_float(r[2 * j + 1]), s1[c + 1], h1[c + 1]);
                     v0 = fmaxf(v0, 0.2f * v0);
                     v1 = fmaxf(v1, 0.2f * v1);
                     split_bf16x2(v0, v1, hi[j], lo[j]);
                 }
-                const size_t o = ((size_t)(tile >> 1) * 196 + (tile & 1) * 98 + m) * 64 + half * 32;
+                const size_t o = ((size_t)(tile >> 1) * 196 + (tile & 1) * 98 + m) * 64 + cg * 16;
                 uint4* dh = reinterpret_cast<uint4*>(p.act1_hi + o);
                 uint4* dl = reinterpret_cast<uint4*>(p.act1_lo + o);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    dh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                    dl[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-                }
+                dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+                dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
             }
         }
         tc_fence_before();
