@@ -417,7 +417,7 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
     if (fused_front) {
         // conv0 + conv1 (+ both BN + LeakyReLU) in one TMA-fed tcgen05 kernel (tc_front.cuh)
         CUtensorMap tx, tw0, tw1;
-        if ((rc = tc::make_tmap_image5d(&tx, x, B))) return rc;
+        if ((rc = tc::make_tmap_image_rows(&tx, x, B))) return rc;
         if ((rc = tc::make_tmap_bf16(&tw0, Wb(f.w0x), 128, 192, 192, 128))) return rc;
         if ((rc = tc::make_tmap_bf16(&tw1, Wb(f.w1x), 512, 64, 64, 64))) return rc;
         static bool attr_set = false;

@@ -5,9 +5,14 @@
 // Tile = 98 conv1 pixels (7 rows × 14 cols of the 14×14 map) of one image, 2 tiles per image; UMMA M = 128
 // (rows 98..127 are don't-care).  For each of the 4 row offsets sy of conv1's 4×4 window:
 //
-//   * TMA (5-D tensor map over the NCHW bf16 image, dims x16|px|y16|py|b·c, box 16×14×1×7×1, SWIZZLE_32B)
-//     drops, per (channel c, kernel row ky), a [98 pixels × 16 input columns] slab straight into smem in the
-//     K-major 32-byte-swizzled UMMA operand layout: no im2col, no register staging, every box fully in bounds.
+//   * TMA (4-D tensor map over the NCHW bf16 image, dims x|y16|py|b·c, box 224×1×7×1, no swizzle) drops, per
+//     (channel c, kernel row ky), 7 whole image rows = a [98 pixels × 16 input columns] slab straight into smem
+//     as 98 rows of 32 bytes: no im2col, no register staging, every box fully in bounds, 448-byte runs.
+//     The MMA reads the slab as a K-major SWIZZLE_32B operand.  The data are NOT swizzled, so for slab rows with
+//     bit 2 set (r & 4) the hardware's chunk XOR hands the MMA the two 16-byte halves (input columns 0-7 / 8-15)
+//     exchanged.  W0' is block-sparse over the column offset sx (4 columns each), so for those pixels the
+//     accumulator column group cg simply holds the conv0 output of column offset sx = cg ^ 2; epilogue 0
+//     (thread = pixel row) files it under the right K slice of conv1.  Nothing is moved twice.
 //   * conv0 as a GEMM over those slabs:  D0[pixel, (sx,co)] = Σ_{c,ky} A[pixel, 16 cols] · W0'[(sx,co), (c,ky,16 cols)]
 //     with W0' the conv0 weight laid out block-sparse over the 4 column offsets sx (each output column group sx
 //     only sees its own 4 of the 16 input columns).  12 MMAs (M128 N128 K16) per sy; the 4× zero padding is
@@ -40,12 +45,12 @@ constexpr int FR_OFF_BAR = FR_OFF_A1 + FR_A1_BYTES;
 constexpr int FR_OFF_PRM = FR_OFF_BAR + 256;
 constexpr int FRONT_SMEM = FR_OFF_PRM + (32 + 32 + 64 + 64) * 4 + 1024;
 
-__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1,
-                                            int32_t c2, int32_t c3, int32_t c4) {
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1,
+                                            int32_t c2, int32_t c3) {
     asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
-          "r"(c3), "r"(c4)
+          "r"(c3), "l"(kEvictFirst)
         : "memory");
 }
 
@@ -127,7 +132,7 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                         mbar_expect_tx(&a0_full[s], 4 * FR_BOX_BYTES);
 #pragma unroll
                         for (int ky = 0; ky < 4; ++ky)
-                            tma_load_5d(sA0 + s * FR_A0_STAGE + ky * FR_A0_SLOT, &tmX, &a0_full[s], 0, 0, sy * 4 + ky, py0, b * 3 + c);
+                            tma_load_4d(sA0 + s * FR_A0_STAGE + ky * FR_A0_SLOT, &tmX, &a0_full[s], 0, sy * 4 + ky, py0, b * 3 + c);
                     }
             }
         }
@@ -183,10 +188,11 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         // ===================== epilogue warps =====================
         // 16 warps: TMEM lane quarter q = warp % 4, 32-column group cg = (warp-2)/4 = conv0 column offset sx
         const int q = warp & 3;
-        const int cg = (warp - 2) >> 2;               // sx: D0 columns cg*32 .. +31 → K block cg/2, 64-byte half cg%2
+        const int cg = (warp - 2) >> 2;               // D0 columns cg*32 .. +31
         const int m = q * 32 + lane;                  // tile row = conv1 pixel index inside the tile
+        const int sx = cg ^ ((m >> 1) & 2);           // conv0 column offset those columns hold for this row (header: half swap)
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        uint8_t* a1row = sA1 + (cg >> 1) * 16384 + m * 128;
+        uint8_t* a1row = sA1 + (sx >> 1) * 16384 + m * 128;   // conv1 K slice (sy, sx, c): K block sx/2, 64-byte half sx%2
         uint32_t g = 0, lt = 0;
         pdl_wait();          // act1 planes are still being read by the previous forward's conv2 until it completes
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {

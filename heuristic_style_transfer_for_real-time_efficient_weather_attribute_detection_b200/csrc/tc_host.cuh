@@ -62,20 +62,24 @@ inline int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint6
     return PMG_OK;
 }
 
-// 5-D view of a bf16 NCHW image batch (B,3,224,224) for the fused front end (tc_front.cuh):
-//   dims (innermost first)  x16 = 16 | px = 14 | y16 = 16 | py = 14 | b·c = 3B     (x = 16·px + x16, y = 16·py + y16)
-//   box                     16 × 14 × 1 × 7 × 1  = the 16 input columns of 98 conv1 pixels for one (channel, row)
-inline int make_tmap_image5d(CUtensorMap* m, const void* base, int B) {
+// 4-D view of a bf16 NCHW image batch (B,3,224,224) for the fused front end (tc_front.cuh):
+//   dims (innermost first)  x = 224 | y16 = 16 | py = 14 | b·c = 3B          (y = 16·py + y16)
+//   box                     224 × 1 × 7 × 1  = 7 whole image rows (448 contiguous bytes each) = the 16 input columns
+//                           of 98 conv1 pixels for one (channel, kernel row); NO swizzle, so TMA moves 448-byte
+//                           runs (a swizzled 16-column inner box made it move 98 separate 32-byte rows per box,
+//                           which bounded the whole kernel).  The UMMA descriptor still reads the slab with the
+//                           32-byte swizzle; tc_front.cuh explains how the resulting half swap is absorbed.
+inline int make_tmap_image_rows(CUtensorMap* m, const void* base, int B) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { pmg::set_cuda_error(cudaErrorNotSupported, "cuTensorMapEncodeTiled entry point"); return PMG_ERR_CUDA; }
-    cuuint64_t dims[5] = {16, 14, 16, 14, (cuuint64_t)3 * B};
-    cuuint64_t strides[4] = {32, 448, 7168, 100352};
-    cuuint32_t box[5] = {16, 14, 1, 7, 1};
-    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+    cuuint64_t dims[4] = {224, 16, 14, (cuuint64_t)3 * B};
+    cuuint64_t strides[3] = {448, 7168, 100352};
+    cuuint32_t box[4] = {224, 1, 7, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { pmg::set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(5d image)"); return PMG_ERR_CUDA; }
+    if (r != CUDA_SUCCESS) { pmg::set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(image rows)"); return PMG_ERR_CUDA; }
     return PMG_OK;
 }
 
