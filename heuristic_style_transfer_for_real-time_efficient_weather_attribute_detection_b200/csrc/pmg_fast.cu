@@ -18,6 +18,7 @@
 #include "tc_host.cuh"
 #include "tc_gram.cuh"
 #include "tc_front.cuh"
+#include "tc_encoder.cuh"
 
 namespace pmg {
 
@@ -34,6 +35,7 @@ struct FastW {
     size_t win[8], wo[8], wf1[8], wf2[8];
     size_t w0x, w1x;                     // fused front end: block-sparse conv0 [128][192], conv1 as (sy,kb) blocks [512][64]
     size_t wq;                           // [64][192]: rows 0..ntask-1 task queries, then the ncls_total classifier rows, zero pad
+    size_t wenc;                         // fused token stage: pre-swizzled weight stream (tc_encoder.cuh), nl layers + heads block
     size_t total;
 };
 
@@ -48,6 +50,7 @@ static FastW fast_w(const Plan& p) {
     }
     f.wq = take(64 * 192);
     f.w0x = take(128 * 192); f.w1x = take(512 * 64);
+    f.wenc = take(((size_t)p.nl * tc::ENC_LAYER_BYTES + tc::ENC_STAGE) / sizeof(bf16));
     f.total = o;
     return f;
 }
@@ -134,6 +137,43 @@ int pack_fast(const Plan& p, const PackedLayout& L, const float* const* prm, cha
         const int n = p.cls_off[t + 1] - p.cls_off[t];
         cvt(prm[i], f.wq + (size_t)(p.ntask + p.cls_off[t]) * 192 * sizeof(bf16), (size_t)n * 192);
         i += 2;
+    }
+    // fused token stage: every encoder weight as pre-swizzled [rows × 64 K] blocks in the order the kernel's
+    // MMA warp consumes them (tc_encoder.cuh), then the heads operand
+    {
+        uint8_t* stream = reinterpret_cast<uint8_t*>(base + f.wenc);
+        static const int ffn_order[12][2] = {{1, 0}, {1, 1}, {2, 0}, {1, 2}, {2, 1}, {1, 3}, {2, 2}, {1, 4}, {2, 3}, {1, 5}, {2, 4}, {2, 5}};
+        int pi = 18;
+        for (int l = 0; l < p.nl; ++l, pi += 12) {
+            tc::EncPackArgs a{};
+            int n = 0;
+            const unsigned lb = (unsigned)((size_t)l * tc::ENC_LAYER_BYTES);
+            auto add = [&](const void* src, int bf, int ld, int r0, int r1, int r2, int seg, int nrows, int k0, unsigned dst) {
+                tc::EncPackDesc& d = a.d[n++];
+                d.src = src; d.src_bf16 = bf; d.ld = ld; d.row0[0] = r0; d.row0[1] = r1; d.row0[2] = r2; d.seg = seg;
+                d.nrows = nrows; d.k0 = k0; d.dst = dst;
+            };
+            for (int h = 0; h < 4; ++h)
+                for (int kb = 0; kb < 3; ++kb)
+                    add(prm[pi], 0, 192, 48 * h, 192 + 48 * h, 384 + 48 * h, 48, 144, 64 * kb, lb + tc::ENC_L_QKV + (h * 3 + kb) * tc::ENC_QKV_BLK);
+            for (int kb = 0; kb < 3; ++kb) add(prm[pi + 2], 0, 192, 0, 0, 0, 192, 192, 64 * kb, lb + tc::ENC_L_OUT + kb * tc::ENC_STAGE);
+            for (int i = 0; i < 12; ++i) {
+                const int c = ffn_order[i][1];
+                const unsigned sb = lb + tc::ENC_L_FFN + i * tc::ENC_STAGE;
+                if (ffn_order[i][0] == 1)
+                    for (int kb = 0; kb < 3; ++kb) add(prm[pi + 4], 0, 192, 64 * c, 0, 0, 64, 64, 64 * kb, sb + kb * tc::ENC_KB);
+                else
+                    add(prm[pi + 6], 0, 384, 0, 0, 0, 192, 192, 64 * c, sb);
+            }
+            tc::enc_pack_kernel<<<n, 256, 0, st>>>(a, stream);
+        }
+        tc::EncPackArgs a{};
+        for (int kb = 0; kb < 3; ++kb) {
+            tc::EncPackDesc& d = a.d[kb];
+            d.src = Bp(f.wq); d.src_bf16 = 1; d.ld = 192; d.row0[0] = d.row0[1] = d.row0[2] = 0; d.seg = 64; d.nrows = 64; d.k0 = 64 * kb;
+            d.dst = (unsigned)((size_t)p.nl * tc::ENC_LAYER_BYTES) + kb * tc::ENC_KB;
+        }
+        tc::enc_pack_kernel<<<3, 256, 0, st>>>(a, stream);
     }
     PMG_LAUNCH_OK("pack_fast");
     return PMG_OK;
@@ -386,7 +426,9 @@ size_t fast_workspace_bytes(const Plan&, const Shape&, int B) { return fast_ws(B
 
 // bf16 input: fused front kernel (1 launch) instead of im2col + conv0 + conv1 (3 launches)
 int fast_launch_count(const Plan& p, const Shape&, int, unsigned flags) {
-    return ((flags & PMG_FLAG_NO_FUSED_FRONT) ? 3 : 1) + 2 + 1 + 1 + 1 + 6 * p.nl + (p.nl > 1 ? p.nl - 1 : 0) + 3;
+    const int front = (flags & PMG_FLAG_NO_FUSED_FRONT) ? 3 : 1;
+    if (!(flags & PMG_FLAG_NO_FUSED_ENCODER)) return front + 2 + 1 + 1 + 1;   // conv2, chan_proj, Gram, token_proj, token stage
+    return front + 2 + 1 + 1 + 1 + 6 * p.nl + (p.nl > 1 ? p.nl - 1 : 0) + 3;
 }
 
 template <int BN, int NA, int EPI, int ACT>
@@ -488,6 +530,31 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
                    Ff(w.partial), nullptr, nullptr, nullptr, nullptr, nullptr, w.splits, pstride, st)))
         return rc;
     PMG_MARK(tm, "token_proj");
+    if (!(flags & PMG_FLAG_NO_FUSED_ENCODER)) {
+        // split-K reduce + bias, the whole transformer, task pooling and the heads: one kernel (tc_encoder.cuh)
+        static bool attr_set = false;
+        if (!attr_set) {
+            PMG_CUDA_OK(cudaFuncSetAttribute(tc::encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::ENC_SMEM), "encoder smem attr");
+            attr_set = true;
+        }
+        tc::EncParams e{};
+        e.wstream = reinterpret_cast<const uint8_t*>(fb + f.wenc);
+        e.partial = Ff(w.partial); e.pstride = pstride; e.nsplit = w.splits; e.tok_bias = Pf(L.tok_b);
+        e.cls_bias = Pf(L.cls_b); e.logits = logits;
+        e.tok_in = taps ? taps->tokens_in : nullptr; e.tok_out = taps ? taps->tokens_out : nullptr;
+        e.nl = p.nl; e.B = B; e.ntask = p.ntask; e.ncls_total = p.ncls_total;
+        for (int l = 0; l < p.nl; ++l) {
+            const TfLayerOff& t = L.tf[l];
+            e.layer[l] = {Pf(t.b_in), Pf(t.b_o), Pf(t.b_1), Pf(t.b_2), Pf(t.ln1w), Pf(t.ln1b), Pf(t.ln2w), Pf(t.ln2b)};
+        }
+        for (int t = 0; t < p.ntask; ++t)
+            for (int c = p.cls_off[t]; c < p.cls_off[t + 1]; ++c) e.task_of[c] = (unsigned char)t;
+        const int tiles = (B + tc::ENC_IPT - 1) / tc::ENC_IPT;
+        const int grid = tiles < tc::num_sms() ? tiles : tc::num_sms();
+        PMG_CUDA_OK(tc::launch_pdl(tc::encoder_kernel, dim3(grid), dim3(tc::ENC_THREADS), tc::ENC_SMEM, st, e), "encoder_kernel");
+        PMG_MARK(tm, "encoder_heads");
+        return PMG_OK;
+    }
     {
         const TfLayerOff* t0 = p.nl > 0 ? &L.tf[0] : nullptr;
         PMG_CUDA_OK(tc::launch_pdl(tok_ln_kernel, dim3((T + 3) / 4), dim3(128), 0, st, (const float*)Ff(w.partial), w.splits, pstride,

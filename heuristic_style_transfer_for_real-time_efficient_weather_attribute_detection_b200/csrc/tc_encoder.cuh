@@ -1,0 +1,595 @@
+// tc_encoder.cuh — the whole token stage of the PMG forward in ONE persistent tcgen05 kernel:
+//   token_proj split-K reduce + bias  →  nl × pre-LN TransformerEncoderLayer (d 192, 4 heads × 48, FFN 384, ReLU)
+//   →  task attention pooling + 12 linear heads  →  logits.
+// Reference: models_PMG.py:60-72,144-147,194 (encoder), :47-57 (TaskAttentionPooling), :153-155,198 (heads).
+//
+// Tile = 7 images = 63 token rows (row 63 is a don't-care); B = 1024 gives 147 tiles for the 148 SMs.  The
+// residual stream x of the tile lives in TMEM (columns 0..191, fp32) for the whole kernel: the out-proj and
+// FFN2 MMAs accumulate straight onto it, so the residual adds cost nothing.  Activations that feed an MMA are
+// written by the epilogue warps as two bf16 planes (hi + lo, DESIGN.md "precision") into K-major 128B-swizzled
+// smem operand tiles; all layer weights stream through a 3-stage ring of 24 KB blocks with cp.async.bulk from a
+// pre-swizzled copy (enc_pack_kernel), so one bulk copy lands a ready-to-use UMMA B tile.
+//
+// UMMA M is 128 but only 64 rows are real: operand k-blocks are packed 8 KB apart (64 rows × 128 B), so rows
+// 64..127 of k-block j alias rows 0..63 of k-block j+1 — the MMA computes throw-away rows in TMEM lanes 64..127
+// (rows of D depend only on the same row of A) and smem holds only the real rows.
+//
+// Warp roles (18 warps): 0 = weight producer, 1 = MMA issuer (+ TMEM alloc), warps w with w%4 ∈ {0,1}, w ≥ 4
+// = 8 "compute" warps (TMEM lane quarter q = w%4 holds rows 32q..32q+31; column group g = (w-4)/4), warps with
+// w%4 ∈ {2,3} = 8 "aux" warps that run the 9-token attention core out of shared memory.
+//
+// Per layer:  LN1 → A tile │ per head h: MMA [q_h|k_h|v_h] (N 144, TMEM double-buffered) → compute warps drain
+// (+bias, q·1/√48) to smem fp32 → aux warps: scores, softmax, P·V → O tile (hi/lo) │ out-proj MMA onto x │
+// +bias, LN2 → A tile │ FFN in 6 chunks of 64 hidden units: FFN1 MMA → +bias, ReLU, hi/lo → H chunk tile →
+// FFN2 MMA onto x (chunk c+1's FFN1 runs under chunk c's epilogue) │ +bias.
+// After the last layer: x hi/lo → A tile → one MMA against [queries | classifier rows] (N 64) → softmax-weighted
+// sum over the 9 tokens (the heads are linear in the pooled token) → logits.
+#pragma once
+
+#include "tc_prims.cuh"
+
+namespace tc {
+
+constexpr int ENC_THREADS = 576;
+constexpr int ENC_IPT = 7;                   // images per tile
+constexpr int ENC_ROWS = 63;                 // token rows per tile
+constexpr int ENC_STAGE = 24576;             // weight ring stage
+constexpr int ENC_NSTAGE = 3;
+constexpr int ENC_QKV_LD = 148;              // floats per row of the fp32 [q|k|v] head buffer (144 + 4: conflict-free 16-byte accesses)
+constexpr int ENC_KB = 8192;                 // operand k-block: 64 rows × 128 B
+constexpr int ENC_PLANE = 3 * ENC_KB;        // [64 rows × 192 K] bf16
+constexpr int ENC_OFF_QKV = ENC_NSTAGE * ENC_STAGE;                 // fp32 head buffer; aliased by the FFN hidden chunk tiles
+constexpr int ENC_QKV_BYTES = 64 * ENC_QKV_LD * 4;                  // 37,888 = 37 KB
+constexpr int ENC_OFF_A = ENC_OFF_QKV + ENC_QKV_BYTES;              // LN output / final tokens, hi then lo plane
+constexpr int ENC_OFF_O = ENC_OFF_A + 2 * ENC_PLANE;                // attention output, hi then lo plane
+constexpr int ENC_SC_LD = 65;
+constexpr int ENC_OFF_SC = ENC_OFF_O + 2 * ENC_PLANE;               // [64][65] fp32 heads-GEMM result (also the ≥ 8 KB over-read slack)
+constexpr int ENC_OFF_RED = ENC_OFF_SC + 64 * ENC_SC_LD * 4;        // LayerNorm partial sums: 2 × [4][64] fp32
+constexpr int ENC_OFF_BAR = ENC_OFF_RED + 2 * 4 * 64 * 4;
+constexpr int ENC_SMEM = ENC_OFF_BAR + 256 + 1024;
+
+// weight stream geometry (bytes), per layer
+constexpr int ENC_QKV_BLK = 144 * 128;                               // one k-block of one head's [q|k|v] rows
+constexpr int ENC_L_QKV = 0;
+constexpr int ENC_L_OUT = 12 * ENC_QKV_BLK;                          // 221,184
+constexpr int ENC_L_FFN = ENC_L_OUT + 3 * ENC_STAGE;                 // 294,912
+constexpr int ENC_LAYER_BYTES = ENC_L_FFN + 12 * ENC_STAGE;          // 589,824
+
+struct EncLayerPtrs {
+    const float *b_in, *b_o, *b_1, *b_2, *ln1w, *ln1b, *ln2w, *ln2b;
+};
+struct EncParams {
+    const uint8_t* wstream;          // nl × ENC_LAYER_BYTES + ENC_STAGE (heads), pre-swizzled bf16
+    const float* partial;            // token_proj split-K partial sums [nsplit][T][192]
+    size_t pstride;
+    const float* tok_bias;           // [192]
+    const float* cls_bias;           // [ncls_total]
+    float* logits;                   // [B][ncls_total]
+    float* tok_in;                   // optional taps [T][192]
+    float* tok_out;
+    EncLayerPtrs layer[8];
+    int nsplit, nl, B, ntask, ncls_total;
+    unsigned char task_of[64];
+};
+
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)), "l"(kEvictLast)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// 48 fp32 accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld48(uint32_t taddr, float (&v)[48]) {
+    uint32_t r0[16], r1[16], r2[16];
+    tmem_ld_32x32b_x16(taddr, r0);
+    tmem_ld_32x32b_x16(taddr + 16, r1);
+    tmem_ld_32x32b_x16(taddr + 32, r2);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { v[i] = __uint_as_float(r0[i]); v[16 + i] = __uint_as_float(r1[i]); v[32 + i] = __uint_as_float(r2[i]); }
+}
+__device__ __forceinline__ void tmem_st48(uint32_t taddr, const float (&v)[48]) {
+    uint32_t r[16];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(v[16 * b + i]);
+        tmem_st_32x32b_x16(taddr + 16 * b, r);
+    }
+}
+
+// write 48 values (columns 48g..48g+47 of row m) as hi/lo bf16 into a [64 × 192] K-major SW128 operand tile
+__device__ __forceinline__ void write_operand48(uint8_t* tile_hi, int m, int g, const float (&y)[48]) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split_bf16x2(y[8 * c + 2 * i], y[8 * c + 2 * i + 1], hi[i], lo[i]);
+        const int chunk = 6 * g + c;                       // 16-byte chunk index inside the 384-byte row
+        uint8_t* dst = tile_hi + (chunk >> 3) * ENC_KB + m * 128 + (((chunk & 7) ^ (m & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(dst + ENC_PLANE) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// LayerNorm (in place) over 192 columns held by the 4 column-group threads of a row (48 each); two-pass, fp32.
+__device__ __forceinline__ void layer_norm48(float (&v)[48], float* red, int m, int g,
+                                             const float* __restrict__ w, const float* __restrict__ b) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 48; ++i) s += v[i];
+    red[g * 64 + m] = s;
+    named_bar_sync(1, 256);
+    const float mu = (red[m] + red[64 + m] + red[128 + m] + red[192 + m]) * (1.f / 192.f);
+    float qd = 0.f;
+#pragma unroll
+    for (int i = 0; i < 48; ++i) { const float d = v[i] - mu; qd = fmaf(d, d, qd); }
+    red[256 + g * 64 + m] = qd;
+    named_bar_sync(1, 256);
+    const float var = (red[256 + m] + red[320 + m] + red[384 + m] + red[448 + m]) * (1.f / 192.f);
+    const float rs = 1.f / sqrtf(var + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 48; i += 4) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + 48 * g + i));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(b + 48 * g + i));
+        v[i] = fmaf((v[i] - mu) * rs, w4.x, b4.x);
+        v[i + 1] = fmaf((v[i + 1] - mu) * rs, w4.y, b4.y);
+        v[i + 2] = fmaf((v[i + 2] - mu) * rs, w4.z, b4.z);
+        v[i + 3] = fmaf((v[i + 3] - mu) * rs, w4.w, b4.w);
+    }
+}
+
+__global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sW = smem;
+    float* sQKV = reinterpret_cast<float*>(smem + ENC_OFF_QKV);
+    uint8_t* sH = smem + ENC_OFF_QKV;               // hidden chunk tiles [buf][plane] × 8 KB (FFN phase only)
+    uint8_t* sA = smem + ENC_OFF_A;
+    uint8_t* sO = smem + ENC_OFF_O;
+    float* sSC = reinterpret_cast<float*>(smem + ENC_OFF_SC);
+    float* sRed = reinterpret_cast<float*>(smem + ENC_OFF_RED);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ENC_OFF_BAR);
+    uint64_t* w_full = bars;            // [3]
+    uint64_t* w_empty = bars + 3;       // [3]
+    uint64_t* a_ready = bars + 6;
+    uint64_t* dq_full = bars + 7;       // [2]
+    uint64_t* dq_empty = bars + 9;      // [2]
+    uint64_t* qkv_full = bars + 11;
+    uint64_t* qkv_empty = bars + 12;
+    uint64_t* o_ready = bars + 13;
+    uint64_t* x_full = bars + 14;
+    uint64_t* dh_full = bars + 15;      // [2]
+    uint64_t* dh_empty = bars + 17;     // [2]
+    uint64_t* h_ready = bars + 19;      // [2]
+    uint64_t* h_free = bars + 21;       // [2]
+    uint64_t* sc_full = bars + 23;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wq = warp & 3;
+    const int n_tiles = (p.B + ENC_IPT - 1) / ENC_IPT;
+    const int T = p.B * 9;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 3; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+        mbar_init(a_ready, 8);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&dq_full[i], 1); mbar_init(&dq_empty[i], 6);
+            mbar_init(&dh_full[i], 1); mbar_init(&dh_empty[i], 8);
+            mbar_init(&h_ready[i], 8); mbar_init(&h_free[i], 1);
+        }
+        mbar_init(qkv_full, 6); mbar_init(qkv_empty, 8); mbar_init(o_ready, 32); mbar_init(x_full, 1); mbar_init(sc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_trigger();
+
+    if (warp == 0) {
+        // ===================== weight producer =====================
+        if (lane == 0) {
+            uint32_t wi = 0;
+            auto load = [&](size_t off, uint32_t bytes) {
+                const int s = wi % ENC_NSTAGE;
+                const uint32_t ph = (wi / ENC_NSTAGE) & 1;
+                mbar_wait(&w_empty[s], ph ^ 1);
+                mbar_expect_tx(&w_full[s], bytes);
+                bulk_g2s(sW + s * ENC_STAGE, p.wstream + off, bytes, &w_full[s]);
+                ++wi;
+            };
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int l = 0; l < p.nl; ++l) {
+                    const size_t base = (size_t)l * ENC_LAYER_BYTES;
+                    for (int i = 0; i < 12; ++i) load(base + ENC_L_QKV + (size_t)i * ENC_QKV_BLK, ENC_QKV_BLK);
+                    for (int i = 0; i < 3; ++i) load(base + ENC_L_OUT + (size_t)i * ENC_STAGE, ENC_STAGE);
+                    for (int i = 0; i < 12; ++i) load(base + ENC_L_FFN + (size_t)i * ENC_STAGE, ENC_STAGE);
+                }
+                load((size_t)p.nl * ENC_LAYER_BYTES, ENC_STAGE);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t id144 = make_idesc_bf16(128, 144, 0, 0);
+            constexpr uint32_t id192 = make_idesc_bf16(128, 192, 0, 0);
+            constexpr uint32_t id64 = make_idesc_bf16(128, 64, 0, 0);
+            const uint32_t aW = smem_u32(sW), aA = smem_u32(sA), aO = smem_u32(sO), aH = smem_u32(sH);
+            const uint32_t tX = tmem_base, tS = tmem_base + 192;
+            uint32_t wi = 0, na = 0, hq = 0, no = 0, hc = 0;
+            // one weight stage against a [64 × 64·nkb] hi/lo operand: D (+)= (A_hi + A_lo) · Wᵀ
+            auto mma_stage = [&](uint32_t a_hi, uint32_t a_lo, uint32_t d, uint32_t idesc, uint32_t w_off, bool first) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint64_t bd = make_desc_k_sw128(w_off + k * 32);
+                    umma_bf16(d, make_desc_k_sw128(a_hi + k * 32), bd, idesc, (first && k == 0) ? 0u : 1u);
+                    umma_bf16(d, make_desc_k_sw128(a_lo + k * 32), bd, idesc, 1u);
+                }
+            };
+            auto wait_w = [&]() -> uint32_t {
+                const int s = wi % ENC_NSTAGE;
+                mbar_wait(&w_full[s], (wi / ENC_NSTAGE) & 1);
+                tc_fence_after();
+                return aW + s * ENC_STAGE;
+            };
+            auto free_w = [&]() { umma_commit(&w_empty[wi % ENC_NSTAGE]); ++wi; };
+            auto ffn2 = [&](uint32_t pc) {               // x += H(chunk pc) · W2[:, chunk]ᵀ
+                const uint32_t b = pc & 1;
+                mbar_wait(&h_ready[b], (pc >> 1) & 1);
+                const uint32_t w = wait_w();
+                mma_stage(aH + b * 2 * ENC_KB, aH + b * 2 * ENC_KB + ENC_KB, tX, id192, w, false);
+                free_w();
+                umma_commit(&h_free[b]);
+            };
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int l = 0; l < p.nl; ++l) {
+                    mbar_wait(a_ready, na & 1); ++na;
+                    tc_fence_after();
+                    for (int h = 0; h < 4; ++h, ++hq) {                       // [q_h | k_h | v_h] = LN1(x) · W_hᵀ
+                        const uint32_t b = hq & 1;
+                        mbar_wait(&dq_empty[b], ((hq >> 1) & 1) ^ 1);
+                        tc_fence_after();
+                        for (int kb = 0; kb < 3; ++kb) {
+                            const uint32_t w = wait_w();
+                            mma_stage(aA + kb * ENC_KB, aA + ENC_PLANE + kb * ENC_KB, tS + 144 * b, id144, w, kb == 0);
+                            free_w();
+                        }
+                        umma_commit(&dq_full[b]);
+                    }
+                    mbar_wait(o_ready, no & 1); ++no;                          // x += O · Woᵀ
+                    tc_fence_after();
+                    for (int kb = 0; kb < 3; ++kb) {
+                        const uint32_t w = wait_w();
+                        mma_stage(aO + kb * ENC_KB, aO + ENC_PLANE + kb * ENC_KB, tX, id192, w, false);
+                        free_w();
+                    }
+                    umma_commit(x_full);
+                    mbar_wait(a_ready, na & 1); ++na;                          // LN2(x) in the A tile
+                    tc_fence_after();
+                    for (int c = 0; c < 6; ++c, ++hc) {                        // hidden chunk c = LN2(x) · W1[64c..]ᵀ
+                        const uint32_t b = hc & 1;
+                        mbar_wait(&dh_empty[b], ((hc >> 1) & 1) ^ 1);
+                        tc_fence_after();
+                        const uint32_t w = wait_w();
+#pragma unroll
+                        for (int kb = 0; kb < 3; ++kb)
+                            mma_stage(aA + kb * ENC_KB, aA + ENC_PLANE + kb * ENC_KB, tS + 64 * b, id64, w + kb * ENC_KB, kb == 0);
+                        free_w();
+                        umma_commit(&dh_full[b]);
+                        if (c >= 1) ffn2(hc - 1);
+                    }
+                    ffn2(hc - 1);
+                    umma_commit(x_full);
+                }
+                // heads: [scores | class projections] = x · [Q | W_cls]ᵀ
+                mbar_wait(a_ready, na & 1); ++na;
+                tc_fence_after();
+                {
+                    const uint32_t w = wait_w();
+#pragma unroll
+                    for (int kb = 0; kb < 3; ++kb)
+                        mma_stage(aA + kb * ENC_KB, aA + ENC_PLANE + kb * ENC_KB, tS, id64, w + kb * ENC_KB, kb == 0);
+                    free_w();
+                }
+                umma_commit(sc_full);
+            }
+        }
+    } else if (warp >= 4 && wq < 2) {
+        // ===================== compute warps: TMEM <-> registers, LayerNorm, epilogues =====================
+        const int q = wq, g = (warp - 4) >> 2, m = q * 32 + lane;
+        const int ct = g * 64 + m;                                  // 0..255
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const uint32_t tX = tmem_base + lane_addr + 48 * g;         // this thread's slice of the residual stream
+        const uint32_t tS = tmem_base + lane_addr + 192;
+        uint32_t hq = 0, nx = 0, hc = 0, nsc = 0;
+        float v[48];
+        pdl_wait();                                                 // partial sums come from the token_proj kernel
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int grow = tile * ENC_ROWS + m;
+            const bool valid = m < ENC_ROWS && grow < T;
+            // ---- x0 = Σ_s partial[s] + bias (token_proj epilogue, models_PMG.py:193) ----
+#pragma unroll
+            for (int j = 0; j < 12; ++j) {
+                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid) {
+                    a = __ldg(reinterpret_cast<const float4*>(p.tok_bias + 48 * g + 4 * j));
+                    for (int s = 0; s < p.nsplit; ++s) {
+                        const float4 t = *reinterpret_cast<const float4*>(p.partial + (size_t)s * p.pstride + (size_t)grow * 192 + 48 * g + 4 * j);
+                        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+                    }
+                    if (p.tok_in) *reinterpret_cast<float4*>(p.tok_in + (size_t)grow * 192 + 48 * g + 4 * j) = a;
+                }
+                v[4 * j] = a.x; v[4 * j + 1] = a.y; v[4 * j + 2] = a.z; v[4 * j + 3] = a.w;
+            }
+            if (p.nl > 0) tmem_st48(tX, v);
+            for (int l = 0; l < p.nl; ++l) {
+                const EncLayerPtrs& lp = p.layer[l];
+                // ---- LN1 → A tile ----
+                layer_norm48(v, sRed, m, g, lp.ln1w, lp.ln1b);      // x itself stays in TMEM
+                write_operand48(sA, m, g, v);
+                tmem_st_wait();
+                fence_proxy_async();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_ready);
+                // ---- per head: drain [q|k|v] (+bias) to the fp32 head buffer; g = 0/1/2 ↔ q/k/v ----
+                for (int h = 0; h < 4; ++h, ++hq) {
+                    if (g < 3) {
+                        const uint32_t b = hq & 1;
+                        mbar_wait(&dq_full[b], (hq >> 1) & 1);
+                        tc_fence_after();
+                        tmem_ld48(tS + 144 * b + 48 * g, v);
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&dq_empty[b]);
+                        const float* bias = lp.b_in + 192 * g + 48 * h;
+                        const float scl = (g == 0) ? 0.14433756729740643f : 1.f;      // 1/sqrt(48) folded into q
+                        mbar_wait(qkv_empty, (hq & 1) ^ 1);                           // attention of the previous head is done reading
+                        float* dst = sQKV + m * ENC_QKV_LD + 48 * g;
+#pragma unroll
+                        for (int j = 0; j < 12; ++j) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + 4 * j));
+                            *reinterpret_cast<float4*>(dst + 4 * j) = make_float4((v[4 * j] + b4.x) * scl, (v[4 * j + 1] + b4.y) * scl,
+                                                                                  (v[4 * j + 2] + b4.z) * scl, (v[4 * j + 3] + b4.w) * scl);
+                        }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(qkv_full);
+                    }
+                }
+                // ---- x += attention block done: + out-proj bias, LN2 → A tile ----
+                mbar_wait(x_full, nx & 1); ++nx;
+                tc_fence_after();
+                tmem_ld48(tX, v);
+#pragma unroll
+                for (int i = 0; i < 48; i += 4) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(lp.b_o + 48 * g + i));
+                    v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                }
+                tmem_st48(tX, v);
+                layer_norm48(v, sRed, m, g, lp.ln2w, lp.ln2b);
+                write_operand48(sA, m, g, v);
+                tmem_st_wait();
+                fence_proxy_async();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a_ready);
+                // ---- FFN hidden chunks: + bias, ReLU, hi/lo → H tile ----
+                for (int c = 0; c < 6; ++c, ++hc) {
+                    const uint32_t b = hc & 1;
+                    mbar_wait(&dh_full[b], (hc >> 1) & 1);
+                    tc_fence_after();
+                    uint32_t r[16];
+                    tmem_ld_32x32b_x16(tS + 64 * b + 16 * g, r);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&dh_empty[b]);
+                    uint32_t hi[8], lo[8];
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(lp.b_1 + 64 * c + 16 * g + i));
+                        const float h0 = fmaxf(__uint_as_float(r[i]) + b4.x, 0.f), h1 = fmaxf(__uint_as_float(r[i + 1]) + b4.y, 0.f);
+                        const float h2 = fmaxf(__uint_as_float(r[i + 2]) + b4.z, 0.f), h3 = fmaxf(__uint_as_float(r[i + 3]) + b4.w, 0.f);
+                        split_bf16x2(h0, h1, hi[i >> 1], lo[i >> 1]);
+                        split_bf16x2(h2, h3, hi[(i >> 1) + 1], lo[(i >> 1) + 1]);
+                    }
+                    mbar_wait(&h_free[b], ((hc >> 1) & 1) ^ 1);                       // FFN2 of chunk c-2 has read this tile
+                    uint8_t* hrow = sH + b * 2 * ENC_KB + m * 128;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int sw = ((2 * g + j) ^ (m & 7)) << 4;
+                        *reinterpret_cast<uint4*>(hrow + sw) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                        *reinterpret_cast<uint4*>(hrow + ENC_KB + sw) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&h_ready[b]);
+                }
+                // ---- x += FFN done: + bias ----
+                mbar_wait(x_full, nx & 1); ++nx;
+                tc_fence_after();
+                tmem_ld48(tX, v);
+#pragma unroll
+                for (int i = 0; i < 48; i += 4) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(lp.b_2 + 48 * g + i));
+                    v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                }
+                if (l + 1 < p.nl) tmem_st48(tX, v);
+            }
+            // ---- final tokens → heads operand ----
+            if (p.tok_out && valid) {
+#pragma unroll
+                for (int j = 0; j < 12; ++j)
+                    *reinterpret_cast<float4*>(p.tok_out + (size_t)grow * 192 + 48 * g + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+            write_operand48(sA, m, g, v);
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready);
+            mbar_wait(sc_full, nsc & 1); ++nsc;
+            tc_fence_after();
+            {
+                uint32_t r[16];
+                tmem_ld_32x32b_x16(tS + 16 * g, r);
+                tmem_ld_wait();
+                tc_fence_before();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) sSC[m * ENC_SC_LD + 16 * g + i] = __uint_as_float(r[i]);
+            }
+            named_bar_sync(1, 256);
+            // ---- task attention pooling + heads (models_PMG.py:47-57,198): one (image, class) per thread ----
+            for (int idx = ct; idx < ENC_IPT * p.ncls_total; idx += 256) {
+                const int bi = idx / p.ncls_total, c = idx - bi * p.ncls_total, t = p.task_of[c];
+                const int img = tile * ENC_IPT + bi;
+                if (img >= p.B) continue;
+                const float* s = sSC + bi * 9 * ENC_SC_LD;
+                float sv[9], mx = -INFINITY;
+#pragma unroll
+                for (int n = 0; n < 9; ++n) { sv[n] = s[n * ENC_SC_LD + t]; mx = fmaxf(mx, sv[n]); }
+                float den = 0.f, acc = 0.f;
+#pragma unroll
+                for (int n = 0; n < 9; ++n) {
+                    const float e = expf(sv[n] - mx);
+                    den += e;
+                    acc = fmaf(e, s[n * ENC_SC_LD + p.ntask + c], acc);
+                }
+                p.logits[(size_t)img * p.ncls_total + c] = acc / den + __ldg(p.cls_bias + c);
+            }
+            named_bar_sync(1, 256);
+        }
+        tc_fence_before();
+    } else if (warp >= 2) {
+        // ===================== aux warps: 9-token attention core out of shared memory =====================
+        // 4 lanes per token row: lane part s owns 12 of the head's 48 dims (partial q·k, then 12 output dims)
+        const int aw = ((warp - 2) >> 2) * 2 + (wq - 2);
+        const int row = aw * 8 + (lane >> 2), s = lane & 3;
+        const int ib = min(row / 9, ENC_IPT - 1) * 9;             // first row of this row's image
+        uint32_t hq = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int l = 0; l < p.nl; ++l) {
+                for (int h = 0; h < 4; ++h, ++hq) {
+                    mbar_wait(qkv_full, hq & 1);
+                    const float* qp = sQKV + row * ENC_QKV_LD + 12 * s;
+                    const float* kp = sQKV + ib * ENC_QKV_LD + 48 + 12 * s;
+                    const float* vp = sQKV + ib * ENC_QKV_LD + 96 + 12 * s;
+                    float sc[9];
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) sc[j] = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float4 q4 = *reinterpret_cast<const float4*>(qp + 4 * c);
+#pragma unroll
+                        for (int j = 0; j < 9; ++j) {
+                            const float4 k4 = *reinterpret_cast<const float4*>(kp + j * ENC_QKV_LD + 4 * c);
+                            sc[j] = fmaf(q4.x, k4.x, fmaf(q4.y, k4.y, fmaf(q4.z, k4.z, fmaf(q4.w, k4.w, sc[j]))));
+                        }
+                    }
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) {
+                        sc[j] += __shfl_xor_sync(0xffffffffu, sc[j], 1);
+                        sc[j] += __shfl_xor_sync(0xffffffffu, sc[j], 2);
+                        mx = fmaxf(mx, sc[j]);
+                    }
+                    float den = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) { sc[j] = expf(sc[j] - mx); den += sc[j]; }
+                    const float inv = 1.f / den;
+                    float o[12];
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) o[i] = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 9; ++j) {
+                        const float pj = sc[j] * inv;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            const float4 v4 = *reinterpret_cast<const float4*>(vp + j * ENC_QKV_LD + 4 * c);
+                            o[4 * c] = fmaf(pj, v4.x, o[4 * c]); o[4 * c + 1] = fmaf(pj, v4.y, o[4 * c + 1]);
+                            o[4 * c + 2] = fmaf(pj, v4.z, o[4 * c + 2]); o[4 * c + 3] = fmaf(pj, v4.w, o[4 * c + 3]);
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(qkv_empty);            // every lane has finished reading the head buffer
+                    // O tile: columns 48h + 12s .. +11 of this row, hi/lo planes, 8-byte pieces
+#pragma unroll
+                    for (int t = 0; t < 3; ++t) {
+                        uint32_t h0, l0, h1, l1;
+                        split_bf16x2(o[4 * t], o[4 * t + 1], h0, l0);
+                        split_bf16x2(o[4 * t + 2], o[4 * t + 3], h1, l1);
+                        const int e = 48 * h + 12 * s + 4 * t;           // element column, multiple of 4
+                        const int ce = e & 63;
+                        uint8_t* dst = sO + (e >> 6) * ENC_KB + row * 128 + ((((ce >> 3) ^ (row & 7)) << 4) | ((ce & 7) << 1));
+                        *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
+                        *reinterpret_cast<uint2*>(dst + ENC_PLANE) = make_uint2(l0, l1);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(o_ready);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight stream packing: fp32 (or bf16) [rows][ld] matrices → bf16 blocks of [nrows × 64 K], rows 128 bytes,
+// 16-byte chunks XOR-swizzled with (row & 7) exactly as the UMMA SWIZZLE_128B K-major layout expects.
+// ------------------------------------------------------------------------------------------------
+struct EncPackDesc {
+    const void* src;
+    int src_bf16;        // 0: fp32 source, 1: bf16 source
+    int ld;
+    int row0[3];         // source row of segment i = block row / seg
+    int seg;
+    int nrows;
+    int k0;
+    unsigned dst;        // byte offset in the stream
+};
+struct EncPackArgs {
+    EncPackDesc d[40];
+};
+
+__global__ void __launch_bounds__(256) enc_pack_kernel(const EncPackArgs a, uint8_t* __restrict__ stream) {
+    const EncPackDesc& d = a.d[blockIdx.x];
+    for (int i = threadIdx.x; i < d.nrows * 8; i += blockDim.x) {
+        const int r = i >> 3, j = i & 7;
+        const size_t so = (size_t)(d.row0[r / d.seg] + r % d.seg) * d.ld + d.k0 + 8 * j;
+        uint32_t w[4];
+        if (d.src_bf16) {
+            const uint4 t = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(d.src) + so);
+            w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+        } else {
+            const float* s = reinterpret_cast<const float*>(d.src) + so;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(s[2 * e], s[2 * e + 1]);
+                w[e] = *reinterpret_cast<uint32_t*>(&h);
+            }
+        }
+        *reinterpret_cast<uint4*>(stream + d.dst + r * 128 + ((j ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
+}  // namespace tc
