@@ -41,7 +41,7 @@ class PmgError(RuntimeError):
 EXPORTS = [
     "pmg_abi_version", "pmg_status_string", "pmg_last_cuda_error", "pmg_param_count", "pmg_packed_bytes",
     "pmg_pack_weights", "pmg_workspace_bytes", "pmg_logits_per_image", "pmg_forward_launch_count",
-    "pmg_forward", "pmg_forward_profile", "pmg_gram_batched", "pmg_tc_gemm",
+    "pmg_forward", "pmg_forward_profile", "pmg_gram_batched", "pmg_tc_gemm", "pmg_debug_set_trace",
     "pm_param_count", "pm_packed_bytes", "pm_pack_weights", "pm_workspace_bytes", "pm_feature_shape", "pm_forward",
 ]
 
@@ -81,6 +81,8 @@ def _load() -> C.CDLL:
     lib.pmg_tc_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_void_p, C.c_void_p]
     lib.pmg_tc_gemm.restype = C.c_int
+    lib.pmg_debug_set_trace.argtypes = [C.c_void_p]
+    lib.pmg_debug_set_trace.restype = None
     pcfg = C.POINTER(PmConfig)
     lib.pm_param_count.argtypes = [pcfg]
     lib.pm_param_count.restype = C.c_int

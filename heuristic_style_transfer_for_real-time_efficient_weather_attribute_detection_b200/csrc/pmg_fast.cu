@@ -22,6 +22,8 @@
 
 namespace pmg {
 
+static long long* g_enc_trace = nullptr;   // debug only (pmg_debug_set_trace)
+
 int launch_pool_heads(const Plan& p, const PackedLayout& L, const char* packed, const float* tok, int B, int N,
                       float* logits, cudaStream_t st);
 
@@ -469,7 +471,7 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
         }
         tc::FrontParams fp;
         fp.scale0 = Pf(L.conv_scale[0]); fp.shift0 = Pf(L.conv_shift[0]); fp.scale1 = Pf(L.conv_scale[1]); fp.shift1 = Pf(L.conv_shift[1]);
-        fp.act1_hi = Hb(w.act1_hi); fp.act1_lo = Hb(w.act1_lo); fp.B = B;
+        fp.act1_hi = Hb(w.act1_hi); fp.act1_lo = Hb(w.act1_lo); fp.B = B; fp.trace = g_enc_trace;
         const int grid = 2 * B < tc::num_sms() ? 2 * B : tc::num_sms();
         PMG_CUDA_OK(tc::launch_pdl(tc::front_kernel, dim3(grid), dim3(tc::FRONT_THREADS), tc::FRONT_SMEM, st, tx, tw0, tw1, fp), "front_kernel");
         PMG_MARK(tm, "front_conv0_conv1");
@@ -542,7 +544,7 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
         e.partial = Ff(w.partial); e.pstride = pstride; e.nsplit = w.splits; e.tok_bias = Pf(L.tok_b);
         e.cls_bias = Pf(L.cls_b); e.logits = logits;
         e.tok_in = taps ? taps->tokens_in : nullptr; e.tok_out = taps ? taps->tokens_out : nullptr;
-        e.nl = p.nl; e.B = B; e.ntask = p.ntask; e.ncls_total = p.ncls_total;
+        e.nl = p.nl; e.B = B; e.ntask = p.ntask; e.ncls_total = p.ncls_total; e.trace = g_enc_trace;
         for (int l = 0; l < p.nl; ++l) {
             const TfLayerOff& t = L.tf[l];
             e.layer[l] = {Pf(t.b_in), Pf(t.b_o), Pf(t.b_1), Pf(t.b_2), Pf(t.ln1w), Pf(t.ln1b), Pf(t.ln2w), Pf(t.ln2b)};
@@ -614,6 +616,8 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
 int gram_batched_fast(const void*, int, int, int, int, float, float*, cudaStream_t) { return PMG_ERR_UNSUPPORTED; }
 
 }  // namespace pmg
+
+extern "C" void pmg_debug_set_trace(void* dev_buf_512_i64) { pmg::g_enc_trace = reinterpret_cast<long long*>(dev_buf_512_i64); }
 
 extern "C" int pmg_tc_gemm(const void* a_hi, const void* a_lo, const void* b, int M, int N, int K, int bn, int splits,
                            float* out, pmg_stream_t stream) {

@@ -70,7 +70,9 @@ struct EncParams {
     EncLayerPtrs layer[8];
     int nsplit, nl, B, ntask, ncls_total;
     unsigned char task_of[64];
+    long long* trace;                // optional (pmg_debug_set_trace): clock64 stamps of CTA 0's roles, 512 slots
 };
+#define ENC_T(slot) do { if (p.trace && blockIdx.x == 0) p.trace[slot] = clock64(); } while (0)
 
 __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile(
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
     uint64_t* sc_full = bars + 23;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int wq = warp & 3;
     const int n_tiles = (p.B + ENC_IPT - 1) / ENC_IPT;
     const int T = p.B * 9;
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
 
     if (warp == 0) {
         // ===================== weight producer =====================
-        if (lane == 0) {
+        if (elect_one()) {      // one elected thread; elect.sync keeps the branch warp-uniform for ptxas (no per-MMA ELECT loops)
             uint32_t wi = 0;
             auto load = [&](size_t off, uint32_t bytes) {
                 const int s = wi % ENC_NSTAGE;
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {      // one elected thread; elect.sync keeps the branch warp-uniform for ptxas (no per-MMA ELECT loops)
             constexpr uint32_t id144 = make_idesc_bf16(128, 144, 0, 0);
             constexpr uint32_t id192 = make_idesc_bf16(128, 192, 0, 0);
             constexpr uint32_t id64 = make_idesc_bf16(128, 64, 0, 0);
@@ -257,10 +259,12 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                 free_w();
                 umma_commit(&h_free[b]);
             };
+            ENC_T(0);
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int l = 0; l < p.nl; ++l) {
                     mbar_wait(a_ready, na & 1); ++na;
                     tc_fence_after();
+                    ENC_T(1 + 40 * l);
                     for (int h = 0; h < 4; ++h, ++hq) {                       // [q_h | k_h | v_h] = LN1(x) · W_hᵀ
                         const uint32_t b = hq & 1;
                         mbar_wait(&dq_empty[b], ((hq >> 1) & 1) ^ 1);
@@ -271,17 +275,21 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                             free_w();
                         }
                         umma_commit(&dq_full[b]);
+                        ENC_T(2 + 40 * l + h);
                     }
                     mbar_wait(o_ready, no & 1); ++no;                          // x += O · Woᵀ
                     tc_fence_after();
+                    ENC_T(6 + 40 * l);
                     for (int kb = 0; kb < 3; ++kb) {
                         const uint32_t w = wait_w();
                         mma_stage(aO + kb * ENC_KB, aO + ENC_PLANE + kb * ENC_KB, tX, id192, w, false);
                         free_w();
                     }
                     umma_commit(x_full);
+                    ENC_T(7 + 40 * l);
                     mbar_wait(a_ready, na & 1); ++na;                          // LN2(x) in the A tile
                     tc_fence_after();
+                    ENC_T(8 + 40 * l);
                     for (int c = 0; c < 6; ++c, ++hc) {                        // hidden chunk c = LN2(x) · W1[64c..]ᵀ
                         const uint32_t b = hc & 1;
                         mbar_wait(&dh_empty[b], ((hc >> 1) & 1) ^ 1);
@@ -292,10 +300,12 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                             mma_stage(aA + kb * ENC_KB, aA + ENC_PLANE + kb * ENC_KB, tS + 64 * b, id64, w + kb * ENC_KB, kb == 0);
                         free_w();
                         umma_commit(&dh_full[b]);
-                        if (c >= 1) ffn2(hc - 1);
+                        ENC_T(9 + 40 * l + c);
+                        if (c >= 1) { ffn2(hc - 1); ENC_T(15 + 40 * l + c - 1); }
                     }
                     ffn2(hc - 1);
                     umma_commit(x_full);
+                    ENC_T(20 + 40 * l);
                 }
                 // heads: [scores | class projections] = x · [Q | W_cls]ᵀ
                 mbar_wait(a_ready, na & 1); ++na;
@@ -320,23 +330,56 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
         uint32_t hq = 0, nx = 0, hc = 0, nsc = 0;
         float v[48];
         pdl_wait();                                                 // partial sums come from the token_proj kernel
+        const bool tr = (warp == 4 && lane == 0);
+#define ENC_TC(slot) do { if (tr) ENC_T(slot); } while (0)
+        ENC_TC(100);
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const int grow = tile * ENC_ROWS + m;
             const bool valid = m < ENC_ROWS && grow < T;
             // ---- x0 = Σ_s partial[s] + bias (token_proj epilogue, models_PMG.py:193) ----
+            // coalesced: the 256 compute threads sweep the tile's [63 × 192] fp32 block 16 bytes at a time, park the
+            // sums in the (idle) O region with an XOR chunk swizzle, then every thread picks up its 48-column slice
+            {
+                float4* sX = reinterpret_cast<float4*>(sO);
 #pragma unroll
-            for (int j = 0; j < 12; ++j) {
-                float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid) {
-                    a = __ldg(reinterpret_cast<const float4*>(p.tok_bias + 48 * g + 4 * j));
-                    for (int s = 0; s < p.nsplit; ++s) {
-                        const float4 t = *reinterpret_cast<const float4*>(p.partial + (size_t)s * p.pstride + (size_t)grow * 192 + 48 * g + 4 * j);
-                        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+                for (int half = 0; half < 2; ++half) {
+                    float4 acc[6];
+                    int rr[6], cc[6];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        const int f = ct + 256 * (6 * half + i);
+                        rr[i] = f / 48; cc[i] = f - rr[i] * 48;
+                        acc[i] = __ldg(reinterpret_cast<const float4*>(p.tok_bias) + cc[i]);
                     }
-                    if (p.tok_in) *reinterpret_cast<float4*>(p.tok_in + (size_t)grow * 192 + 48 * g + 4 * j) = a;
+                    for (int s = 0; s < p.nsplit; ++s) {
+                        float4 t[6];
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) {
+                            const int gr = tile * ENC_ROWS + rr[i];
+                            t[i] = (rr[i] < ENC_ROWS && gr < T)
+                                       ? *(reinterpret_cast<const float4*>(p.partial + (size_t)s * p.pstride + (size_t)gr * 192) + cc[i])
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 6; ++i) { acc[i].x += t[i].x; acc[i].y += t[i].y; acc[i].z += t[i].z; acc[i].w += t[i].w; }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        const int gr = tile * ENC_ROWS + rr[i];
+                        const bool ok = rr[i] < ENC_ROWS && gr < T;
+                        if (!ok) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        else if (p.tok_in) *(reinterpret_cast<float4*>(p.tok_in + (size_t)gr * 192) + cc[i]) = acc[i];
+                        sX[rr[i] * 48 + (cc[i] ^ (rr[i] & 7))] = acc[i];
+                    }
                 }
-                v[4 * j] = a.x; v[4 * j + 1] = a.y; v[4 * j + 2] = a.z; v[4 * j + 3] = a.w;
+                named_bar_sync(1, 256);
+#pragma unroll
+                for (int j = 0; j < 12; ++j) {
+                    const float4 a = sX[m * 48 + ((12 * g + j) ^ (m & 7))];
+                    v[4 * j] = a.x; v[4 * j + 1] = a.y; v[4 * j + 2] = a.z; v[4 * j + 3] = a.w;
+                }
             }
+            ENC_TC(101);
             if (p.nl > 0) tmem_st48(tX, v);
             for (int l = 0; l < p.nl; ++l) {
                 const EncLayerPtrs& lp = p.layer[l];
@@ -348,6 +391,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a_ready);
+                ENC_TC(102 + 40 * l);
                 // ---- per head: drain [q|k|v] (+bias) to the fp32 head buffer; g = 0/1/2 ↔ q/k/v ----
                 for (int h = 0; h < 4; ++h, ++hq) {
                     if (g < 3) {
@@ -370,11 +414,13 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                         }
                         __syncwarp();
                         if (lane == 0) mbar_arrive(qkv_full);
+                        ENC_TC(103 + 40 * l + h);
                     }
                 }
                 // ---- x += attention block done: + out-proj bias, LN2 → A tile ----
                 mbar_wait(x_full, nx & 1); ++nx;
                 tc_fence_after();
+                ENC_TC(107 + 40 * l);
                 tmem_ld48(tX, v);
 #pragma unroll
                 for (int i = 0; i < 48; i += 4) {
@@ -389,6 +435,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a_ready);
+                ENC_TC(108 + 40 * l);
                 // ---- FFN hidden chunks: + bias, ReLU, hi/lo → H tile ----
                 for (int c = 0; c < 6; ++c, ++hc) {
                     const uint32_t b = hc & 1;
@@ -420,10 +467,12 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&h_ready[b]);
+                    ENC_TC(109 + 40 * l + c);
                 }
                 // ---- x += FFN done: + bias ----
                 mbar_wait(x_full, nx & 1); ++nx;
                 tc_fence_after();
+                ENC_TC(115 + 40 * l);
                 tmem_ld48(tX, v);
 #pragma unroll
                 for (int i = 0; i < 48; i += 4) {
@@ -445,6 +494,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
             if (lane == 0) mbar_arrive(a_ready);
             mbar_wait(sc_full, nsc & 1); ++nsc;
             tc_fence_after();
+            ENC_TC(190);
             {
                 uint32_t r[16];
                 tmem_ld_32x32b_x16(tS + 16 * g, r);
@@ -473,6 +523,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                 p.logits[(size_t)img * p.ncls_total + c] = acc / den + __ldg(p.cls_bias + c);
             }
             named_bar_sync(1, 256);
+            ENC_TC(191);
         }
         tc_fence_before();
     } else if (warp >= 2) {
@@ -486,6 +537,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
             for (int l = 0; l < p.nl; ++l) {
                 for (int h = 0; h < 4; ++h, ++hq) {
                     mbar_wait(qkv_full, hq & 1);
+                    if (warp == 2 && lane == 0) ENC_T(200 + 40 * l + 2 * h);
                     const float* qp = sQKV + row * ENC_QKV_LD + 12 * s;
                     const float* kp = sQKV + ib * ENC_QKV_LD + 48 + 12 * s;
                     const float* vp = sQKV + ib * ENC_QKV_LD + 96 + 12 * s;
@@ -542,6 +594,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(o_ready);
+                    if (warp == 2 && lane == 0) ENC_T(201 + 40 * l + 2 * h);
                 }
             }
         }

@@ -5,9 +5,10 @@
 // Tile = 98 conv1 pixels (7 rows × 14 cols of the 14×14 map) of one image, 2 tiles per image; UMMA M = 128
 // (rows 98..127 are don't-care).  For each of the 4 row offsets sy of conv1's 4×4 window:
 //
-//   * TMA (4-D tensor map over the NCHW bf16 image, dims x|y16|py|b·c, box 224×1×7×1, no swizzle) drops, per
-//     (channel c, kernel row ky), 7 whole image rows = a [98 pixels × 16 input columns] slab straight into smem
-//     as 98 rows of 32 bytes: no im2col, no register staging, every box fully in bounds, 448-byte runs.
+//   * TMA (4-D tensor map over the NCHW bf16 image, dims x|py|y16|b·c, box 224×8×4×1, no swizzle) drops, per
+//     channel c, four slabs (kernel rows ky) of 8 whole image rows each = [98(+14) pixels × 16 input columns]
+//     straight into smem as rows of 32 bytes: no im2col, no register staging, 448-byte runs, ONE bulk tensor
+//     copy per (sy, c) step (the 8th image row is the neighbouring tile's / zero fill: don't-care MMA rows).
 //     The MMA reads the slab as a K-major SWIZZLE_32B operand.  The data are NOT swizzled, so for slab rows with
 //     bit 2 set (r & 4) the hardware's chunk XOR hands the MMA the two 16-byte halves (input columns 0-7 / 8-15)
 //     exchanged.  W0' is block-sparse over the column offset sx (4 columns each), so for those pixels the
@@ -33,11 +34,11 @@ namespace tc {
 constexpr int FRONT_THREADS = 576;                 // warp 0 TMA, warp 1 MMA, warps 2-17 epilogue (lane quarter × 32-column group)
 constexpr int FR_W0_BYTES = 3 * 128 * 128;         // 48 KB: 3 K-blocks × [128 rows × 128 B]
 constexpr int FR_W1_BYTES = 8 * 64 * 128;          // 64 KB: (sy, kb) × [64 rows × 128 B]
-constexpr int FR_A0_SLOT = 4096;                   // one TMA box (98 rows × 32 B = 3136 B) per 4 KB slot
-constexpr int FR_A0_STAGE = 4 * FR_A0_SLOT;        // one channel: 4 kernel rows
+constexpr int FR_A0_SLOT = 3584;                   // one kernel row ky: 8 image rows × 448 B (7 used by the tile; 256-byte multiple)
+constexpr int FR_A0_STAGE = 4 * FR_A0_SLOT;        // one channel: 4 kernel rows = ONE TMA box
 constexpr int FR_A0_STAGES = 3;
 constexpr int FR_A1_BYTES = 2 * 2 * 128 * 128;     // 64 KB: [plane hi/lo][kb][128 rows × 128 B]
-constexpr int FR_BOX_BYTES = 98 * 32;
+constexpr int FR_BOX_BYTES = FR_A0_STAGE;        // box 224 × 8 × 4 × 1 bf16 (out-of-range image rows are zero-filled but counted)
 constexpr int FR_OFF_W1 = FR_W0_BYTES;
 constexpr int FR_OFF_A0 = FR_OFF_W1 + FR_W1_BYTES;
 constexpr int FR_OFF_A1 = FR_OFF_A0 + FR_A0_STAGES * FR_A0_STAGE;
@@ -54,6 +55,14 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
         : "memory");
 }
 
+// L2 prefetch of one image-row box: the smem ring holds ~38 KB per SM, far less than HBM latency × bandwidth needs
+// in flight (≈ 90 KB per SM), so the producer asks L2 for the boxes of the NEXT tile while it loads this one
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
 // K-major operand whose rows are 32 bytes (16 bf16 = one UMMA K step), 32-byte swizzle, 8-row groups 256 B apart
 __device__ __forceinline__ uint64_t make_desc_k_sw32(uint32_t saddr) { return make_smem_desc(saddr, 16, 256, LAYOUT_SW32); }
 
@@ -62,7 +71,9 @@ struct FrontParams {
     const float* scale1; const float* shift1;    // [64]
     __nv_bfloat16* act1_hi; __nv_bfloat16* act1_lo;   // [B·196, 64]
     int B;
+    long long* trace;                            // optional debug stamps (pmg_debug_set_trace), slots 256..383
 };
+#define FR_T(slot) do { if (p.trace && blockIdx.x == 0 && lt == 2) p.trace[256 + (slot)] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(FRONT_THREADS, 1)
 front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW0,
@@ -89,7 +100,7 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     float* s1 = h0 + 32;
     float* h1 = s1 + 64;
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int n_tiles = 2 * p.B;
 
     if (threadIdx.x == 0) {
@@ -116,29 +127,38 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (elect_one()) {      // one elected thread; elect.sync keeps the branch warp-uniform for ptxas (no per-MMA ELECT loops)
             mbar_expect_tx(w_bar, FR_W0_BYTES + FR_W1_BYTES);
             for (int i = 0; i < 3; ++i) tma_load_2d(sW0 + i * 16384, &tmW0, w_bar, i * 64, 0);
             for (int i = 0; i < 8; ++i) tma_load_2d(sW1 + i * 8192, &tmW1, w_bar, 0, i * 64);
             pdl_wait();      // weights are constants; everything below may depend on earlier kernels
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            constexpr int PF = 12;                       // prefetch distance in (sy, c) steps = one tile
+            auto prefetch = [&](uint32_t j) {             // j-th (tile, sy, c) step of this CTA
+                const int tile = blockIdx.x + (int)(j / 12) * gridDim.x;
+                if (tile >= n_tiles) return;
+                const int r = j % 12, sy = r / 3, c = r - 3 * sy;
+#pragma unroll
+                tma_prefetch_4d(&tmX, 0, (tile & 1) * 7, sy * 4, (tile >> 1) * 3 + c);
+            };
+            for (uint32_t j = 0; j < PF; ++j) prefetch(j);
+            uint32_t it = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
                 const int b = tile >> 1, py0 = (tile & 1) * 7;
                 for (int sy = 0; sy < 4; ++sy)
                     for (int c = 0; c < 3; ++c, ++it) {
                         const int s = it % FR_A0_STAGES;
                         const uint32_t ph = (it / FR_A0_STAGES) & 1;
+                        prefetch(it + PF);
                         mbar_wait(&a0_empty[s], ph ^ 1);
-                        mbar_expect_tx(&a0_full[s], 4 * FR_BOX_BYTES);
-#pragma unroll
-                        for (int ky = 0; ky < 4; ++ky)
-                            tma_load_4d(sA0 + s * FR_A0_STAGE + ky * FR_A0_SLOT, &tmX, &a0_full[s], 0, sy * 4 + ky, py0, b * 3 + c);
+                        FR_T(sy * 3 + c);
+                        mbar_expect_tx(&a0_full[s], FR_BOX_BYTES);
+                        tma_load_4d(sA0 + s * FR_A0_STAGE, &tmX, &a0_full[s], 0, py0, sy * 4, b * 3 + c);
                     }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {      // one elected thread; elect.sync keeps the branch warp-uniform for ptxas (no per-MMA ELECT loops)
             constexpr uint32_t idesc0 = make_idesc_bf16(128, 128, 0, 0);
             constexpr uint32_t idesc1 = make_idesc_bf16(128, 64, 0, 0);
             const uint32_t aW0 = smem_u32(sW0), aW1 = smem_u32(sW1), aA0 = smem_u32(sA0), aA1 = smem_u32(sA1);
@@ -164,11 +184,13 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                     const uint32_t as = g & 1, aph = (g >> 1) & 1;
                     mbar_wait(&d0_empty[as], aph ^ 1);
                     tc_fence_after();
+                    FR_T(20 + 4 * sy);
                     for (int c = 0; c < 3; ++c, ++it) {
                         const int s = it % FR_A0_STAGES;
                         const uint32_t ph = (it / FR_A0_STAGES) & 1;
                         mbar_wait(&a0_full[s], ph);
                         tc_fence_after();
+                        if (c == 2) FR_T(21 + 4 * sy);
 #pragma unroll
                         for (int ky = 0; ky < 4; ++ky) {
                             const int kk = c * 4 + ky;
@@ -178,10 +200,13 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                         umma_commit(&a0_empty[s]);
                     }
                     umma_commit(&d0_full[as]);
+                    FR_T(22 + 4 * sy);
                     if (sy >= 1) mma1(g - 1);
+                    FR_T(23 + 4 * sy);
                 }
                 mma1(g - 1);
                 umma_commit(d1_full);
+                FR_T(36);
             }
         }
     } else {
@@ -200,6 +225,7 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                 const uint32_t as = g & 1, aph = (g >> 1) & 1;
                 mbar_wait(&d0_full[as], aph);
                 tc_fence_after();
+                if (warp == 2 && lane == 0) FR_T(40 + 4 * sy);
                 uint32_t r[32], H[16], L[16];
                 tmem_ld_32x32b_x32(tD0 + as * 128 + lane_addr + (uint32_t)(cg * 32), r);
                 tmem_ld_wait();
@@ -216,7 +242,9 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                     split_bf16x2(v0, v1, H[2 * j], L[2 * j]);
                     split_bf16x2(v2, v3, H[2 * j + 1], L[2 * j + 1]);
                 }
+                if (warp == 2 && lane == 0) FR_T(41 + 4 * sy);
                 if (g > 0) mbar_wait(a1_free, (g - 1) & 1);        // conv1 MMAs of the previous slice have read A1
+                if (warp == 2 && lane == 0) FR_T(42 + 4 * sy);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int sw = (((cg & 1) * 4 + j) ^ (m & 7)) << 4;
@@ -226,10 +254,12 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a1_ready);
+                if (warp == 2 && lane == 0) FR_T(43 + 4 * sy);
             }
             // ---- epilogue 1: act1 = LeakyReLU(BN(D1)), this warp's 16 of the 64 channels ----
             mbar_wait(d1_full, lt & 1);
             tc_fence_after();
+            if (warp == 2 && lane == 0) FR_T(60);
             uint32_t r[16];
             tmem_ld_32x32b_x16(tD1 + lane_addr + (uint32_t)(cg * 16), r);
             tmem_ld_wait();
@@ -253,6 +283,7 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                 dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
                 dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
             }
+            if (warp == 2 && lane == 0) FR_T(61);
         }
         tc_fence_before();
     }

@@ -97,7 +97,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
     float* s_shift = s_scale + GEMM_MAX_N;
     uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_shift + GEMM_MAX_N);      // 8 × 4 KB, 128-byte aligned
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
     const int groups_m = (tiles_m + MT - 1) / MT;
     const int tiles_n = p.N / BN;
@@ -129,7 +129,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
 
     if (warp == 0) {
         // ===== TMA producer =====
-        if (lane == 0) {
+        if (elect_one()) {      // one elected thread; elect.sync keeps the branch warp-uniform for ptxas (no per-MMA ELECT loops)
             uint32_t it = 0;
             for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
                 const int mg = item % groups_m, nt = (item / groups_m) % tiles_n, sp = item / (groups_m * tiles_n);
@@ -152,7 +152,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
+        if (elect_one()) {      // one elected thread; elect.sync keeps the branch warp-uniform for ptxas (no per-MMA ELECT loops)
             constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, BN, 0, 0);
             uint32_t it = 0, li = 0;
             for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {

@@ -36,7 +36,7 @@ gram96_tc_kernel(const float* __restrict__ chan, __nv_bfloat16* __restrict__ g_h
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
     uint8_t* s_stage = smem + GRAM_STAGES * 2 * GRAM_PLANE + 256;             // 12 × 4 KB
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < GRAM_STAGES; ++s) { mbar_init(&full_bar[s], 96); mbar_init(&empty_bar[s], 1); }
@@ -100,7 +100,7 @@ gram96_tc_kernel(const float* __restrict__ chan, __nv_bfloat16* __restrict__ g_h
         }
     } else if (warp == 3) {
         // ===== MMA issuer =====
-        if (lane == 0) {
+        if (elect_one()) {      // one elected thread; elect.sync keeps the branch warp-uniform for ptxas (no per-MMA ELECT loops)
             constexpr uint32_t idesc = make_idesc_bf16(128, 96, 0, 0);
             uint32_t it = 0;
             for (int tok = blockIdx.x; tok < n_tokens; tok += gridDim.x, ++it) {

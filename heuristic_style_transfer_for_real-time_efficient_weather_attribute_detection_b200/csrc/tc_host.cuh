@@ -63,18 +63,19 @@ inline int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint6
 }
 
 // 4-D view of a bf16 NCHW image batch (B,3,224,224) for the fused front end (tc_front.cuh):
-//   dims (innermost first)  x = 224 | y16 = 16 | py = 14 | b·c = 3B          (y = 16·py + y16)
-//   box                     224 × 1 × 7 × 1  = 7 whole image rows (448 contiguous bytes each) = the 16 input columns
-//                           of 98 conv1 pixels for one (channel, kernel row); NO swizzle, so TMA moves 448-byte
+//   dims (innermost first)  x = 224 | py = 14 | y16 = 16 | b·c = 3B          (y = 16·py + y16)
+//   box                     224 × 8 × 4 × 1  = for 4 kernel rows, 8 whole image rows (448 contiguous bytes each; the
+//                           tile uses 7, an 8th keeps every kernel-row slab a 256-byte multiple) = the 16 input columns
+//                           of 98 conv1 pixels for one channel; NO swizzle, so TMA moves 448-byte
 //                           runs (a swizzled 16-column inner box made it move 98 separate 32-byte rows per box,
 //                           which bounded the whole kernel).  The UMMA descriptor still reads the slab with the
 //                           32-byte swizzle; tc_front.cuh explains how the resulting half swap is absorbed.
 inline int make_tmap_image_rows(CUtensorMap* m, const void* base, int B) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { pmg::set_cuda_error(cudaErrorNotSupported, "cuTensorMapEncodeTiled entry point"); return PMG_ERR_CUDA; }
-    cuuint64_t dims[4] = {224, 16, 14, (cuuint64_t)3 * B};
-    cuuint64_t strides[3] = {448, 7168, 100352};
-    cuuint32_t box[4] = {224, 1, 7, 1};
+    cuuint64_t dims[4] = {224, 14, 16, (cuuint64_t)3 * B};
+    cuuint64_t strides[3] = {7168, 448, 100352};
+    cuuint32_t box[4] = {224, 8, 4, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -176,6 +176,11 @@ int pm_forward(const pm_config* cfg, const void* packed, const void* x, int x_dt
 int pmg_tc_gemm(const void* a_hi, const void* a_lo, const void* b, int M, int N, int K, int bn, int splits,
                 float* out, pmg_stream_t stream);
 
+/* Debug / tuning hook, not a product path: when set to a device buffer of 512 int64, CTA 0 of the fused token-stage
+ * kernel records clock64() stamps of its warp roles there (scratch/enc_trace.py decodes them).  NULL switches it off.
+ * Process-global; not thread safe. */
+void pmg_debug_set_trace(void* dev_buf_512_i64);
+
 #ifdef __cplusplus
 }
 #endif
