@@ -26,13 +26,21 @@ sys.path.insert(0, ROOT)
 FLOPS_PER_IMAGE = 77_348_864
 CONV_GRAM_FLOPS = 34_654_208            # conv stack + chan_proj + Gram
 BYTES_PER_IMAGE = 3 * 224 * 224 * 2 + 52 * 4   # bf16 image in + fp32 logits out
-STAGE_FLOPS = {                          # per image, committed config
-    "conv0": 9_633_792, "conv1": 12_845_056, "conv2": 3_211_264, "chan_proj": 4_816_896, "gram": 4_147_200,
-    "token_proj": 31_850_496, "encoder_layer": 5_370_624, "pool_heads": 102_912,
-    "backbone_gram": 34_654_208, "encoder": 10_741_248,
-}
-STAGE_BYTES = {                          # per image algorithmic HBM bytes when the stage runs as its own kernel
-    "conv0": 3 * 224 * 224 * 2 + 32 * 56 * 56 * 4, "pool_heads": 9 * 192 * 4 + 52 * 4,
+# per image, committed config: (algorithmic FLOPs, algorithmic HBM bytes) of each stage as it is split into kernels
+# (SURVEY.md §8a for the FLOPs; bytes = the stage's compulsory reads + writes)
+STAGES = {
+    "front_conv0_conv1": (9_633_792 + 12_845_056, 3 * 224 * 224 * 2 + 2 * 196 * 64 * 2),   # bf16 image in, act1 hi/lo out
+    "im2col0": (0, 3 * 224 * 224 * 2 + 3136 * 64 * 2),
+    "conv0": (9_633_792, 3136 * 64 * 2 + 2 * 196 * 512 * 2),
+    "conv1": (12_845_056, 2 * 196 * 512 * 2 + 2 * 196 * 64 * 2),
+    "conv2": (3_211_264, 2 * 196 * 64 * 2 + 2 * 196 * 128 * 2),
+    "chan_proj": (4_816_896, 2 * 196 * 128 * 2 + 196 * 96 * 4),
+    "gram": (4_147_200, 196 * 96 * 4 + 2 * 9 * 9216 * 2),
+    "token_proj": (31_850_496, 2 * 9 * 9216 * 2 + 2 * 9 * 192 * 4),
+    "tok_reduce_ln": (0, 3 * 9 * 192 * 4 + 2 * 9 * 192 * 2),
+    "encoder_layer": (5_370_624, 9 * 192 * 4 * 2),
+    "pool_heads": (102_912, 9 * 192 * 4 + 52 * 4),
+    "encoder_heads": (10_741_248 + 102_912, 2 * 9 * 192 * 4 + 52 * 4),
 }
 
 
@@ -230,26 +238,41 @@ def main():
         ms = float(t.item())
     value = GB * args.steps / (ms / 1e3)
 
-    # ---- end to end through the public API: pinned host batch → H2D → forward → D2H logits, every step
-    ms_e2e = float("nan")
+    # ---- end to end through the public API: pinned host batch → H2D → (GPU ToTensor+Normalize) → forward → D2H logits,
+    # every step.  Three host input formats: decoded uint8 HWC images (headline: 150 KB/image over PCIe), the
+    # normalised bf16 batch, and the fp32 batch the reference's own DataLoader delivers.
+    e2e_ms = {}
     if not args.no_e2e:
-        x_host = x.cpu().pin_memory()
+        gcpu = torch.Generator().manual_seed(rank)
+        hosts = {
+            "uint8_nhwc": torch.randint(0, 256, (B, 224, 224, 3), dtype=torch.uint8, generator=gcpu).pin_memory(),
+            "bf16_nchw": x.cpu().pin_memory(),
+            "fp32_nchw": x.float().cpu().pin_memory(),
+        }
         pipe = HostPipeline(model, chunk=args.e2e_chunk, device=dev)
-        for _ in range(3):
-            pipe.infer(x_host)
-        fence()
-        e0.record()
-        for _ in range(args.steps):
-            pipe.infer(x_host)   # logits land in pinned host memory per rank: the D2H read is the result delivery
-        e1.record()
-        fence()
-        ms_e2e = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
+        for name, x_host in hosts.items():
+            for _ in range(3):
+                pipe.infer(x_host)
+            fence()
+            e0.record()
+            for _ in range(args.steps):
+                pipe.infer(x_host)   # logits land in pinned host memory per rank: the D2H read is the result delivery
+            e1.record()
+            fence()
+            ms_leg = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms_leg], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms_leg = float(t.item())
+            e2e_ms[name] = ms_leg
+        del hosts
     clocks = sampler.stop() if sampler else None
-    e2e_value = GB * args.steps / (ms_e2e / 1e3) if ms_e2e == ms_e2e else None
+    E2E_BYTES = {"uint8_nhwc": 3 * 224 * 224, "bf16_nchw": 3 * 224 * 224 * 2, "fp32_nchw": 3 * 224 * 224 * 4}
+
+    def e2e_entry(name):
+        ms_leg = e2e_ms[name]
+        return {"value": round(GB * args.steps / (ms_leg / 1e3), 1), "unit": "images/s", "h2d_bytes_per_step": B * E2E_BYTES[name],
+                "d2h_bytes_per_step": B * 52 * 4, "ms_per_step": round(ms_leg / args.steps, 4), "host_input": name}
 
     if rank != 0:
         if world > 1:
@@ -283,20 +306,33 @@ def main():
     if os.path.exists(tp):
         with open(tp) as f:
             traffic = json.load(f).get(dom)
-    dom_flops = STAGE_FLOPS.get(dom, 0) * B
-    ach = dom_flops / (per_launch[dom] / 1e3) / 1e12
-    roofline = {
-        "kernel": dom, "bound": "tensor", "achieved": round(ach, 2), "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-        "frac": round(ach / pk["bf16_tflops"], 4), "traffic": traffic, "peak_source": pk["source"],
+    dom_flops, dom_bytes = STAGES.get(dom, (0, 0))
+    ridge = pk["bf16_tflops"] * 1e12 / (pk["hbm_gbs"] * 1e9)
+    sec = per_launch[dom] / 1e3
+    if dom_bytes and dom_flops / dom_bytes < ridge:       # arithmetic intensity below the ridge: HBM-bound kernel
+        ach = dom_bytes * B / sec / 1e9
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": round(ach, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": round(ach / pk["hbm_gbs"], 4)}
+    else:
+        ach = dom_flops * B / sec / 1e12
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": round(ach, 2), "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": round(ach / pk["bf16_tflops"], 4)}
+    roofline.update({
+        "traffic": traffic, "peak_source": pk["source"],
+        "algorithmic_per_image": {"flops": dom_flops, "bytes": dom_bytes},
         "ms_per_launch": round(per_launch[dom], 4), "share_of_forward": round(per_forward[dom] / sum(per_forward.values()), 3),
         "stage_ms": {k: round(v, 4) for k, v in per_forward.items()},
+        "stage_frac_of_own_roofline": {
+            k: round(max(STAGES[k][0] * B / (per_launch[k] / 1e3) / 1e12 / pk["bf16_tflops"],
+                         STAGES[k][1] * B / (per_launch[k] / 1e3) / 1e9 / pk["hbm_gbs"]), 3)
+            for k in per_launch if k in STAGES},
         "forward": {
             "tensor_frac": round(value / world * FLOPS_PER_IMAGE / 1e12 / pk["bf16_tflops"], 4),
             "conv_gram_tensor_frac": round(value / world * CONV_GRAM_FLOPS / 1e12 / pk["bf16_tflops"], 4),
             "hbm_frac": round(value / world * BYTES_PER_IMAGE / 1e9 / pk["hbm_gbs"], 4),
             "flops_per_image": FLOPS_PER_IMAGE, "bytes_per_image": BYTES_PER_IMAGE,
         },
-    }
+    })
     launches = model.launches_per_forward(B) * args.steps
     line = {
         "metric": "pmg_images_per_sec", "value": round(value, 1), "unit": "images/s", "n_gpus": world,
@@ -307,10 +343,11 @@ def main():
                    "path": "generic-fp32" if args.force_generic else "default",
                    "collective": "one all_gather of (B_local,52) fp32 logits per step" if world > 1 else "none"},
         "clocks": clocks,
-        "e2e": None if e2e_value is None else {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": B * 3 * 224 * 224 * 2,
-                "d2h_bytes_per_step": B * 52 * 4, "ms_per_step": round(ms_e2e / args.steps, 4),
-                "api": "pmg_b200.runner.HostPipeline.infer(pinned host bf16 batch) -> pinned host logits",
-                "chunk": args.e2e_chunk},
+        "e2e": None if not e2e_ms else dict(
+            e2e_entry("uint8_nhwc"),
+            api="pmg_b200.runner.HostPipeline.infer(pinned host uint8 HWC images) -> GPU ToTensor+Normalize "
+                "(prepost.preprocess_u8) -> forward -> pinned host logits", chunk=args.e2e_chunk,
+            other_host_inputs={k: e2e_entry(k) for k in ("bf16_nchw", "fp32_nchw")}),
         "gpu_launches": launches,
         "roofline": roofline,
     }

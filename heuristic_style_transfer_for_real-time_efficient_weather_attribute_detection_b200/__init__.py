@@ -17,5 +17,6 @@ from .models_PM import MultiTaskPatchGAN  # noqa: F401
 from .compat import install_as_reference_models  # noqa: F401
 from . import gram as gram              # noqa: F401
 from . import runner as runner          # noqa: F401
+from . import prepost as prepost        # noqa: F401
 
-__all__ = ["MultiTaskPatchGANGramModelNonOverlapV2", "MultiTaskPatchGAN", "install_as_reference_models", "gram", "runner"]
+__all__ = ["MultiTaskPatchGANGramModelNonOverlapV2", "MultiTaskPatchGAN", "install_as_reference_models", "gram", "runner", "prepost"]

@@ -99,8 +99,13 @@ class HostPipeline:
     This is the call the end-to-end bench times; the reference's equivalent is the
     ``inputs.to(device)`` → ``model(inputs)`` → ``.cpu()`` loop of Functions/PMG_evaluation.py:124-150."""
 
-    def __init__(self, model, chunk: int = 128, device: Optional[torch.device] = None):
+    def __init__(self, model, chunk: int = 128, device: Optional[torch.device] = None, u8_layout: str = "NHWC"):
+        """``x_host`` may be the normalised float batch (B,3,H,W) fp32 / bf16 — what the reference's loaders deliver — or
+        the decoded uint8 images, (B,H,W,3) for ``u8_layout="NHWC"`` / (B,3,H,W) for "NCHW": then ToTensor + Normalize
+        (utils/datasets_utils.py:212-214) run on the GPU (prepost.preprocess_u8) and only 150 KB/image cross PCIe."""
         self.model = model
+        self.u8_layout = u8_layout
+        self._pre = [None, None]
         self.chunk = int(chunk)
         self.device = device or next(model.parameters()).device
         self.copy_stream = torch.cuda.Stream(self.device)
@@ -135,7 +140,14 @@ class HostPipeline:
                 copied[i].record(self.copy_stream)
             with torch.cuda.stream(self.compute_stream):
                 self.compute_stream.wait_event(copied[i])
-                logits = self.model.forward_packed(buf[: hi - lo])
+                xin = buf[: hi - lo]
+                if xin.dtype == torch.uint8:
+                    from . import prepost
+                    n, hh, ww = (xin.shape[0], xin.shape[1], xin.shape[2]) if self.u8_layout == "NHWC" else (xin.shape[0], xin.shape[2], xin.shape[3])
+                    if self._pre[i & 1] is None or self._pre[i & 1].shape[1:] != (3, hh, ww) or self._pre[i & 1].shape[0] < n:
+                        self._pre[i & 1] = torch.empty((self.chunk, 3, hh, ww), dtype=torch.bfloat16, device=self.device)
+                    xin = prepost.preprocess_u8(xin, self.u8_layout, torch.bfloat16, out=self._pre[i & 1][:n])
+                logits = self.model.forward_packed(xin)
                 consumed[i].record(self.compute_stream)
                 self._out[lo:hi].copy_(logits, non_blocking=True)
         cur.wait_stream(self.compute_stream)

@@ -136,6 +136,23 @@ int pmg_gram_batched(const void* F, int f_dtype, int B, int C, int HW, float sca
                      pmg_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Callers' pre/post-processing on the GPU (the steps either side of model(x) in the reference's loops).
+ * ------------------------------------------------------------------------------------------------ */
+#define PMG_LAYOUT_NCHW 0
+#define PMG_LAYOUT_NHWC 1
+/* transforms.ToTensor() + transforms.Normalize(mean, std) (utils/datasets_utils.py:212-214) on decoded uint8
+ * images: dst[b,c,y,x] = (src/255 - mean[c]) / std[c], fp32 arithmetic in torchvision's operation order
+ * (bit-identical in fp32; rounded to nearest-even for bf16).  src (B,3,H,W) or (B,H,W,3) uint8; dst (B,3,H,W).
+ * mean3 / std3 are HOST pointers to 3 floats. */
+int pmg_preprocess_u8(const void* src, int layout, int B, int H, int W, const float* mean3, const float* std3,
+                      int out_dtype, void* dst, pmg_stream_t stream);
+/* Per-task softmax / max / arg-max / threshold of Functions/PMG_evaluation.py:144-146 on the packed logits
+ * (B, sum(ncls)): probs (B, sum(ncls)), preds (B, n_tasks) int32 with -1 where max prob < prob_threshold,
+ * max_probs (B, n_tasks); any output may be NULL (not all).  ncls is a HOST array. */
+int pmg_postprocess(const float* logits, int B, int n_tasks, const int32_t* ncls, float prob_threshold,
+                    float* probs, int32_t* preds, float* max_probs, pmg_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * PM model (PatchGAN multi-task, no Gram branch) — BASELINE.json configs[3].
  * Reference boundary: Models/models_PM.py:79-194 class MultiTaskPatchGAN (forward :159-194,
  * TaskHeadImproved.forward :54-76); built by test_PM.py:153-164 with ndf=64, norm="instance".
