@@ -52,7 +52,7 @@ static FastW fast_w(const Plan& p) {
     }
     f.wq = take(64 * 192);
     f.w0x = take(128 * 192); f.w1x = take(512 * 64);
-    f.wenc = take(((size_t)p.nl * tc::ENC_LAYER_BYTES + tc::ENC_STAGE) / sizeof(bf16));
+    f.wenc = take(((size_t)(p.nl <= tc::ENC_MAX_LAYERS ? p.nl : 0) * tc::ENC_LAYER_BYTES + tc::ENC_STAGE) / sizeof(bf16));
     f.total = o;
     return f;
 }
@@ -142,9 +142,9 @@ int pack_fast(const Plan& p, const PackedLayout& L, const float* const* prm, cha
     }
     // fused token stage: every encoder weight as pre-swizzled [rows × 64 K] blocks in the order the kernel's
     // MMA warp consumes them (tc_encoder.cuh), then the heads operand
-    {
+    if (p.nl <= tc::ENC_MAX_LAYERS) {
         uint8_t* stream = reinterpret_cast<uint8_t*>(base + f.wenc);
-        static const int ffn_order[12][2] = {{1, 0}, {1, 1}, {2, 0}, {1, 2}, {2, 1}, {1, 3}, {2, 2}, {1, 4}, {2, 3}, {1, 5}, {2, 4}, {2, 5}};
+        static const int ffn_order[6][2] = {{1, 0}, {1, 1}, {2, 0}, {1, 2}, {2, 1}, {2, 2}};   // FFN1 / FFN2 of 128-unit chunk c
         int pi = 18;
         for (int l = 0; l < p.nl; ++l, pi += 12) {
             tc::EncPackArgs a{};
@@ -159,13 +159,13 @@ int pack_fast(const Plan& p, const PackedLayout& L, const float* const* prm, cha
                 for (int kb = 0; kb < 3; ++kb)
                     add(prm[pi], 0, 192, 48 * h, 192 + 48 * h, 384 + 48 * h, 48, 144, 64 * kb, lb + tc::ENC_L_QKV + (h * 3 + kb) * tc::ENC_QKV_BLK);
             for (int kb = 0; kb < 3; ++kb) add(prm[pi + 2], 0, 192, 0, 0, 0, 192, 192, 64 * kb, lb + tc::ENC_L_OUT + kb * tc::ENC_STAGE);
-            for (int i = 0; i < 12; ++i) {
+            unsigned off = lb + tc::ENC_L_FFN;
+            for (int i = 0; i < 6; ++i) {
                 const int c = ffn_order[i][1];
-                const unsigned sb = lb + tc::ENC_L_FFN + i * tc::ENC_STAGE;
                 if (ffn_order[i][0] == 1)
-                    for (int kb = 0; kb < 3; ++kb) add(prm[pi + 4], 0, 192, 64 * c, 0, 0, 64, 64, 64 * kb, sb + kb * tc::ENC_KB);
+                    for (int kb = 0; kb < 3; ++kb, off += tc::ENC_F1_BLK) add(prm[pi + 4], 0, 192, 128 * c, 0, 0, 128, 128, 64 * kb, off);
                 else
-                    add(prm[pi + 6], 0, 384, 0, 0, 0, 192, 192, 64 * c, sb);
+                    for (int kb = 0; kb < 2; ++kb, off += tc::ENC_STAGE) add(prm[pi + 6], 0, 384, 0, 0, 0, 192, 192, 128 * c + 64 * kb, off);
             }
             tc::enc_pack_kernel<<<n, 256, 0, st>>>(a, stream);
         }
@@ -429,7 +429,7 @@ size_t fast_workspace_bytes(const Plan&, const Shape&, int B) { return fast_ws(B
 // bf16 input: fused front kernel (1 launch) instead of im2col + conv0 + conv1 (3 launches)
 int fast_launch_count(const Plan& p, const Shape&, int, unsigned flags) {
     const int front = (flags & PMG_FLAG_NO_FUSED_FRONT) ? 3 : 1;
-    if (!(flags & PMG_FLAG_NO_FUSED_ENCODER)) return front + 2 + 1 + 1 + 1;   // conv2, chan_proj, Gram, token_proj, token stage
+    if (!(flags & PMG_FLAG_NO_FUSED_ENCODER) && p.nl <= tc::ENC_MAX_LAYERS) return front + 2 + 1 + 1 + 1;   // conv2, chan_proj, Gram, token_proj, token stage
     return front + 2 + 1 + 1 + 1 + 6 * p.nl + (p.nl > 1 ? p.nl - 1 : 0) + 3;
 }
 
@@ -532,7 +532,7 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
                    Ff(w.partial), nullptr, nullptr, nullptr, nullptr, nullptr, w.splits, pstride, st)))
         return rc;
     PMG_MARK(tm, "token_proj");
-    if (!(flags & PMG_FLAG_NO_FUSED_ENCODER)) {
+    if (!(flags & PMG_FLAG_NO_FUSED_ENCODER) && p.nl <= tc::ENC_MAX_LAYERS) {
         // split-K reduce + bias, the whole transformer, task pooling and the heads: one kernel (tc_encoder.cuh)
         static bool attr_set = false;
         if (!attr_set) {

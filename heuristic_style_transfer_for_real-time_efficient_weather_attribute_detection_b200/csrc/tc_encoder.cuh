@@ -1,5 +1,5 @@
 // tc_encoder.cuh — the whole token stage of the PMG forward in ONE persistent tcgen05 kernel:
-//   token_proj split-K reduce + bias  →  nl × pre-LN TransformerEncoderLayer (d 192, 4 heads × 48, FFN 384, ReLU)
+//   token_proj split-K reduce + bias  →  nl (≤ 2) × pre-LN TransformerEncoderLayer (d 192, 4 heads × 48, FFN 384, ReLU)
 //   →  task attention pooling + 12 linear heads  →  logits.
 // Reference: models_PMG.py:60-72,144-147,194 (encoder), :47-57 (TaskAttentionPooling), :153-155,198 (heads).
 //
@@ -8,7 +8,9 @@
 // FFN2 MMAs accumulate straight onto it, so the residual adds cost nothing.  Activations that feed an MMA are
 // written by the epilogue warps as two bf16 planes (hi + lo, DESIGN.md "precision") into K-major 128B-swizzled
 // smem operand tiles; all layer weights stream through a 3-stage ring of 24 KB blocks with cp.async.bulk from a
-// pre-swizzled copy (enc_pack_kernel), so one bulk copy lands a ready-to-use UMMA B tile.
+// pre-swizzled copy (enc_pack_kernel), so one bulk copy lands a ready-to-use UMMA B tile.  Every small parameter
+// (biases, LayerNorm affine, task map) is staged in smem once per CTA, before griddepcontrol.wait, so no global
+// load sits on the per-phase critical path.
 //
 // UMMA M is 128 but only 64 rows are real: operand k-blocks are packed 8 KB apart (64 rows × 128 B), so rows
 // 64..127 of k-block j alias rows 0..63 of k-block j+1 — the MMA computes throw-away rows in TMEM lanes 64..127
@@ -16,12 +18,12 @@
 //
 // Warp roles (18 warps): 0 = weight producer, 1 = MMA issuer (+ TMEM alloc), warps w with w%4 ∈ {0,1}, w ≥ 4
 // = 8 "compute" warps (TMEM lane quarter q = w%4 holds rows 32q..32q+31; column group g = (w-4)/4), warps with
-// w%4 ∈ {2,3} = 8 "aux" warps that run the 9-token attention core out of shared memory.
+// w%4 ∈ {2,3} = "aux" warps; three of them (2, 3, 7) run the 9-token attention core out of shared memory.
 //
 // Per layer:  LN1 → A tile │ per head h: MMA [q_h|k_h|v_h] (N 144, TMEM double-buffered) → compute warps drain
-// (+bias, q·1/√48) to smem fp32 → aux warps: scores, softmax, P·V → O tile (hi/lo) │ out-proj MMA onto x │
-// +bias, LN2 → A tile │ FFN in 6 chunks of 64 hidden units: FFN1 MMA → +bias, ReLU, hi/lo → H chunk tile →
-// FFN2 MMA onto x (chunk c+1's FFN1 runs under chunk c's epilogue) │ +bias.
+// (+bias, q·log2e/√48) to smem fp32 → aux warps: scores, softmax, P·V → O tile (hi/lo) │ out-proj MMA onto x │
+// +bias, LN2 → A tile │ FFN in 3 chunks of 128 hidden units: FFN1 MMA (N 128, TMEM double-buffered) → +bias,
+// ReLU, hi/lo → H tile → FFN2 MMA onto x (chunk c+1's FFN1 runs under chunk c's epilogue) │ +bias.
 // After the last layer: x hi/lo → A tile → one MMA against [queries | classifier rows] (N 64) → softmax-weighted
 // sum over the 9 tokens (the heads are linear in the pooled token) → logits.
 #pragma once
@@ -33,27 +35,35 @@ namespace tc {
 constexpr int ENC_THREADS = 576;
 constexpr int ENC_IPT = 7;                   // images per tile
 constexpr int ENC_ROWS = 63;                 // token rows per tile
+constexpr int ENC_MAX_LAYERS = 2;            // parameters of every layer stay resident in smem
 constexpr int ENC_STAGE = 24576;             // weight ring stage
 constexpr int ENC_NSTAGE = 3;
-constexpr int ENC_QKV_LD = 148;              // floats per row of the fp32 [q|k|v] head buffer (144 + 4: conflict-free 16-byte accesses)
+constexpr int ENC_QKV_LD = 148;              // floats per row of the fp32 [q|k|v] head buffer (144 + 4: conflict-free 16-byte row accesses)
 constexpr int ENC_KB = 8192;                 // operand k-block: 64 rows × 128 B
 constexpr int ENC_PLANE = 3 * ENC_KB;        // [64 rows × 192 K] bf16
-constexpr int ENC_OFF_QKV = ENC_NSTAGE * ENC_STAGE;                 // fp32 head buffer; aliased by the FFN hidden chunk tiles
+constexpr int ENC_OFF_QKV = ENC_NSTAGE * ENC_STAGE;                 // fp32 head buffer; aliased by the FFN hidden tile and the heads result
 constexpr int ENC_QKV_BYTES = 64 * ENC_QKV_LD * 4;                  // 37,888 = 37 KB
 constexpr int ENC_OFF_A = ENC_OFF_QKV + ENC_QKV_BYTES;              // LN output / final tokens, hi then lo plane
 constexpr int ENC_OFF_O = ENC_OFF_A + 2 * ENC_PLANE;                // attention output, hi then lo plane
-constexpr int ENC_SC_LD = 65;
-constexpr int ENC_OFF_SC = ENC_OFF_O + 2 * ENC_PLANE;               // [64][65] fp32 heads-GEMM result (also the ≥ 8 KB over-read slack)
-constexpr int ENC_OFF_RED = ENC_OFF_SC + 64 * ENC_SC_LD * 4;        // LayerNorm partial sums: 2 × [4][64] fp32
+constexpr int ENC_SC_LD = 65;                                       // [64][65] fp32 heads-GEMM result (inside the QKV region)
+// per-layer parameter block (floats): b_in 576 | b_o 192 | b_1 384 | b_2 192 | ln1w | ln1b | ln2w | ln2b (192 each)
+constexpr int ENC_P_BIN = 0, ENC_P_BO = 576, ENC_P_B1 = 768, ENC_P_B2 = 1152, ENC_P_LN1W = 1344, ENC_P_LN1B = 1536,
+              ENC_P_LN2W = 1728, ENC_P_LN2B = 1920, ENC_P_LAYER = 2112;
+constexpr int ENC_P_TOKB = ENC_MAX_LAYERS * ENC_P_LAYER, ENC_P_CLSB = ENC_P_TOKB + 192, ENC_P_FLOATS = ENC_P_CLSB + 64;
+constexpr int ENC_OFF_PRM = ENC_OFF_O + 2 * ENC_PLANE;              // also the ≥ 8 KB over-read slack behind the O tile
+constexpr int ENC_OFF_TASK = ENC_OFF_PRM + ENC_P_FLOATS * 4;        // task_of[64] bytes
+constexpr int ENC_OFF_RED = ENC_OFF_TASK + 64;                      // LayerNorm partial sums: 2 × [4][64] fp32
 constexpr int ENC_OFF_BAR = ENC_OFF_RED + 2 * 4 * 64 * 4;
 constexpr int ENC_SMEM = ENC_OFF_BAR + 256 + 1024;
+static_assert(ENC_SMEM <= 232448, "token-stage kernel exceeds the 227 KB shared-memory limit");
 
-// weight stream geometry (bytes), per layer
+// weight stream geometry (bytes), per layer, in the order the MMA warp consumes it
 constexpr int ENC_QKV_BLK = 144 * 128;                               // one k-block of one head's [q|k|v] rows
+constexpr int ENC_F1_BLK = 128 * 128;                                // one k-block of one FFN1 chunk (128 hidden units)
 constexpr int ENC_L_QKV = 0;
 constexpr int ENC_L_OUT = 12 * ENC_QKV_BLK;                          // 221,184
-constexpr int ENC_L_FFN = ENC_L_OUT + 3 * ENC_STAGE;                 // 294,912
-constexpr int ENC_LAYER_BYTES = ENC_L_FFN + 12 * ENC_STAGE;          // 589,824
+constexpr int ENC_L_FFN = ENC_L_OUT + 3 * ENC_STAGE;                 // 294,912: F1(0) F1(1) F2(0) F1(2) F2(1) F2(2)
+constexpr int ENC_LAYER_BYTES = ENC_L_FFN + 9 * ENC_F1_BLK + 6 * ENC_STAGE;   // 589,824
 
 struct EncLayerPtrs {
     const float *b_in, *b_o, *b_1, *b_2, *ln1w, *ln1b, *ln2w, *ln2b;
@@ -67,7 +77,7 @@ struct EncParams {
     float* logits;                   // [B][ncls_total]
     float* tok_in;                   // optional taps [T][192]
     float* tok_out;
-    EncLayerPtrs layer[8];
+    EncLayerPtrs layer[ENC_MAX_LAYERS];
     int nsplit, nl, B, ntask, ncls_total;
     unsigned char task_of[64];
     long long* trace;                // optional (pmg_debug_set_trace): clock64 stamps of CTA 0's roles, 512 slots
@@ -79,6 +89,14 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)), "l"(kEvictLast)
         : "memory");
+}
+// 16-byte asynchronous copy global → shared; src_bytes = 0 zero-fills
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_st_32x32b_x16(uint32_t taddr, const uint32_t (&r)[16]) {
     asm volatile(
@@ -127,26 +145,38 @@ __device__ __forceinline__ void write_operand48(uint8_t* tile_hi, int m, int g, 
     }
 }
 
-// LayerNorm (in place) over 192 columns held by the 4 column-group threads of a row (48 each); two-pass, fp32.
-__device__ __forceinline__ void layer_norm48(float (&v)[48], float* red, int m, int g,
-                                             const float* __restrict__ w, const float* __restrict__ b) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 48; ++i) s += v[i];
-    red[g * 64 + m] = s;
-    named_bar_sync(1, 256);
-    const float mu = (red[m] + red[64 + m] + red[128 + m] + red[192 + m]) * (1.f / 192.f);
-    float qd = 0.f;
-#pragma unroll
-    for (int i = 0; i < 48; ++i) { const float d = v[i] - mu; qd = fmaf(d, d, qd); }
-    red[256 + g * 64 + m] = qd;
-    named_bar_sync(1, 256);
-    const float var = (red[256 + m] + red[320 + m] + red[384 + m] + red[448 + m]) * (1.f / 192.f);
-    const float rs = 1.f / sqrtf(var + 1e-5f);
+// v += bias (48 floats from shared memory)
+__device__ __forceinline__ void add_bias48(float (&v)[48], const float* b) {
 #pragma unroll
     for (int i = 0; i < 48; i += 4) {
-        const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + 48 * g + i));
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(b + 48 * g + i));
+        const float4 b4 = *reinterpret_cast<const float4*>(b + i);
+        v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+    }
+}
+
+// LayerNorm (in place) over 192 columns held by the 4 column-group threads of a row (48 each); two-pass, fp32;
+// w / b point at this thread's 48-column slice in shared memory.
+__device__ __forceinline__ void layer_norm48(float (&v)[48], float* red, int m, int g, const float* w, const float* b) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 48; i += 4) { s0 += v[i]; s1 += v[i + 1]; s2 += v[i + 2]; s3 += v[i + 3]; }
+    red[g * 64 + m] = (s0 + s1) + (s2 + s3);
+    named_bar_sync(1, 256);
+    const float mu = ((red[m] + red[64 + m]) + (red[128 + m] + red[192 + m])) * (1.f / 192.f);
+    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 48; i += 4) {
+        const float d0 = v[i] - mu, d1 = v[i + 1] - mu, d2 = v[i + 2] - mu, d3 = v[i + 3] - mu;
+        q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+    }
+    red[256 + g * 64 + m] = (q0 + q1) + (q2 + q3);
+    named_bar_sync(1, 256);
+    const float var = ((red[256 + m] + red[320 + m]) + (red[384 + m] + red[448 + m])) * (1.f / 192.f);
+    const float rs = rsqrtf(var + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 48; i += 4) {
+        const float4 w4 = *reinterpret_cast<const float4*>(w + i);
+        const float4 b4 = *reinterpret_cast<const float4*>(b + i);
         v[i] = fmaf((v[i] - mu) * rs, w4.x, b4.x);
         v[i + 1] = fmaf((v[i + 1] - mu) * rs, w4.y, b4.y);
         v[i + 2] = fmaf((v[i + 2] - mu) * rs, w4.z, b4.z);
@@ -154,15 +184,133 @@ __device__ __forceinline__ void layer_norm48(float (&v)[48], float* red, int m, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 9-token attention core of one head out of the fp32 [q|k|v] head buffer (models_PMG.py:64: nn.MultiheadAttention,
+// 4 heads × 48, scale 1/sqrt(48) folded into q together with log2 e).  Three warps; a thread owns 3 query rows of one
+// image × 12 of the head's 48 dims, so every K / V chunk it loads serves three rows.  (Spreading the same work over
+// four warps incl. two compute warps measured slower: 83 vs 78 µs per 1024 images.)  The 4 lanes of a row group sum
+// their partial q·k with two xor-shuffles.  Result: O tile columns 48h.. as hi/lo bf16 planes.
+// ------------------------------------------------------------------------------------------------
+struct AttnCtx {
+    const float* qp; const float* kp; const float* vp;
+    int r0, part;
+    bool active;
+};
+__device__ __forceinline__ AttnCtx attn_ctx(const float* sQKV, int ai, int lane) {
+    AttnCtx c;
+    const int q4 = lane >> 2;
+    const int rgi = ai * 8 + q4;                       // 21 row groups (7 images × 3) over 3 warps × 8 lane quads
+    c.active = rgi < 21;
+    const int rg = c.active ? rgi : 20;
+    const int img = rg / 3;
+    c.part = lane & 3;
+    c.r0 = img * 9 + (rg - img * 3) * 3;
+    c.qp = sQKV + c.r0 * ENC_QKV_LD + 12 * c.part;
+    c.kp = sQKV + img * 9 * ENC_QKV_LD + 48 + 12 * c.part;
+    c.vp = c.kp + 48;
+    return c;
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void attention_head(const AttnCtx& ac, uint8_t* sO, int h, uint64_t* qkv_empty, uint64_t* o_ready, int lane) {
+    float4 qv[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) qv[r][c] = *reinterpret_cast<const float4*>(ac.qp + r * ENC_QKV_LD + 4 * c);
+    float sc[3][9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float4 k4 = *reinterpret_cast<const float4*>(ac.kp + j * ENC_QKV_LD + 4 * c);
+            a0 = fmaf(qv[0][c].x, k4.x, fmaf(qv[0][c].y, k4.y, fmaf(qv[0][c].z, k4.z, fmaf(qv[0][c].w, k4.w, a0))));
+            a1 = fmaf(qv[1][c].x, k4.x, fmaf(qv[1][c].y, k4.y, fmaf(qv[1][c].z, k4.z, fmaf(qv[1][c].w, k4.w, a1))));
+            a2 = fmaf(qv[2][c].x, k4.x, fmaf(qv[2][c].y, k4.y, fmaf(qv[2][c].z, k4.z, fmaf(qv[2][c].w, k4.w, a2))));
+        }
+        sc[0][j] = a0; sc[1][j] = a1; sc[2][j] = a2;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) sc[r][j] += __shfl_xor_sync(0xffffffffu, sc[r][j], 1);
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) { sc[r][j] += __shfl_xor_sync(0xffffffffu, sc[r][j], 2); mx = fmaxf(mx, sc[r][j]); }
+        float den = 0.f;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) { sc[r][j] = fast_exp2(sc[r][j] - mx); den += sc[r][j]; }
+        const float inv = fast_rcp(den);
+#pragma unroll
+        for (int j = 0; j < 9; ++j) sc[r][j] *= inv;
+    }
+    float o[3][12];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int i = 0; i < 12; ++i) o[r][i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float4 v4 = *reinterpret_cast<const float4*>(ac.vp + j * ENC_QKV_LD + 4 * c);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const float pj = sc[r][j];
+                o[r][4 * c] = fmaf(pj, v4.x, o[r][4 * c]); o[r][4 * c + 1] = fmaf(pj, v4.y, o[r][4 * c + 1]);
+                o[r][4 * c + 2] = fmaf(pj, v4.z, o[r][4 * c + 2]); o[r][4 * c + 3] = fmaf(pj, v4.w, o[r][4 * c + 3]);
+            }
+        }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(qkv_empty);            // every lane of this warp has finished reading the head buffer
+    // O tile: columns 48h + 12·part .. +11 of rows r0..r0+2, hi/lo planes, 8-byte pieces
+    if (ac.active) {
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int e = 48 * h + 12 * ac.part + 4 * t;         // element column, multiple of 4
+            const int ce = e & 63;
+            uint8_t* col = sO + (e >> 6) * ENC_KB + ((ce & 7) << 1);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int row = ac.r0 + r;
+                uint32_t h0, l0, h1, l1;
+                split_bf16x2(o[r][4 * t], o[r][4 * t + 1], h0, l0);
+                split_bf16x2(o[r][4 * t + 2], o[r][4 * t + 3], h1, l1);
+                uint8_t* dst = col + row * 128 + (((ce >> 3) ^ (row & 7)) << 4);
+                *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(dst + ENC_PLANE) = make_uint2(l0, l1);
+            }
+        }
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(o_ready);
+}
+
 __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sW = smem;
     float* sQKV = reinterpret_cast<float*>(smem + ENC_OFF_QKV);
-    uint8_t* sH = smem + ENC_OFF_QKV;               // hidden chunk tiles [buf][plane] × 8 KB (FFN phase only)
+    uint8_t* sH = smem + ENC_OFF_QKV;               // FFN hidden tile [plane hi/lo][kb 2] × 8 KB (FFN phase only)
+    float* sSC = reinterpret_cast<float*>(smem + ENC_OFF_QKV);   // heads result (after the last layer only)
     uint8_t* sA = smem + ENC_OFF_A;
     uint8_t* sO = smem + ENC_OFF_O;
-    float* sSC = reinterpret_cast<float*>(smem + ENC_OFF_SC);
+    float* sPrm = reinterpret_cast<float*>(smem + ENC_OFF_PRM);
+    unsigned char* sTask = smem + ENC_OFF_TASK;
     float* sRed = reinterpret_cast<float*>(smem + ENC_OFF_RED);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ENC_OFF_BAR);
     uint64_t* w_full = bars;            // [3]
@@ -176,10 +324,10 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
     uint64_t* x_full = bars + 14;
     uint64_t* dh_full = bars + 15;      // [2]
     uint64_t* dh_empty = bars + 17;     // [2]
-    uint64_t* h_ready = bars + 19;      // [2]
-    uint64_t* h_free = bars + 21;       // [2]
-    uint64_t* sc_full = bars + 23;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+    uint64_t* h_ready = bars + 19;
+    uint64_t* h_free = bars + 20;
+    uint64_t* sc_full = bars + 21;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int wq = warp & 3;
@@ -192,12 +340,29 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
         for (int i = 0; i < 2; ++i) {
             mbar_init(&dq_full[i], 1); mbar_init(&dq_empty[i], 6);
             mbar_init(&dh_full[i], 1); mbar_init(&dh_empty[i], 8);
-            mbar_init(&h_ready[i], 8); mbar_init(&h_free[i], 1);
         }
-        mbar_init(qkv_full, 6); mbar_init(qkv_empty, 8); mbar_init(o_ready, 32); mbar_init(x_full, 1); mbar_init(sc_full, 1);
+        mbar_init(h_ready, 8); mbar_init(h_free, 1);
+        mbar_init(qkv_full, 6); mbar_init(qkv_empty, 3); mbar_init(o_ready, 12); mbar_init(x_full, 1); mbar_init(sc_full, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
+    // parameters are constants of the model: stage them before waiting for the previous kernel
+    for (int l = 0; l < p.nl; ++l) {
+        const EncLayerPtrs& lp = p.layer[l];
+        float* d = sPrm + l * ENC_P_LAYER;
+        for (int i = threadIdx.x; i < 576; i += ENC_THREADS) d[ENC_P_BIN + i] = __ldg(lp.b_in + i);
+        for (int i = threadIdx.x; i < 384; i += ENC_THREADS) d[ENC_P_B1 + i] = __ldg(lp.b_1 + i);
+        for (int i = threadIdx.x; i < 192; i += ENC_THREADS) {
+            d[ENC_P_BO + i] = __ldg(lp.b_o + i); d[ENC_P_B2 + i] = __ldg(lp.b_2 + i);
+            d[ENC_P_LN1W + i] = __ldg(lp.ln1w + i); d[ENC_P_LN1B + i] = __ldg(lp.ln1b + i);
+            d[ENC_P_LN2W + i] = __ldg(lp.ln2w + i); d[ENC_P_LN2B + i] = __ldg(lp.ln2b + i);
+        }
+    }
+    for (int i = threadIdx.x; i < 192; i += ENC_THREADS) sPrm[ENC_P_TOKB + i] = __ldg(p.tok_bias + i);
+    if (threadIdx.x < 64) {
+        sPrm[ENC_P_CLSB + threadIdx.x] = threadIdx.x < p.ncls_total ? __ldg(p.cls_bias + threadIdx.x) : 0.f;
+        sTask[threadIdx.x] = p.task_of[threadIdx.x];
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -206,7 +371,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
 
     if (warp == 0) {
         // ===================== weight producer =====================
-        if (elect_one()) {      // one elected thread; elect.sync keeps the branch warp-uniform for ptxas (no per-MMA ELECT loops)
+        if (elect_one()) {      // one elected thread; elect.sync keeps the branch warp-uniform for ptxas
             uint32_t wi = 0;
             auto load = [&](size_t off, uint32_t bytes) {
                 const int s = wi % ENC_NSTAGE;
@@ -221,21 +386,25 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                     const size_t base = (size_t)l * ENC_LAYER_BYTES;
                     for (int i = 0; i < 12; ++i) load(base + ENC_L_QKV + (size_t)i * ENC_QKV_BLK, ENC_QKV_BLK);
                     for (int i = 0; i < 3; ++i) load(base + ENC_L_OUT + (size_t)i * ENC_STAGE, ENC_STAGE);
-                    for (int i = 0; i < 12; ++i) load(base + ENC_L_FFN + (size_t)i * ENC_STAGE, ENC_STAGE);
+                    size_t off = base + ENC_L_FFN;
+                    auto f1 = [&]() { for (int i = 0; i < 3; ++i, off += ENC_F1_BLK) load(off, ENC_F1_BLK); };
+                    auto f2 = [&]() { for (int i = 0; i < 2; ++i, off += ENC_STAGE) load(off, ENC_STAGE); };
+                    f1(); f1(); f2(); f1(); f2(); f2();
                 }
                 load((size_t)p.nl * ENC_LAYER_BYTES, ENC_STAGE);
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (elect_one()) {      // one elected thread; elect.sync keeps the branch warp-uniform for ptxas (no per-MMA ELECT loops)
+        if (elect_one()) {
             constexpr uint32_t id144 = make_idesc_bf16(128, 144, 0, 0);
             constexpr uint32_t id192 = make_idesc_bf16(128, 192, 0, 0);
+            constexpr uint32_t id128 = make_idesc_bf16(128, 128, 0, 0);
             constexpr uint32_t id64 = make_idesc_bf16(128, 64, 0, 0);
             const uint32_t aW = smem_u32(sW), aA = smem_u32(sA), aO = smem_u32(sO), aH = smem_u32(sH);
             const uint32_t tX = tmem_base, tS = tmem_base + 192;
             uint32_t wi = 0, na = 0, hq = 0, no = 0, hc = 0;
-            // one weight stage against a [64 × 64·nkb] hi/lo operand: D (+)= (A_hi + A_lo) · Wᵀ
+            // one weight k-block against one [64 × 64] hi/lo operand k-block: D (+)= (A_hi + A_lo) · Wᵀ
             auto mma_stage = [&](uint32_t a_hi, uint32_t a_lo, uint32_t d, uint32_t idesc, uint32_t w_off, bool first) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -251,13 +420,15 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                 return aW + s * ENC_STAGE;
             };
             auto free_w = [&]() { umma_commit(&w_empty[wi % ENC_NSTAGE]); ++wi; };
-            auto ffn2 = [&](uint32_t pc) {               // x += H(chunk pc) · W2[:, chunk]ᵀ
-                const uint32_t b = pc & 1;
-                mbar_wait(&h_ready[b], (pc >> 1) & 1);
-                const uint32_t w = wait_w();
-                mma_stage(aH + b * 2 * ENC_KB, aH + b * 2 * ENC_KB + ENC_KB, tX, id192, w, false);
-                free_w();
-                umma_commit(&h_free[b]);
+            auto ffn2 = [&](uint32_t pc) {               // x += H(chunk pc) · W2[:, 128·chunk ..]ᵀ
+                mbar_wait(h_ready, pc & 1);
+                tc_fence_after();
+                for (int kb = 0; kb < 2; ++kb) {
+                    const uint32_t w = wait_w();
+                    mma_stage(aH + kb * ENC_KB, aH + 2 * ENC_KB + kb * ENC_KB, tX, id192, w, false);
+                    free_w();
+                }
+                umma_commit(h_free);
             };
             ENC_T(0);
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -290,15 +461,15 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                     mbar_wait(a_ready, na & 1); ++na;                          // LN2(x) in the A tile
                     tc_fence_after();
                     ENC_T(8 + 40 * l);
-                    for (int c = 0; c < 6; ++c, ++hc) {                        // hidden chunk c = LN2(x) · W1[64c..]ᵀ
+                    for (int c = 0; c < 3; ++c, ++hc) {                        // hidden chunk c = LN2(x) · W1[128c..]ᵀ
                         const uint32_t b = hc & 1;
                         mbar_wait(&dh_empty[b], ((hc >> 1) & 1) ^ 1);
                         tc_fence_after();
-                        const uint32_t w = wait_w();
-#pragma unroll
-                        for (int kb = 0; kb < 3; ++kb)
-                            mma_stage(aA + kb * ENC_KB, aA + ENC_PLANE + kb * ENC_KB, tS + 64 * b, id64, w + kb * ENC_KB, kb == 0);
-                        free_w();
+                        for (int kb = 0; kb < 3; ++kb) {
+                            const uint32_t w = wait_w();
+                            mma_stage(aA + kb * ENC_KB, aA + ENC_PLANE + kb * ENC_KB, tS + 128 * b, id128, w, kb == 0);
+                            free_w();
+                        }
                         umma_commit(&dh_full[b]);
                         ENC_T(9 + 40 * l + c);
                         if (c >= 1) { ffn2(hc - 1); ENC_T(15 + 40 * l + c - 1); }
@@ -337,54 +508,56 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
             const int grow = tile * ENC_ROWS + m;
             const bool valid = m < ENC_ROWS && grow < T;
             // ---- x0 = Σ_s partial[s] + bias (token_proj epilogue, models_PMG.py:193) ----
-            // coalesced: the 256 compute threads sweep the tile's [63 × 192] fp32 block 16 bytes at a time, park the
-            // sums in the (idle) O region with an XOR chunk swizzle, then every thread picks up its 48-column slice
+            // the 256 compute threads pull the tile's [63 × 192] fp32 block of two split-K partials at a time with
+            // 16-byte cp.async into the (idle) O and A regions, chunk-swizzled per row; then every thread adds up
+            // its own 48-column slice.  One global round trip, no registers held across it.
             {
-                float4* sX = reinterpret_cast<float4*>(sO);
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    float4 acc[6];
-                    int rr[6], cc[6];
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) {
-                        const int f = ct + 256 * (6 * half + i);
-                        rr[i] = f / 48; cc[i] = f - rr[i] * 48;
-                        acc[i] = __ldg(reinterpret_cast<const float4*>(p.tok_bias) + cc[i]);
-                    }
-                    for (int s = 0; s < p.nsplit; ++s) {
-                        float4 t[6];
-#pragma unroll
-                        for (int i = 0; i < 6; ++i) {
-                            const int gr = tile * ENC_ROWS + rr[i];
-                            t[i] = (rr[i] < ENC_ROWS && gr < T)
-                                       ? *(reinterpret_cast<const float4*>(p.partial + (size_t)s * p.pstride + (size_t)gr * 192) + cc[i])
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-#pragma unroll
-                        for (int i = 0; i < 6; ++i) { acc[i].x += t[i].x; acc[i].y += t[i].y; acc[i].z += t[i].z; acc[i].w += t[i].w; }
-                    }
-#pragma unroll
-                    for (int i = 0; i < 6; ++i) {
-                        const int gr = tile * ENC_ROWS + rr[i];
-                        const bool ok = rr[i] < ENC_ROWS && gr < T;
-                        if (!ok) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        else if (p.tok_in) *(reinterpret_cast<float4*>(p.tok_in + (size_t)gr * 192) + cc[i]) = acc[i];
-                        sX[rr[i] * 48 + (cc[i] ^ (rr[i] & 7))] = acc[i];
-                    }
+                for (int i = 0; i < 48; i += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(sPrm + ENC_P_TOKB + 48 * g + i);
+                    v[i] = b4.x; v[i + 1] = b4.y; v[i + 2] = b4.z; v[i + 3] = b4.w;
                 }
-                named_bar_sync(1, 256);
+                for (int s0 = 0; s0 < p.nsplit; s0 += 2) {
+                    const int nb = min(2, p.nsplit - s0);
 #pragma unroll
-                for (int j = 0; j < 12; ++j) {
-                    const float4 a = sX[m * 48 + ((12 * g + j) ^ (m & 7))];
-                    v[4 * j] = a.x; v[4 * j + 1] = a.y; v[4 * j + 2] = a.z; v[4 * j + 3] = a.w;
+                    for (int i = 0; i < 12; ++i) {
+                        const int f = ct + 256 * i, r = f / 48, c4 = f - r * 48;
+                        const int gr = tile * ENC_ROWS + r;
+                        const bool ok = r < ENC_ROWS && gr < T;
+                        const uint32_t so = (uint32_t)(r * 48 + (c4 ^ (r & 7))) * 16;
+                        const float* src = p.partial + (size_t)s0 * p.pstride + (ok ? (size_t)gr * 192 + 4 * c4 : 0);
+                        cp_async16(sO + so, src, ok ? 16u : 0u);
+                        if (nb == 2) cp_async16(sA + so, src + p.pstride, ok ? 16u : 0u);
+                    }
+                    cp_async_wait_all();
+                    named_bar_sync(1, 256);
+#pragma unroll
+                    for (int j = 0; j < 12; ++j) {
+                        const uint32_t so = (uint32_t)(m * 48 + ((12 * g + j) ^ (m & 7))) * 16;
+                        const float4 a = *reinterpret_cast<const float4*>(sO + so);
+                        v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
+                        if (nb == 2) {
+                            const float4 c = *reinterpret_cast<const float4*>(sA + so);
+                            v[4 * j] += c.x; v[4 * j + 1] += c.y; v[4 * j + 2] += c.z; v[4 * j + 3] += c.w;
+                        }
+                    }
+                    if (s0 + 2 < p.nsplit) named_bar_sync(1, 256);   // staging is reused by the next pair of splits
+                }
+                if (!valid) {
+#pragma unroll
+                    for (int i = 0; i < 48; ++i) v[i] = 0.f;
+                } else if (p.tok_in) {
+#pragma unroll
+                    for (int j = 0; j < 12; ++j)
+                        *reinterpret_cast<float4*>(p.tok_in + (size_t)grow * 192 + 48 * g + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 }
             }
             ENC_TC(101);
             if (p.nl > 0) tmem_st48(tX, v);
             for (int l = 0; l < p.nl; ++l) {
-                const EncLayerPtrs& lp = p.layer[l];
+                const float* lp = sPrm + l * ENC_P_LAYER;
                 // ---- LN1 → A tile ----
-                layer_norm48(v, sRed, m, g, lp.ln1w, lp.ln1b);      // x itself stays in TMEM
+                layer_norm48(v, sRed, m, g, lp + ENC_P_LN1W + 48 * g, lp + ENC_P_LN1B + 48 * g);      // x itself stays in TMEM
                 write_operand48(sA, m, g, v);
                 tmem_st_wait();
                 fence_proxy_async();
@@ -402,13 +575,14 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&dq_empty[b]);
-                        const float* bias = lp.b_in + 192 * g + 48 * h;
-                        const float scl = (g == 0) ? 0.14433756729740643f : 1.f;      // 1/sqrt(48) folded into q
+                        const float* bias = lp + ENC_P_BIN + 192 * g + 48 * h;
+                        // softmax runs in the exp2 domain: fold log2(e)/sqrt(48) into q
+                        const float scl = (g == 0) ? 0.20823509638153327f : 1.f;
                         mbar_wait(qkv_empty, (hq & 1) ^ 1);                           // attention of the previous head is done reading
                         float* dst = sQKV + m * ENC_QKV_LD + 48 * g;
 #pragma unroll
                         for (int j = 0; j < 12; ++j) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + 4 * j));
+                            const float4 b4 = *reinterpret_cast<const float4*>(bias + 4 * j);
                             *reinterpret_cast<float4*>(dst + 4 * j) = make_float4((v[4 * j] + b4.x) * scl, (v[4 * j + 1] + b4.y) * scl,
                                                                                   (v[4 * j + 2] + b4.z) * scl, (v[4 * j + 3] + b4.w) * scl);
                         }
@@ -422,13 +596,9 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                 tc_fence_after();
                 ENC_TC(107 + 40 * l);
                 tmem_ld48(tX, v);
-#pragma unroll
-                for (int i = 0; i < 48; i += 4) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(lp.b_o + 48 * g + i));
-                    v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
-                }
+                add_bias48(v, lp + ENC_P_BO + 48 * g);
                 tmem_st48(tX, v);
-                layer_norm48(v, sRed, m, g, lp.ln2w, lp.ln2b);
+                layer_norm48(v, sRed, m, g, lp + ENC_P_LN2W + 48 * g, lp + ENC_P_LN2B + 48 * g);
                 write_operand48(sA, m, g, v);
                 tmem_st_wait();
                 fence_proxy_async();
@@ -436,37 +606,38 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a_ready);
                 ENC_TC(108 + 40 * l);
-                // ---- FFN hidden chunks: + bias, ReLU, hi/lo → H tile ----
-                for (int c = 0; c < 6; ++c, ++hc) {
+                // ---- FFN hidden chunks (128 units each): + bias, ReLU, hi/lo → H tile ----
+                for (int c = 0; c < 3; ++c, ++hc) {
                     const uint32_t b = hc & 1;
                     mbar_wait(&dh_full[b], (hc >> 1) & 1);
                     tc_fence_after();
-                    uint32_t r[16];
-                    tmem_ld_32x32b_x16(tS + 64 * b + 16 * g, r);
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(tS + 128 * b + 32 * g, r);
                     tmem_ld_wait();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&dh_empty[b]);
-                    uint32_t hi[8], lo[8];
+                    uint32_t hi[16], lo[16];
+                    const float* b1 = lp + ENC_P_B1 + 128 * c + 32 * g;
 #pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(lp.b_1 + 64 * c + 16 * g + i));
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(b1 + i);
                         const float h0 = fmaxf(__uint_as_float(r[i]) + b4.x, 0.f), h1 = fmaxf(__uint_as_float(r[i + 1]) + b4.y, 0.f);
                         const float h2 = fmaxf(__uint_as_float(r[i + 2]) + b4.z, 0.f), h3 = fmaxf(__uint_as_float(r[i + 3]) + b4.w, 0.f);
                         split_bf16x2(h0, h1, hi[i >> 1], lo[i >> 1]);
                         split_bf16x2(h2, h3, hi[(i >> 1) + 1], lo[(i >> 1) + 1]);
                     }
-                    mbar_wait(&h_free[b], ((hc >> 1) & 1) ^ 1);                       // FFN2 of chunk c-2 has read this tile
-                    uint8_t* hrow = sH + b * 2 * ENC_KB + m * 128;
+                    mbar_wait(h_free, (hc & 1) ^ 1);                                  // FFN2 of the previous chunk has read the H tile
+                    uint8_t* hrow = sH + (g >> 1) * ENC_KB + m * 128;                  // hidden columns 32g.. → k-block g/2, chunks 4(g%2)..+3
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const int sw = ((2 * g + j) ^ (m & 7)) << 4;
+                    for (int j = 0; j < 4; ++j) {
+                        const int sw = ((4 * (g & 1) + j) ^ (m & 7)) << 4;
                         *reinterpret_cast<uint4*>(hrow + sw) = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                        *reinterpret_cast<uint4*>(hrow + ENC_KB + sw) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                        *reinterpret_cast<uint4*>(hrow + 2 * ENC_KB + sw) = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
                     }
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&h_ready[b]);
+                    if (lane == 0) mbar_arrive(h_ready);
                     ENC_TC(109 + 40 * l + c);
                 }
                 // ---- x += FFN done: + bias ----
@@ -474,11 +645,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                 tc_fence_after();
                 ENC_TC(115 + 40 * l);
                 tmem_ld48(tX, v);
-#pragma unroll
-                for (int i = 0; i < 48; i += 4) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(lp.b_2 + 48 * g + i));
-                    v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
-                }
+                add_bias48(v, lp + ENC_P_B2 + 48 * g);
                 if (l + 1 < p.nl) tmem_st48(tX, v);
             }
             // ---- final tokens → heads operand ----
@@ -506,7 +673,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
             named_bar_sync(1, 256);
             // ---- task attention pooling + heads (models_PMG.py:47-57,198): one (image, class) per thread ----
             for (int idx = ct; idx < ENC_IPT * p.ncls_total; idx += 256) {
-                const int bi = idx / p.ncls_total, c = idx - bi * p.ncls_total, t = p.task_of[c];
+                const int bi = idx / p.ncls_total, c = idx - bi * p.ncls_total, t = sTask[c];
                 const int img = tile * ENC_IPT + bi;
                 if (img >= p.B) continue;
                 const float* s = sSC + bi * 9 * ENC_SC_LD;
@@ -520,84 +687,24 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                     den += e;
                     acc = fmaf(e, s[n * ENC_SC_LD + p.ntask + c], acc);
                 }
-                p.logits[(size_t)img * p.ncls_total + c] = acc / den + __ldg(p.cls_bias + c);
+                p.logits[(size_t)img * p.ncls_total + c] = acc / den + sPrm[ENC_P_CLSB + c];
             }
             named_bar_sync(1, 256);
             ENC_TC(191);
         }
         tc_fence_before();
-    } else if (warp >= 2) {
-        // ===================== aux warps: 9-token attention core out of shared memory =====================
-        // 4 lanes per token row: lane part s owns 12 of the head's 48 dims (partial q·k, then 12 output dims)
-        const int aw = ((warp - 2) >> 2) * 2 + (wq - 2);
-        const int row = aw * 8 + (lane >> 2), s = lane & 3;
-        const int ib = min(row / 9, ENC_IPT - 1) * 9;             // first row of this row's image
+    } else if (warp == 2 || warp == 3 || warp == 7) {
+        // ===================== aux warps: three of them run the attention core =====================
+        const AttnCtx ac = attn_ctx(sQKV, warp == 7 ? 2 : warp - 2, lane);
         uint32_t hq = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            for (int l = 0; l < p.nl; ++l) {
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+            for (int l = 0; l < p.nl; ++l)
                 for (int h = 0; h < 4; ++h, ++hq) {
                     mbar_wait(qkv_full, hq & 1);
                     if (warp == 2 && lane == 0) ENC_T(200 + 40 * l + 2 * h);
-                    const float* qp = sQKV + row * ENC_QKV_LD + 12 * s;
-                    const float* kp = sQKV + ib * ENC_QKV_LD + 48 + 12 * s;
-                    const float* vp = sQKV + ib * ENC_QKV_LD + 96 + 12 * s;
-                    float sc[9];
-#pragma unroll
-                    for (int j = 0; j < 9; ++j) sc[j] = 0.f;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) {
-                        const float4 q4 = *reinterpret_cast<const float4*>(qp + 4 * c);
-#pragma unroll
-                        for (int j = 0; j < 9; ++j) {
-                            const float4 k4 = *reinterpret_cast<const float4*>(kp + j * ENC_QKV_LD + 4 * c);
-                            sc[j] = fmaf(q4.x, k4.x, fmaf(q4.y, k4.y, fmaf(q4.z, k4.z, fmaf(q4.w, k4.w, sc[j]))));
-                        }
-                    }
-                    float mx = -INFINITY;
-#pragma unroll
-                    for (int j = 0; j < 9; ++j) {
-                        sc[j] += __shfl_xor_sync(0xffffffffu, sc[j], 1);
-                        sc[j] += __shfl_xor_sync(0xffffffffu, sc[j], 2);
-                        mx = fmaxf(mx, sc[j]);
-                    }
-                    float den = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 9; ++j) { sc[j] = expf(sc[j] - mx); den += sc[j]; }
-                    const float inv = 1.f / den;
-                    float o[12];
-#pragma unroll
-                    for (int i = 0; i < 12; ++i) o[i] = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 9; ++j) {
-                        const float pj = sc[j] * inv;
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) {
-                            const float4 v4 = *reinterpret_cast<const float4*>(vp + j * ENC_QKV_LD + 4 * c);
-                            o[4 * c] = fmaf(pj, v4.x, o[4 * c]); o[4 * c + 1] = fmaf(pj, v4.y, o[4 * c + 1]);
-                            o[4 * c + 2] = fmaf(pj, v4.z, o[4 * c + 2]); o[4 * c + 3] = fmaf(pj, v4.w, o[4 * c + 3]);
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(qkv_empty);            // every lane has finished reading the head buffer
-                    // O tile: columns 48h + 12s .. +11 of this row, hi/lo planes, 8-byte pieces
-#pragma unroll
-                    for (int t = 0; t < 3; ++t) {
-                        uint32_t h0, l0, h1, l1;
-                        split_bf16x2(o[4 * t], o[4 * t + 1], h0, l0);
-                        split_bf16x2(o[4 * t + 2], o[4 * t + 3], h1, l1);
-                        const int e = 48 * h + 12 * s + 4 * t;           // element column, multiple of 4
-                        const int ce = e & 63;
-                        uint8_t* dst = sO + (e >> 6) * ENC_KB + row * 128 + ((((ce >> 3) ^ (row & 7)) << 4) | ((ce & 7) << 1));
-                        *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
-                        *reinterpret_cast<uint2*>(dst + ENC_PLANE) = make_uint2(l0, l1);
-                    }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(o_ready);
+                    attention_head(ac, sO, h, qkv_empty, o_ready, lane);
                     if (warp == 2 && lane == 0) ENC_T(201 + 40 * l + 2 * h);
                 }
-            }
-        }
     }
     __syncthreads();
     if (warp == 1) {

@@ -152,3 +152,73 @@ class HostPipeline:
                 self._out[lo:hi].copy_(logits, non_blocking=True)
         cur.wait_stream(self.compute_stream)
         return self._out[:B]
+
+
+class GraphedPMG:
+    """Latency path for the B = 1 / small ragged batches of the reference's own callers:
+    utils/benchmark_utils.py:67-75 and utils/camera_utils.py:119-123 call ``model(x)`` one image at a time and then
+    read every task's result with its own device→host sync.  Here the whole forward (6 kernel launches, plus the
+    per-task softmax / arg-max kernel when ``postprocess=True``) is captured once per input shape into a CUDA graph;
+    a call is one device-to-device copy into the graph's static input + one ``cudaGraphLaunch``.
+
+    ``__call__(x)`` keeps the module contract (``Dict[task, Tensor(B, ncls)]`` on the device, views of one packed
+    tensor).  With ``host_outputs=True`` the packed logits are copied to pinned host memory inside the graph and the
+    call synchronises once, so the caller's 12 ``.cpu()`` reads cost nothing.  Outputs are views of static buffers:
+    consume them before the next call."""
+
+    def __init__(self, model, postprocess: bool = False, prob_threshold: float = 0.0, host_outputs: bool = False):
+        self.model = model
+        self.postprocess = postprocess
+        self.prob_threshold = float(prob_threshold)
+        self.host_outputs = host_outputs
+        self._graphs = {}
+
+    def _capture(self, x: torch.Tensor):
+        from . import prepost
+        dev = x.device
+        static_in = torch.empty_like(x)
+        static_in.copy_(x)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):                       # packs weights, sizes the workspace, sets kernel attributes
+                lg = self.model.forward_packed(static_in)
+                if self.postprocess:
+                    prepost.postprocess(lg, self.model.num_classes_per_task, self.prob_threshold)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        host = None
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g), torch.no_grad():
+            logits = self.model.forward_packed(static_in)
+            post = prepost.postprocess(logits, self.model.num_classes_per_task, self.prob_threshold) if self.postprocess else None
+            if self.host_outputs:
+                host = torch.empty(logits.shape, dtype=logits.dtype, pin_memory=True)
+                host.copy_(logits, non_blocking=True)
+        return {"graph": g, "in": static_in, "logits": logits, "post": post, "host": host}
+
+    @torch.no_grad()
+    def forward_packed(self, x: torch.Tensor):
+        if not x.is_cuda:
+            raise RuntimeError("GraphedPMG needs a CUDA tensor: there is no CPU fallback")
+        key = (tuple(x.shape), x.dtype, x.device)
+        st = self._graphs.get(key)
+        if st is None:
+            st = self._graphs[key] = self._capture(x.contiguous())
+        else:
+            st["in"].copy_(x, non_blocking=True)
+        st["graph"].replay()
+        if self.host_outputs:
+            torch.cuda.current_stream(x.device).synchronize()
+            return st["host"]
+        return st["logits"]
+
+    def __call__(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
+        return self.model._split(self.forward_packed(x))
+
+    def predictions(self, x: torch.Tensor):
+        """(probs, preds, max_probs) of prepost.postprocess for this batch (requires ``postprocess=True``)."""
+        if not self.postprocess:
+            raise RuntimeError("construct GraphedPMG(..., postprocess=True)")
+        self.forward_packed(x)
+        return self._graphs[(tuple(x.shape), x.dtype, x.device)]["post"]
