@@ -19,6 +19,7 @@
 #include "tc_gram.cuh"
 #include "tc_front.cuh"
 #include "tc_encoder.cuh"
+#include "tc_gramb.cuh"
 
 namespace pmg {
 
@@ -613,7 +614,49 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
 // ------------------------------------------------------------------------------------------------
 // test / microbenchmark hooks
 // ------------------------------------------------------------------------------------------------
-int gram_batched_fast(const void*, int, int, int, int, float, float*, cudaStream_t) { return PMG_ERR_UNSUPPORTED; }
+static int make_tmap_gram3d(CUtensorMap* m, const void* base, int B, int C, int HW, uint32_t box_rows) {
+    tc::EncodeTiledFn fn = tc::encode_fn();
+    if (!fn) { set_cuda_error(cudaErrorNotSupported, "cuTensorMapEncodeTiled entry point"); return PMG_ERR_CUDA; }
+    cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B};
+    cuuint64_t strides[2] = {(cuuint64_t)HW * 2, (cuuint64_t)C * HW * 2};
+    cuuint32_t box[3] = {64, box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(gram 3d)"); return PMG_ERR_CUDA; }
+    return PMG_OK;
+}
+
+template <int BN>
+static int launch_gram_tc(const void* F, int B, int C, int HW, float scale, float* G, cudaStream_t st) {
+    CUtensorMap ta, tb;
+    int rc;
+    if ((rc = make_tmap_gram3d(&ta, F, B, C, HW, 128))) return rc;
+    if ((rc = make_tmap_gram3d(&tb, F, B, C, HW, BN))) return rc;
+    constexpr int smem = tc::gb_smem_bytes<BN>();
+    static bool attr_set = false;
+    if (!attr_set) {
+        PMG_CUDA_OK(cudaFuncSetAttribute(tc::gram_batched_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "gram tc smem attr");
+        attr_set = true;
+    }
+    tc::GramBParams p{G, B, C, HW, scale};
+    const long long items = (long long)B * ((C + 127) / 128) * ((C + BN - 1) / BN);
+    const int grid = (int)(items < tc::num_sms() ? items : tc::num_sms());
+    tc::gram_batched_tc_kernel<BN><<<grid, tc::GB_THREADS, smem, st>>>(ta, tb, p);
+    PMG_LAUNCH_OK("gram_batched_tc");
+    return PMG_OK;
+}
+
+// tcgen05 batched Gram (tc_gramb.cuh): bf16 input whose rows TMA can address (HW % 8 == 0: 16-byte pitch)
+int gram_batched_fast(const void* F, int f_dtype, int B, int C, int HW, float scale, float* G, cudaStream_t st) {
+    if (f_dtype != PMG_BF16 || HW % 8 != 0 || C % 4 != 0 || C < 16) return PMG_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(F) & 15) || (reinterpret_cast<uintptr_t>(G) & 15)) return PMG_ERR_UNSUPPORTED;
+    if (C <= 32) return launch_gram_tc<32>(F, B, C, HW, scale, G, st);
+    if (C <= 64) return launch_gram_tc<64>(F, B, C, HW, scale, G, st);
+    if (C <= 96) return launch_gram_tc<96>(F, B, C, HW, scale, G, st);
+    return launch_gram_tc<128>(F, B, C, HW, scale, G, st);
+}
 
 }  // namespace pmg
 

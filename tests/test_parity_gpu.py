@@ -121,11 +121,15 @@ def test_full_size_properties():
 def test_gram_microbench_kernel_matches_matmul():
     from pmg_b200.gram import gram_batched
     gen = torch.Generator(device="cuda").manual_seed(0)
-    for (B, C, HW) in [(4, 96, 25), (3, 128, 16), (2, 64, 196), (2, 256, 1000), (1, 512, 3136)]:
+    # HW % 8 == 0 → tcgen05 kernel (tc_gramb.cuh), incl. partial k-block tails (HW 200, 1000), channel counts that
+    # are not a tile multiple (80, 320) and the multi-tile C = 512; HW 25 / fp32 input → CUDA-core kernel
+    for (B, C, HW) in [(4, 96, 25), (3, 128, 16), (5, 64, 16), (2, 64, 196), (3, 80, 200), (2, 96, 3136), (2, 256, 1000),
+                       (2, 320, 64), (1, 512, 3136), (150, 128, 64), (2, 512, 16384)]:
         F = torch.randn(B, C, HW, device="cuda", generator=gen).to(torch.bfloat16)
         ref = torch.matmul(F.double(), F.double().mT) / HW
         got = gram_batched(F)
-        assert rel_fro(got.cpu().numpy(), ref.cpu().numpy()) <= 1e-5, (B, C, HW)
+        # tensor-core fp32 accumulation over K = HW terms: measured 3e-8 (HW 16) … 5.5e-5 (HW 16384); gate 1e-3 (north_star)
+        assert rel_fro(got.cpu().numpy(), ref.cpu().numpy()) <= (2e-4 if HW % 8 == 0 else 1e-5), (B, C, HW)
         got2 = gram_batched(F.float(), scale=1.0 / (C * HW))
         assert rel_fro(got2.cpu().numpy(), (ref * HW / (C * HW)).cpu().numpy()) <= 1e-5
 
