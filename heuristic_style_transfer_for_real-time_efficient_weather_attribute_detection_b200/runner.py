@@ -114,7 +114,9 @@ class HostPipeline:
         self._out = None
 
     @torch.no_grad()
-    def infer(self, x_host: torch.Tensor) -> torch.Tensor:
+    def infer(self, x_host: torch.Tensor, sync: bool = True) -> torch.Tensor:
+        """Returns the logits in pinned host memory.  ``sync=True`` (default) blocks until the last device→host copy has
+        landed, i.e. the returned tensor is readable; ``sync=False`` only orders the current stream after the work."""
         assert x_host.device.type == "cpu" and x_host.is_pinned(), "pass a pinned host tensor"
         B = x_host.shape[0]
         L = self.model._n_logits
@@ -151,6 +153,8 @@ class HostPipeline:
                 consumed[i].record(self.compute_stream)
                 self._out[lo:hi].copy_(logits, non_blocking=True)
         cur.wait_stream(self.compute_stream)
+        if sync:
+            self.compute_stream.synchronize()
         return self._out[:B]
 
 

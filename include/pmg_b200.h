@@ -197,6 +197,9 @@ int pmg_tc_gemm(const void* a_hi, const void* a_lo, const void* b, int M, int N,
  * kernel records clock64() stamps of its warp roles there (scratch/enc_trace.py decodes them).  NULL switches it off.
  * Process-global; not thread safe. */
 void pmg_debug_set_trace(void* dev_buf_512_i64);
+/* Hardware probe (tools/tmem_a_probe.py): D[128x64] fp32 = A[128x64] · B[64x64]^T, bf16 row-major inputs, with the A
+ * operand of the MMA read from tensor memory. */
+int pmg_debug_tmem_a(const void* A, const void* B, float* D, pmg_stream_t stream);
 
 #ifdef __cplusplus
 }
