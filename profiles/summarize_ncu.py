@@ -47,7 +47,7 @@ def launches_md(path: str, tag: str) -> str:
         a = agg.setdefault(n, {"n": 0, "us": 0.0, "grid": g, "block": b})
         a["n"] += 1
         a["us"] += us
-    ours = {k: v for k, v in agg.items() if not k.startswith("at::")}
+    ours = {k: v for k, v in agg.items() if not k.startswith("at::") and "profile_delay_kernel" not in k}
     tot = sum(v["us"] for v in ours.values())
     out = [f"# ncu launch list — {tag}", "",
            "`ncu --metrics gpu__time_duration.sum --clock-control none` (cold-cache, serialised launches: compare",
