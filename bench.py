@@ -33,6 +33,7 @@ STAGES = {
     "im2col0": (0, 3 * 224 * 224 * 2 + 3136 * 64 * 2),
     "conv0": (9_633_792, 3136 * 64 * 2 + 2 * 196 * 512 * 2),
     "conv1": (12_845_056, 2 * 196 * 512 * 2 + 2 * 196 * 64 * 2),
+    "conv2_chan_proj": (3_211_264 + 4_816_896, 2 * 196 * 64 * 2 + 196 * 96 * 4),
     "conv2": (3_211_264, 2 * 196 * 64 * 2 + 2 * 196 * 128 * 2),
     "chan_proj": (4_816_896, 2 * 196 * 128 * 2 + 196 * 96 * 4),
     "gram": (4_147_200, 196 * 96 * 4 + 2 * 9 * 9216 * 2),

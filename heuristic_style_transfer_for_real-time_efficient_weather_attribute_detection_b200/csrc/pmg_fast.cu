@@ -19,6 +19,7 @@
 #include "tc_gram.cuh"
 #include "tc_front.cuh"
 #include "tc_encoder.cuh"
+#include "tc_mid.cuh"
 #include "tc_gramb.cuh"
 
 namespace pmg {
@@ -430,8 +431,9 @@ size_t fast_workspace_bytes(const Plan&, const Shape&, int B) { return fast_ws(B
 // bf16 input: fused front kernel (1 launch) instead of im2col + conv0 + conv1 (3 launches)
 int fast_launch_count(const Plan& p, const Shape&, int, unsigned flags) {
     const int front = (flags & PMG_FLAG_NO_FUSED_FRONT) ? 3 : 1;
-    if (!(flags & PMG_FLAG_NO_FUSED_ENCODER) && p.nl <= tc::ENC_MAX_LAYERS) return front + 2 + 1 + 1 + 1;   // conv2, chan_proj, Gram, token_proj, token stage
-    return front + 2 + 1 + 1 + 1 + 6 * p.nl + (p.nl > 1 ? p.nl - 1 : 0) + 3;
+    const int mid = (flags & PMG_FLAG_NO_FUSED_MID) ? 2 : 1;                                                 // conv2 + chan_proj
+    if (!(flags & PMG_FLAG_NO_FUSED_ENCODER) && p.nl <= tc::ENC_MAX_LAYERS) return front + mid + 1 + 1 + 1;   // + Gram, token_proj, token stage
+    return front + mid + 1 + 1 + 1 + 6 * p.nl + (p.nl > 1 ? p.nl - 1 : 0) + 3;
 }
 
 template <int BN, int NA, int EPI, int ACT>
@@ -503,6 +505,25 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
         return rc;
     PMG_MARK(tm, "conv1");
     }
+    if (!(flags & PMG_FLAG_NO_FUSED_MID)) {
+        // conv2 (:124-128) + chan_proj (:136,182) in one kernel: the 128-channel activation stays on chip (tc_mid.cuh)
+        CUtensorMap ta_hi, ta_lo, tw2, tw3;
+        if ((rc = tc::make_tmap_bf16(&ta_hi, Hb(w.act1_hi), P, 64, 64, 128))) return rc;
+        if ((rc = tc::make_tmap_bf16(&ta_lo, Hb(w.act1_lo), P, 64, 64, 128))) return rc;
+        if ((rc = tc::make_tmap_bf16(&tw2, Wb(f.w2), 128, 64, 64, 128))) return rc;
+        if ((rc = tc::make_tmap_bf16(&tw3, Wb(f.w3), 96, 128, 128, 96))) return rc;
+        static bool attr_set = false;
+        if (!attr_set) {
+            PMG_CUDA_OK(cudaFuncSetAttribute(tc::mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::MID_SMEM), "mid smem attr");
+            attr_set = true;
+        }
+        tc::MidParams mp;
+        mp.scale2 = Pf(L.conv_scale[2]); mp.shift2 = Pf(L.conv_shift[2]); mp.chan = Ff(w.chan); mp.P = P;
+        const int tiles = (P + 127) / 128;
+        const int grid = tiles < tc::num_sms() ? tiles : tc::num_sms();
+        PMG_CUDA_OK(tc::launch_pdl(tc::mid_kernel, dim3(grid), dim3(tc::MID_THREADS), tc::MID_SMEM, st, ta_hi, ta_lo, tw2, tw3, mp), "mid_kernel");
+        PMG_MARK(tm, "conv2_chan_proj");
+    } else {
     // conv2: final 1×1 (:124-128)
     if ((rc = gemm<128, 2, tc::EPI_SPLIT, tc::GACT_LEAKY>(Hb(w.act1_hi), Hb(w.act1_lo), 64, Wb(f.w2), P, 128, 64, 128, nullptr,
                    Hb(w.act2_hi), Hb(w.act2_lo), Pf(L.conv_scale[2]), Pf(L.conv_shift[2]), nullptr, 1, 0, st)))
@@ -513,6 +534,7 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
                    nullptr, nullptr, nullptr, nullptr, nullptr, 1, 0, st)))
         return rc;
     PMG_MARK(tm, "chan_proj");
+    }
     if (taps && taps->chan)
         PMG_CUDA_OK(cudaMemcpyAsync(taps->chan, Ff(w.chan), (size_t)P * 96 * 4, cudaMemcpyDeviceToDevice, st), "tap chan");
     // patches + Gram (:185-188)

@@ -60,6 +60,7 @@ typedef struct pmg_config {
 #define PMG_FLAG_FORCE_GENERIC 1u  /* skip the tcgen05 fast path even when the config/shape allow it */
 #define PMG_FLAG_FORCE_FAST 2u     /* fail with PMG_ERR_UNSUPPORTED instead of using the generic kernels */
 #define PMG_FLAG_NO_FUSED_FRONT 4u /* fast path: run conv0/conv1 as im2col + two GEMMs instead of the fused TMA-fed kernel */
+#define PMG_FLAG_NO_FUSED_MID 16u /* fast path: run conv2 and chan_proj as two GEMMs instead of the fused kernel */
 #define PMG_FLAG_NO_FUSED_ENCODER 8u /* fast path: run the transformer / pooling / heads as separate kernels instead of the fused token-stage kernel */
 
 /* Optional taps for parity tests: any non-null member receives that intermediate in fp32.
