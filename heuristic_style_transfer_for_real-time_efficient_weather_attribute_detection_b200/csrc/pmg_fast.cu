@@ -9,7 +9,7 @@
 //   conv1  [B·196, 512]  × [512, 64]   + BN + LeakyReLU                                       :115-117
 //   conv2  [B·196, 64]   × [64, 128]   + BN + LeakyReLU                                       :125-127
 //   chan   [B·196, 128]  × [128, 96]                                                          :136,182
-//   token  [B·9, 9216]   × [9216, 192] split-K                                                :141,193
+//   token  [B·9, 6144]   × [6144, 192] split-K (9216 folded to the 6 upper 32×32 Gram blocks) :141,193
 //   encoder linears (QKV, out-proj, FFN)                                                      :64-69,194
 // Activations travel between kernels as two bf16 planes (hi + lo, ~16 significant bits) so the result
 // stays within the 1e-3 parity gate with wide margin (DESIGN.md "precision").  Per-patch Gram, LayerNorm,
@@ -35,7 +35,8 @@ using bf16 = __nv_bfloat16;
 // layout of the fast section of the packed weights (bf16, [N][K] K-contiguous = UMMA "K-major" B operand)
 // ------------------------------------------------------------------------------------------------
 struct FastW {
-    size_t w0, w1, w2, w3, wt;          // conv0 [32][64] (K 48 zero-padded to 64), conv1 [64][512] (K = (sy,sx,c)), conv2 [128][64], chan [96][128], token [192][9216]
+    size_t w0, w1, w2, w3;              // conv0 [32][64] (K 48 zero-padded to 64), conv1 [64][512] (K = (sy,sx,c)), conv2 [128][64], chan [96][128]
+    size_t wth, wtl;                     // token_proj folded over the Gram's symmetry: hi [192][6144], lo [192][3072] (off-diagonal blocks)
     size_t win[8], wo[8], wf1[8], wf2[8];
     size_t w0x, w1x;                     // fused front end: block-sparse conv0 [128][192], conv1 as (sy,kb) blocks [512][64]
     size_t wq;                           // [64][192]: rows 0..ntask-1 task queries, then the ncls_total classifier rows, zero pad
@@ -48,7 +49,7 @@ static FastW fast_w(const Plan& p) {
     size_t o = 0;
     auto take = [&](size_t n) { size_t r = o; o = align256(o + n * sizeof(bf16)); return r; };
     f.w0 = take(32 * 64); f.w1 = take(64 * 512); f.w2 = take(128 * 64); f.w3 = take(96 * 128);
-    f.wt = take((size_t)192 * 9216);
+    f.wth = take((size_t)192 * 6144); f.wtl = take((size_t)192 * 3072);
     for (int l = 0; l < p.nl && l < 8; ++l) {
         f.win[l] = take(576 * 192); f.wo[l] = take(192 * 192); f.wf1[l] = take(384 * 192); f.wf2[l] = take(192 * 384);
     }
@@ -109,6 +110,26 @@ __global__ void pack_w1x_kernel(const float* __restrict__ in, bf16* __restrict__
     out[i] = __float2bfloat16_rn(in[((n * 32 + c) * 4 + sy) * 4 + sx]);
 }
 
+// token_proj weight (192, 96·96) folded over G = Gᵀ.  The Gram kernel stores only the 6 upper 32×32 blocks of each
+// 96×96 matrix, K' = blk·1024 + il·32 + jl with blk order (0,0) (1,1) (2,2) | (0,1) (0,2) (1,2):
+//   diagonal block (b,b):      W'[n][K'] = W[n][(32b+il)·96 + 32b+jl]                                   (exact in bf16)
+//   off-diagonal (bi < bj):    W'[n][K'] = W[n][(32bi+il)·96 + 32bj+jl] + W[n][(32bj+jl)·96 + 32bi+il]   (hi + lo planes)
+__global__ void pack_wt_folded_kernel(const float* __restrict__ in, bf16* __restrict__ hi, bf16* __restrict__ lo) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 192 * 6144) return;
+    const int n = i / 6144, k = i % 6144, blk = k >> 10, il = (k >> 5) & 31, jl = k & 31;
+    const float* w = in + (size_t)n * 9216;
+    if (blk < 3) {
+        hi[i] = __float2bfloat16_rn(w[(32 * blk + il) * 96 + 32 * blk + jl]);
+    } else {
+        const int bi = blk == 5 ? 1 : 0, bj = blk == 3 ? 1 : 2;
+        const float v = w[(32 * bi + il) * 96 + 32 * bj + jl] + w[(32 * bj + jl) * 96 + 32 * bi + il];
+        const bf16 h = __float2bfloat16_rn(v);
+        hi[i] = h;
+        lo[(size_t)n * 3072 + (k - 3072)] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
 int pack_fast(const Plan& p, const PackedLayout& L, const float* const* prm, char* packed, cudaStream_t st) {
     if (!is_committed(p)) return PMG_OK;
     const FastW f = fast_w(p);
@@ -124,7 +145,7 @@ int pack_fast(const Plan& p, const PackedLayout& L, const float* const* prm, cha
     pack_w1x_kernel<<<(512 * 64 + 255) / 256, 256, 0, st>>>(prm[5], Bp(f.w1x));
     cvt(prm[10], f.w2, 128 * 64);
     cvt(prm[15], f.w3, 96 * 128);
-    cvt(prm[16], f.wt, (size_t)192 * 9216);
+    pack_wt_folded_kernel<<<(192 * 6144 + 255) / 256, 256, 0, st>>>(prm[16], Bp(f.wth), Bp(f.wtl));
     int i = 18;
     for (int l = 0; l < p.nl; ++l) {
         cvt(prm[i], f.win[l], 576 * 192);
@@ -393,7 +414,7 @@ __global__ void __launch_bounds__(256) pool_finish_kernel(const FinishArgs a) {
 struct FastWs {
     size_t a0_hi, a0_lo, act0_hi, act0_lo, act1_hi, act1_lo, act2_hi, act2_lo, chan, g_hi, g_lo, partial, tok,
         h_hi, h_lo, qkv, ffh_hi, ffh_lo, sc, total;
-    int splits;
+    int splits, splits_lo;               // split-K factors of the two token_proj GEMMs (hi weights K 6144, lo weights K 3072)
 };
 
 static int token_splits(int T) {
@@ -401,7 +422,7 @@ static int token_splits(int T) {
     int s = 148 / tiles;
     if (s < 1) s = 1;
     if (s > 16) s = 16;
-    return tc::effective_splits(9216, s);
+    return s;
 }
 
 static FastWs fast_ws(int B) {
@@ -414,9 +435,10 @@ static FastWs fast_ws(int B) {
     w.act1_hi = take(P * 64 * 2); w.act1_lo = take(P * 64 * 2);
     w.act2_hi = take(P * 128 * 2); w.act2_lo = take(P * 128 * 2);
     w.chan = take(P * 96 * 4);
-    w.g_hi = take(T * 9216 * 2); w.g_lo = take(T * 9216 * 2);
-    w.splits = token_splits((int)T);
-    w.partial = take((size_t)w.splits * T * 192 * 4);
+    w.g_hi = take(T * 6144 * 2); w.g_lo = take(T * 6144 * 2);
+    w.splits = tc::effective_splits(6144, token_splits((int)T));
+    w.splits_lo = tc::effective_splits(3072, token_splits((int)T));
+    w.partial = take((size_t)(w.splits + w.splits_lo) * T * 192 * 4);
     w.tok = take(T * 192 * 4);
     w.h_hi = take(T * 192 * 2); w.h_lo = take(T * 192 * 2);
     w.qkv = take(T * 576 * 4);
@@ -432,8 +454,8 @@ size_t fast_workspace_bytes(const Plan&, const Shape&, int B) { return fast_ws(B
 int fast_launch_count(const Plan& p, const Shape&, int, unsigned flags) {
     const int front = (flags & PMG_FLAG_NO_FUSED_FRONT) ? 3 : 1;
     const int mid = (flags & PMG_FLAG_NO_FUSED_MID) ? 2 : 1;                                                 // conv2 + chan_proj
-    if (!(flags & PMG_FLAG_NO_FUSED_ENCODER) && p.nl <= tc::ENC_MAX_LAYERS) return front + mid + 1 + 1 + 1;   // + Gram, token_proj, token stage
-    return front + mid + 1 + 1 + 1 + 6 * p.nl + (p.nl > 1 ? p.nl - 1 : 0) + 3;
+    if (!(flags & PMG_FLAG_NO_FUSED_ENCODER) && p.nl <= tc::ENC_MAX_LAYERS) return front + mid + 1 + 2 + 1;   // + Gram, token_proj (2), token stage
+    return front + mid + 1 + 2 + 1 + 6 * p.nl + (p.nl > 1 ? p.nl - 1 : 0) + 3;
 }
 
 template <int BN, int NA, int EPI, int ACT>
@@ -551,8 +573,12 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
     PMG_MARK(tm, "gram");
     // token_proj (:192-193): split-K partial sums, reduced (+bias) by tok_ln_kernel
     const size_t pstride = (size_t)T * 192;
-    if ((rc = gemm<192, 2, tc::EPI_PARTIAL, tc::GACT_NONE>(Hb(w.g_hi), Hb(w.g_lo), 9216, Wb(f.wt), T, 192, 9216, 192,
+    // G' (upper blocks, hi+lo) · W'hᵀ, then the off-diagonal part of G'hi · W'lᵀ as extra split-K partials
+    if ((rc = gemm<192, 2, tc::EPI_PARTIAL, tc::GACT_NONE>(Hb(w.g_hi), Hb(w.g_lo), 6144, Wb(f.wth), T, 192, 6144, 192,
                    Ff(w.partial), nullptr, nullptr, nullptr, nullptr, nullptr, w.splits, pstride, st)))
+        return rc;
+    if ((rc = gemm<192, 1, tc::EPI_PARTIAL, tc::GACT_NONE>(Hb(w.g_hi) + 3072, nullptr, 6144, Wb(f.wtl), T, 192, 3072, 192,
+                   Ff(w.partial) + (size_t)w.splits * pstride, nullptr, nullptr, nullptr, nullptr, nullptr, w.splits_lo, pstride, st)))
         return rc;
     PMG_MARK(tm, "token_proj");
     if (!(flags & PMG_FLAG_NO_FUSED_ENCODER) && p.nl <= tc::ENC_MAX_LAYERS) {
@@ -564,7 +590,7 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
         }
         tc::EncParams e{};
         e.wstream = reinterpret_cast<const uint8_t*>(fb + f.wenc);
-        e.partial = Ff(w.partial); e.pstride = pstride; e.nsplit = w.splits; e.tok_bias = Pf(L.tok_b);
+        e.partial = Ff(w.partial); e.pstride = pstride; e.nsplit = w.splits + w.splits_lo; e.tok_bias = Pf(L.tok_b);
         e.cls_bias = Pf(L.cls_b); e.logits = logits;
         e.tok_in = taps ? taps->tokens_in : nullptr; e.tok_out = taps ? taps->tokens_out : nullptr;
         e.nl = p.nl; e.B = B; e.ntask = p.ntask; e.ncls_total = p.ncls_total; e.trace = g_enc_trace;
@@ -582,7 +608,7 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
     }
     {
         const TfLayerOff* t0 = p.nl > 0 ? &L.tf[0] : nullptr;
-        PMG_CUDA_OK(tc::launch_pdl(tok_ln_kernel, dim3((T + 3) / 4), dim3(128), 0, st, (const float*)Ff(w.partial), w.splits, pstride,
+        PMG_CUDA_OK(tc::launch_pdl(tok_ln_kernel, dim3((T + 3) / 4), dim3(128), 0, st, (const float*)Ff(w.partial), w.splits + w.splits_lo, pstride,
                                    Pf(L.tok_b), Ff(w.tok), t0 ? Pf(t0->ln1w) : (const float*)nullptr,
                                    t0 ? Pf(t0->ln1b) : (const float*)nullptr, Hb(w.h_hi), Hb(w.h_lo), T, t0 ? 1 : 0), "tok_ln");
         PMG_MARK(tm, "tok_reduce_ln");

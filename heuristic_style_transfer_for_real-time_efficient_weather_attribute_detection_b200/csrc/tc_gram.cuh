@@ -10,8 +10,8 @@
 //   * one thread issues 6 tcgen05.mma (M=128 rows incl. 32 pad rows, N=96, K=2×16):
 //         D = Ph·Phᵀ + Ph·Plᵀ + Pl·Phᵀ            (fp32 in TMEM; Pl·Plᵀ ≈ 2⁻¹⁸ relative is dropped)
 //     the SAME smem tile serves as A and B operand, so P is read from global once;
-//   * 3 epilogue warps pull D out of TMEM, scale by 1/25, split into hi/lo bf16 and store the token's
-//     9216-entry row that token_proj consumes (192-byte contiguous runs per thread), plus fp32 G on request.
+//   * 9 epilogue warps (one per 32×32 block) pull D out of TMEM, scale by 1/25, split into hi/lo bf16 and store the
+//     6 upper blocks (G is symmetric) as the token's 6144-entry row that token_proj consumes, plus fp32 G on request.
 // smem operand stages (3) and TMEM accumulators (2) are multi-buffered, so loads, MMAs and the 36 KB/token
 // store stream overlap.
 #pragma once
@@ -124,11 +124,16 @@ gram96_tc_kernel(const float* __restrict__ chan, __nv_bfloat16* __restrict__ g_h
             }
         }
     } else {
-        // ===== epilogue: 9 warps, warp w ↔ TMEM lane quarter q = w%4 (rows 32q..32q+31, q < 3) and the
-        // 32-column chunk (w-4)/4; one warp per (quarter, chunk) keeps three times as many warps in flight =====
+        // ===== epilogue: 9 warps, warp w ↔ 32×32 block (q, ch) of G: TMEM lane quarter q = w%4 (rows 32q..32q+31,
+        // q < 3) and 32-column chunk ch = (w-4)/4.  G is symmetric, so only the 6 upper blocks (ch ≥ q) are stored for
+        // token_proj (which runs on weights folded accordingly, pmg_fast.cu: pack_wt_folded_kernel): per token
+        // 6144 instead of 9216 entries, block order (0,0) (1,1) (2,2) | (0,1) (0,2) (1,2), row-major inside a block.
         const int q = warp & 3;
         {
-            const int c0 = ((warp - 4) >> 2) * 32;
+            const int ch = (warp - 4) >> 2;
+            const int c0 = ch * 32;
+            const bool upper = ch >= q;
+            const int blk = ch == q ? q : q + ch + 2;
             uint8_t* wbuf = s_stage + (warp - 4) * 4096;
             const int sr = lane >> 3, sc = lane & 7;
             uint32_t it = 0;
@@ -137,26 +142,31 @@ gram96_tc_kernel(const float* __restrict__ chan, __nv_bfloat16* __restrict__ g_h
                 mbar_wait(&tmem_full_bar[as], aph);
                 tc_fence_after();
                 uint32_t r[32];
-                tmem_ld_32x32b_x32(tmem_base + as * 128 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-                tmem_ld_wait();
+                if (upper || g_f32) {
+                    tmem_ld_32x32b_x32(tmem_base + as * 128 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+                    tmem_ld_wait();
+                }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
-                uint32_t w[32];
+                if (upper) {
+                    uint32_t w[32];
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    split_bf16x2(__uint_as_float(r[2 * j]) * 0.04f, __uint_as_float(r[2 * j + 1]) * 0.04f, w[j], w[16 + j]);
-                // row slice [hi 64 B | lo 64 B] → warp-private swizzled staging → 8 lanes per row, coalesced
-                __syncwarp();
-                stage_write_row(wbuf, lane, w);
-                __syncwarp();
-                const size_t tbase = (size_t)tok * 9216 + (size_t)(q * 32 + sr) * 96 + c0 + (sc & 3) * 8;
-                __nv_bfloat16* dst = (sc < 4 ? g_hi : g_lo) + tbase;
+                    for (int j = 0; j < 16; ++j)
+                        split_bf16x2(__uint_as_float(r[2 * j]) * 0.04f, __uint_as_float(r[2 * j + 1]) * 0.04f, w[j], w[16 + j]);
+                    // row slice [hi 64 B | lo 64 B] → warp-private swizzled staging → 8 lanes per row: one store
+                    // instruction covers 4 rows = 256 contiguous bytes of the block in each plane
+                    __syncwarp();
+                    stage_write_row(wbuf, lane, w);
+                    __syncwarp();
+                    const size_t tbase = (size_t)tok * 6144 + (size_t)blk * 1024 + (size_t)sr * 32 + (sc & 3) * 8;
+                    __nv_bfloat16* dst = (sc < 4 ? g_hi : g_lo) + tbase;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int rr = 4 * i + sr;
-                    *reinterpret_cast<uint4*>(dst + (size_t)(4 * i) * 96) =
-                        *reinterpret_cast<const uint4*>(wbuf + rr * 128 + ((sc ^ (rr & 7)) << 4));
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = 4 * i + sr;
+                        *reinterpret_cast<uint4*>(dst + (size_t)(4 * i) * 32) =
+                            *reinterpret_cast<const uint4*>(wbuf + rr * 128 + ((sc ^ (rr & 7)) << 4));
+                    }
                 }
                 if (g_f32) {
                     float4* df = reinterpret_cast<float4*>(g_f32 + (size_t)tok * 9216 + (size_t)(q * 32 + lane) * 96 + c0);
