@@ -574,6 +574,8 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
     // token_proj (:192-193): split-K partial sums, reduced (+bias) by tok_ln_kernel
     const size_t pstride = (size_t)T * 192;
     // G' (upper blocks, hi+lo) · W'hᵀ, then the off-diagonal part of G'hi · W'lᵀ as extra split-K partials
+    // (the CTA-pair variant tc_gemm2.cuh — tcgen05 cta_group::2 — is parity-tested and measured 64 us here vs 60 us
+    // for these cta_group::1 launches: the op is tensor-bound at ~56 % of peak either way, so it is not the default)
     if ((rc = gemm<192, 2, tc::EPI_PARTIAL, tc::GACT_NONE>(Hb(w.g_hi), Hb(w.g_lo), 6144, Wb(f.wth), T, 192, 6144, 192,
                    Ff(w.partial), nullptr, nullptr, nullptr, nullptr, nullptr, w.splits, pstride, st)))
         return rc;
@@ -709,6 +711,13 @@ int gram_batched_fast(const void* F, int f_dtype, int B, int C, int HW, float sc
 }  // namespace pmg
 
 extern "C" void pmg_debug_set_trace(void* dev_buf_512_i64) { pmg::g_enc_trace = reinterpret_cast<long long*>(dev_buf_512_i64); }
+
+extern "C" int pmg_tc_gemm2(const void* a_hi, const void* a_lo, const void* b, int M, int K, int splits, float* out, pmg_stream_t stream) {
+    if (!a_hi || !b || !out) return PMG_ERR_BAD_ARG;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    return a_lo ? tc::launch_gemm2_t<2>(a_hi, a_lo, K, b, K, M, K, splits, out, (size_t)M * 192, st)
+                : tc::launch_gemm2_t<1>(a_hi, a_lo, K, b, K, M, K, splits, out, (size_t)M * 192, st);
+}
 
 extern "C" int pmg_tc_gemm(const void* a_hi, const void* a_lo, const void* b, int M, int N, int K, int bn, int splits,
                            float* out, pmg_stream_t stream) {

@@ -4,6 +4,7 @@
 
 #include "pmg_common.cuh"
 #include "tc_gemm.cuh"
+#include "tc_gemm2.cuh"
 
 namespace tc {
 
@@ -33,6 +34,20 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// same, as clusters of 2 CTAs (CTA pairs for tcgen05 cta_group::2)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl_cluster2(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = 2; at[1].val.clusterDim.y = 1; at[1].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 2;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
@@ -109,6 +124,35 @@ int launch_gemm_t(const void* A_hi, const void* A_lo, int lda, const void* B, in
     const int items = ((tiles_m + gemm_mt<BN>() - 1) / gemm_mt<BN>()) * eff_splits * (p.N / BN);
     const int grid = items < num_sms() ? items : num_sms();
     PMG_CUDA_OK(launch_pdl(gemm_kernel<BN, NA, EPI, ACT>, dim3(grid), dim3(GEMM_THREADS), smem, st, ta_hi, ta_lo, tb, p), "tc gemm");
+    return PMG_OK;
+}
+
+// split-K GEMM on CTA pairs (tc_gemm2.cuh): out[s][M,192] partial sums; A planes [M,K] pitch lda, B [192,K] pitch ldb
+template <int NA>
+int launch_gemm2_t(const void* A_hi, const void* A_lo, int lda, const void* B, int ldb, int M, int K, int splits, float* out,
+                   size_t partial_stride, cudaStream_t st) {
+    if (K % GEMM_BK || M < 1 || splits < 1) return PMG_ERR_BAD_SHAPE;
+    CUtensorMap ta_hi, ta_lo, tb;
+    int rc;
+    if ((rc = make_tmap_bf16(&ta_hi, A_hi, M, K, lda, 128))) return rc;
+    if ((rc = make_tmap_bf16(&ta_lo, NA == 2 ? A_lo : A_hi, M, K, lda, 128))) return rc;
+    if ((rc = make_tmap_bf16(&tb, B, 192, K, ldb, 96))) return rc;
+    Gemm2Params p{};
+    p.M = M; p.K = K; p.out = out; p.partial_stride = partial_stride;
+    const int total_kb = K / GEMM_BK;
+    p.kblocks_per_split = (total_kb + splits - 1) / splits;
+    const int eff_splits = (total_kb + p.kblocks_per_split - 1) / p.kblocks_per_split;
+    constexpr int smem = g2_smem_bytes<NA>();
+    static bool attr_set = false;
+    if (!attr_set) {
+        PMG_CUDA_OK(cudaFuncSetAttribute(gemm2_kernel<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "gemm2 smem attr");
+        PMG_CUDA_OK(cudaFuncSetAttribute(gemm2_kernel<NA>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0), "gemm2 cluster attr");
+        attr_set = true;
+    }
+    const int items = ((M + 255) / 256) * eff_splits;
+    const int max_pairs = num_sms() / 2;
+    const int pairs = items < max_pairs ? items : max_pairs;
+    PMG_CUDA_OK(launch_pdl_cluster2(gemm2_kernel<NA>, dim3(2 * pairs), dim3(G2_THREADS), smem, st, ta_hi, ta_lo, tb, p), "tc gemm2");
     return PMG_OK;
 }
 

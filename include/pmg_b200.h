@@ -202,6 +202,10 @@ void pmg_debug_set_trace(void* dev_buf_512_i64);
  * operand of the MMA read from tensor memory. */
 int pmg_debug_tmem_a(const void* A, const void* B, float* D, pmg_stream_t stream);
 
+/* Same contract for N = 192 on CTA PAIRS (tcgen05 cta_group::2, clusters of 2): out[s][M,192] split-K partial sums
+ * (s < effective splits, always written as partials, also for splits == 1). */
+int pmg_tc_gemm2(const void* a_hi, const void* a_lo, const void* b, int M, int K, int splits, float* out, pmg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

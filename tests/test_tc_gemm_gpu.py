@@ -49,3 +49,27 @@ def test_split_activation_and_split_k(M, N, K, bn, splits):
     assert err.item() < 2e-5, err.item()
     single = _gemm(hi, None, b, bn, splits)
     assert ((single.double() - ref).norm() / ref.norm()).item() > 1e-4   # sanity: lo plane matters
+
+
+@pytest.mark.parametrize("M,K,splits,planes", [(256, 64, 1, 1), (256, 128, 1, 2), (300, 512, 2, 2), (9216, 6144, 2, 2), (90, 3072, 16, 1)])
+def test_cta_pair_gemm(M, K, splits, planes):
+    """tcgen05 cta_group::2 split-K GEMM (tc_gemm2.cuh), N = 192."""
+    from pmg_b200 import _lib
+    g = torch.Generator(device="cuda").manual_seed(M + K)
+    a = torch.randn(M, K, device="cuda", generator=g)
+    hi = a.to(torch.bfloat16)
+    lo = (a - hi.float()).to(torch.bfloat16)
+    b = torch.randn(192, K, device="cuda", generator=g).to(torch.bfloat16)
+    ref = (a.double() if planes == 2 else hi.double()) @ b.double().T
+    total_kb = K // 64
+    per = -(-total_kb // splits)
+    eff = -(-total_kb // per)
+    out = torch.full((eff, M, 192), float("nan"), device="cuda", dtype=torch.float32)
+    rc = _lib.lib.pmg_tc_gemm2(hi.data_ptr(), lo.data_ptr() if planes == 2 else None, b.data_ptr(), M, K, splits, out.data_ptr(),
+                               torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "pmg_tc_gemm2")
+    torch.cuda.synchronize()
+    got = out.sum(0)
+    assert torch.isfinite(got).all()
+    err = ((got.double() - ref).norm() / ref.norm()).item()
+    assert err < 3e-5, err
