@@ -22,7 +22,9 @@
 //     (K-major, 128-byte swizzle) for the K slice (sy, sx, c).
 //   * conv1 accumulates that K slice:  D1[pixel, 64] += A1(hi) · W1[sy] + A1(lo) · W1[sy]   (16 MMAs, M128 N64 K16).
 //
-// After the 4th slice, epilogue 1 applies BN + LeakyReLU and stores act1 as hi/lo bf16 planes [B·196, 64].
+// After the 4th slice, epilogue 1 (its own 4 warps, D1 double-buffered) applies BN + LeakyReLU and stores act1 as hi/lo
+// bf16 planes [B·196, 64] while the other warps already work on the next tile.  conv0 and conv1 MMAs are issued by two
+// different threads, so neither stream is blocked behind a barrier wait of the other.
 // Both weight tensors stay resident in smem for the life of the CTA.  D0 is double-buffered in TMEM so the
 // conv0 MMAs of slice sy+1 run under epilogue 0 of slice sy.
 #pragma once
@@ -31,7 +33,7 @@
 
 namespace tc {
 
-constexpr int FRONT_THREADS = 576;                 // warp 0 TMA, warp 1 MMA, warps 2-17 epilogue (lane quarter × 32-column group)
+constexpr int FRONT_THREADS = 736;                 // warp 0 TMA, 1 conv0 MMA issuer, 2-17 epilogue 0 (lane quarter × 32-column group), 18 conv1 MMA issuer, 19-22 epilogue 1
 constexpr int FR_W0_BYTES = 3 * 128 * 128;         // 48 KB: 3 K-blocks × [128 rows × 128 B]
 constexpr int FR_W1_BYTES = 8 * 64 * 128;          // 64 KB: (sy, kb) × [64 rows × 128 B]
 constexpr int FR_A0_SLOT = 3584;                   // one kernel row ky: 8 image rows × 448 B (7 used by the tile; 256-byte multiple)
@@ -91,10 +93,10 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     uint64_t* d0_empty = bars + 8;       // [2]
     uint64_t* a1_ready = bars + 10;
     uint64_t* a1_free = bars + 11;
-    uint64_t* d1_full = bars + 12;
-    uint64_t* d1_empty = bars + 13;
-    uint64_t* w_bar = bars + 14;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+    uint64_t* d1_full = bars + 12;       // [2]
+    uint64_t* d1_empty = bars + 14;      // [2]
+    uint64_t* w_bar = bars + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
     float* s0 = reinterpret_cast<float*>(smem + FR_OFF_PRM);
     float* h0 = s0 + 32;
     float* s1 = h0 + 32;
@@ -107,7 +109,8 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         prefetch_tmap(&tmX); prefetch_tmap(&tmW0); prefetch_tmap(&tmW1);
         for (int i = 0; i < 3; ++i) { mbar_init(&a0_full[i], 1); mbar_init(&a0_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&d0_full[i], 1); mbar_init(&d0_empty[i], 16); }
-        mbar_init(a1_ready, 16); mbar_init(a1_free, 1); mbar_init(d1_full, 1); mbar_init(d1_empty, 16); mbar_init(w_bar, 1);
+        mbar_init(a1_ready, 16); mbar_init(a1_free, 1); mbar_init(w_bar, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], 4); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -157,28 +160,12 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+        // ===================== conv0 MMA issuer =====================
         if (elect_one()) {      // one elected thread; elect.sync keeps the branch warp-uniform for ptxas (no per-MMA ELECT loops)
             constexpr uint32_t idesc0 = make_idesc_bf16(128, 128, 0, 0);
-            constexpr uint32_t idesc1 = make_idesc_bf16(128, 64, 0, 0);
-            const uint32_t aW0 = smem_u32(sW0), aW1 = smem_u32(sW1), aA0 = smem_u32(sA0), aA1 = smem_u32(sA1);
+            const uint32_t aW0 = smem_u32(sW0), aA0 = smem_u32(sA0);
             mbar_wait(w_bar, 0);
             uint32_t it = 0, g = 0, lt = 0;
-            auto mma1 = [&](uint32_t gg) {
-                const uint32_t sy = gg & 3;
-                mbar_wait(a1_ready, gg & 1);
-                if (sy == 0) mbar_wait(d1_empty, ((gg >> 2) & 1) ^ 1);
-                tc_fence_after();
-#pragma unroll
-                for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t bd = make_desc_k_sw128(aW1 + (sy * 2 + kb) * 8192 + k * 32);
-                        umma_bf16(tD1, make_desc_k_sw128(aA1 + kb * 16384 + k * 32), bd, idesc1, (sy > 0 || kb > 0 || k > 0) ? 1u : 0u);
-                        umma_bf16(tD1, make_desc_k_sw128(aA1 + 32768 + kb * 16384 + k * 32), bd, idesc1, 1u);
-                    }
-                umma_commit(a1_free);
-            };
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
                 for (int sy = 0; sy < 4; ++sy, ++g) {
                     const uint32_t as = g & 1, aph = (g >> 1) & 1;
@@ -201,16 +188,87 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                     }
                     umma_commit(&d0_full[as]);
                     FR_T(22 + 4 * sy);
-                    if (sy >= 1) mma1(g - 1);
+                }
+            }
+        }
+    } else if (warp == 18) {
+        // ===================== conv1 MMA issuer (its own thread: conv0 of later slices is never stuck behind a wait
+        // for this slice's A1 operand, and vice versa) =====================
+        if (elect_one()) {
+            constexpr uint32_t idesc1 = make_idesc_bf16(128, 64, 0, 0);
+            const uint32_t aW1 = smem_u32(sW1), aA1 = smem_u32(sA1);
+            mbar_wait(w_bar, 0);
+            uint32_t g = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+                const uint32_t db = lt & 1;
+                for (uint32_t sy = 0; sy < 4; ++sy, ++g) {
+                    mbar_wait(a1_ready, g & 1);
+                    if (sy == 0) mbar_wait(&d1_empty[db], ((lt >> 1) & 1) ^ 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t bd = make_desc_k_sw128(aW1 + (sy * 2 + kb) * 8192 + k * 32);
+                            umma_bf16(tD1 + 64 * db, make_desc_k_sw128(aA1 + kb * 16384 + k * 32), bd, idesc1, (sy > 0 || kb > 0 || k > 0) ? 1u : 0u);
+                            umma_bf16(tD1 + 64 * db, make_desc_k_sw128(aA1 + 32768 + kb * 16384 + k * 32), bd, idesc1, 1u);
+                        }
+                    umma_commit(a1_free);
                     FR_T(23 + 4 * sy);
                 }
-                mma1(g - 1);
-                umma_commit(d1_full);
+                umma_commit(&d1_full[db]);
                 FR_T(36);
             }
         }
-    } else {
-        // ===================== epilogue warps =====================
+    } else if (warp >= 19) {
+        // ===================== epilogue 1 (4 warps, one per TMEM lane quarter): act1 = LeakyReLU(BN(D1)), all 64 channels
+        // of this thread's pixel → 128 contiguous bytes per plane; runs under the next tile's slices =====================
+        const int q = warp & 3;
+        const int m = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        uint32_t lt = 0;
+        pdl_wait();          // act1 planes are still being read by the previous forward's conv2 until it completes
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+            const uint32_t db = lt & 1;
+            mbar_wait(&d1_full[db], (lt >> 1) & 1);
+            tc_fence_after();
+            if (warp == 19 && lane == 0) FR_T(60);
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32b_x32(tD1 + 64 * db + lane_addr, r0);
+            tmem_ld_32x32b_x32(tD1 + 64 * db + lane_addr + 32, r1);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&d1_empty[db]);
+            if (m < 98) {
+                const size_t o = ((size_t)(tile >> 1) * 196 + (tile & 1) * 98 + m) * 64;
+                uint4* dh = reinterpret_cast<uint4*>(p.act1_hi + o);
+                uint4* dl = reinterpret_cast<uint4*>(p.act1_lo + o);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 4; ++j4) {
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int i = 8 * j4 + 2 * j, c = half * 32 + i;
+                            const uint32_t a0 = half ? r1[i] : r0[i], a1 = half ? r1[i + 1] : r0[i + 1];
+                            float v0 = fmaf(__uint_as_float(a0), s1[c], h1[c]);
+                            float v1 = fmaf(__uint_as_float(a1), s1[c + 1], h1[c + 1]);
+                            v0 = fmaxf(v0, 0.2f * v0);
+                            v1 = fmaxf(v1, 0.2f * v1);
+                            split_bf16x2(v0, v1, hi[j], lo[j]);
+                        }
+                        dh[half * 4 + j4] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        dl[half * 4 + j4] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+            }
+            if (warp == 19 && lane == 0) FR_T(61);
+        }
+        tc_fence_before();
+    } else if (warp >= 2) {
+        // ===================== epilogue 0 warps =====================
         // 16 warps: TMEM lane quarter q = warp % 4, 32-column group cg = (warp-2)/4 = conv0 column offset sx
         const int q = warp & 3;
         const int cg = (warp - 2) >> 2;               // D0 columns cg*32 .. +31
@@ -256,34 +314,6 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                 if (lane == 0) mbar_arrive(a1_ready);
                 if (warp == 2 && lane == 0) FR_T(43 + 4 * sy);
             }
-            // ---- epilogue 1: act1 = LeakyReLU(BN(D1)), this warp's 16 of the 64 channels ----
-            mbar_wait(d1_full, lt & 1);
-            tc_fence_after();
-            if (warp == 2 && lane == 0) FR_T(60);
-            uint32_t r[16];
-            tmem_ld_32x32b_x16(tD1 + lane_addr + (uint32_t)(cg * 16), r);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(d1_empty);
-            if (m < 98) {
-                uint32_t hi[8], lo[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int c = cg * 16 + 2 * j;
-                    float v0 = fmaf(__uint_as_float(r[2 * j]), s1[c], h1[c]);
-                    float v1 = fmaf(__uint_as_float(r[2 * j + 1]), s1[c + 1], h1[c + 1]);
-                    v0 = fmaxf(v0, 0.2f * v0);
-                    v1 = fmaxf(v1, 0.2f * v1);
-                    split_bf16x2(v0, v1, hi[j], lo[j]);
-                }
-                const size_t o = ((size_t)(tile >> 1) * 196 + (tile & 1) * 98 + m) * 64 + cg * 16;
-                uint4* dh = reinterpret_cast<uint4*>(p.act1_hi + o);
-                uint4* dl = reinterpret_cast<uint4*>(p.act1_lo + o);
-                dh[0] = make_uint4(hi[0], hi[1], hi[2], hi[3]); dh[1] = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-                dl[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); dl[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
-            }
-            if (warp == 2 && lane == 0) FR_T(61);
         }
         tc_fence_before();
     }
