@@ -272,8 +272,9 @@ def main():
 
     def e2e_entry(name):
         ms_leg = e2e_ms[name]
-        return {"value": round(GB * args.steps / (ms_leg / 1e3), 1), "unit": "images/s", "h2d_bytes_per_step": B * E2E_BYTES[name],
-                "d2h_bytes_per_step": B * 52 * 4, "ms_per_step": round(ms_leg / args.steps, 4), "host_input": name}
+        return {"value": round(GB * args.steps / (ms_leg / 1e3), 1), "unit": "images/s", "h2d_bytes_per_step": GB * E2E_BYTES[name],
+                "d2h_bytes_per_step": GB * 52 * 4, "ms_per_step": round(ms_leg / args.steps, 4), "host_input": name,
+                "bytes_are": "whole job (all ranks) per step"}
 
     if rank != 0:
         if world > 1:
