@@ -36,6 +36,8 @@ STAGES = {
     "conv2_chan_proj": (3_211_264 + 4_816_896, 2 * 196 * 64 * 2 + 196 * 96 * 4),
     "conv2": (3_211_264, 2 * 196 * 64 * 2 + 2 * 196 * 128 * 2),
     "chan_proj": (4_816_896, 2 * 196 * 128 * 2 + 196 * 96 * 4),
+    # conv2 + chan_proj + Gram in one kernel: act1 hi/lo in, 6 upper 32x32 blocks of G hi/lo out (chan never leaves the SM)
+    "conv2_chan_gram": (3_211_264 + 4_816_896 + 4_147_200, 2 * 196 * 64 * 2 + 2 * 9 * 6144 * 2),
     "gram": (4_147_200, 196 * 96 * 4 + 2 * 9 * 6144 * 2),            # chan in, 6 upper 32x32 blocks of G hi/lo out
     "token_proj": (31_850_496, 2 * 9 * 6144 * 2 + 4 * 9 * 192 * 4),  # G' hi/lo in, split-K partials out (two launches)
     "tok_reduce_ln": (0, 3 * 9 * 192 * 4 + 2 * 9 * 192 * 2),

@@ -20,6 +20,7 @@
 #include "tc_front.cuh"
 #include "tc_encoder.cuh"
 #include "tc_mid.cuh"
+#include "tc_midgram.cuh"
 #include "tc_gramb.cuh"
 
 namespace pmg {
@@ -453,9 +454,10 @@ size_t fast_workspace_bytes(const Plan&, const Shape&, int B) { return fast_ws(B
 // bf16 input: fused front kernel (1 launch) instead of im2col + conv0 + conv1 (3 launches)
 int fast_launch_count(const Plan& p, const Shape&, int, unsigned flags) {
     const int front = (flags & PMG_FLAG_NO_FUSED_FRONT) ? 3 : 1;
-    const int mid = (flags & PMG_FLAG_NO_FUSED_MID) ? 2 : 1;                                                 // conv2 + chan_proj
-    if (!(flags & PMG_FLAG_NO_FUSED_ENCODER) && p.nl <= tc::ENC_MAX_LAYERS) return front + mid + 1 + 2 + 1;   // + Gram, token_proj (2), token stage
-    return front + mid + 1 + 2 + 1 + 6 * p.nl + (p.nl > 1 ? p.nl - 1 : 0) + 3;
+    // conv2 + chan_proj + Gram: one kernel (tc_midgram.cuh), or the fused mid kernel + Gram, or two GEMMs + Gram
+    const int mid = !(flags & (PMG_FLAG_NO_FUSED_MIDGRAM | PMG_FLAG_NO_FUSED_MID)) ? 1 : (flags & PMG_FLAG_NO_FUSED_MID) ? 3 : 2;
+    if (!(flags & PMG_FLAG_NO_FUSED_ENCODER) && p.nl <= tc::ENC_MAX_LAYERS) return front + mid + 2 + 1;   // + token_proj (2), token stage
+    return front + mid + 2 + 1 + 6 * p.nl + (p.nl > 1 ? p.nl - 1 : 0) + 3;
 }
 
 template <int BN, int NA, int EPI, int ACT>
@@ -527,6 +529,27 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
         return rc;
     PMG_MARK(tm, "conv1");
     }
+    const bool fused_midgram = !(flags & (PMG_FLAG_NO_FUSED_MIDGRAM | PMG_FLAG_NO_FUSED_MID));
+    if (fused_midgram) {
+        // conv2 (:124-128) + chan_proj (:136,182) + pad/patches (:157-174) + Gram (:188) in one kernel: neither the
+        // 128-channel activation nor the chan_proj map touch HBM (tc_midgram.cuh)
+        CUtensorMap ta_hi, ta_lo, tw2, tw3;
+        if ((rc = tc::make_tmap_bf16(&ta_hi, Hb(w.act1_hi), P, 64, 64, tc::MG_BOX_ROWS))) return rc;
+        if ((rc = tc::make_tmap_bf16(&ta_lo, Hb(w.act1_lo), P, 64, 64, tc::MG_BOX_ROWS))) return rc;
+        if ((rc = tc::make_tmap_bf16(&tw2, Wb(f.w2), 128, 64, 64, 128))) return rc;
+        if ((rc = tc::make_tmap_bf16(&tw3, Wb(f.w3), 96, 128, 128, 96))) return rc;
+        static bool attr_set = false;
+        if (!attr_set) {
+            PMG_CUDA_OK(cudaFuncSetAttribute(tc::midgram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::MG_SMEM), "midgram smem attr");
+            attr_set = true;
+        }
+        tc::MidGramParams mp;
+        mp.scale2 = Pf(L.conv_scale[2]); mp.shift2 = Pf(L.conv_shift[2]); mp.g_hi = Hb(w.g_hi); mp.g_lo = Hb(w.g_lo);
+        mp.g_f32 = gram; mp.chan = taps ? taps->chan : nullptr; mp.B = B;
+        const int grid = B < tc::num_sms() ? B : tc::num_sms();
+        PMG_CUDA_OK(tc::launch_pdl(tc::midgram_kernel, dim3(grid), dim3(tc::MG_THREADS), tc::MG_SMEM, st, ta_hi, ta_lo, tw2, tw3, mp), "midgram_kernel");
+        PMG_MARK(tm, "conv2_chan_gram");
+    } else {
     if (!(flags & PMG_FLAG_NO_FUSED_MID)) {
         // conv2 (:124-128) + chan_proj (:136,182) in one kernel: the 128-channel activation stays on chip (tc_mid.cuh)
         CUtensorMap ta_hi, ta_lo, tw2, tw3;
@@ -571,6 +594,7 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
                                    (const float*)Ff(w.chan), Hb(w.g_hi), Hb(w.g_lo), gram, T), "gram96_tc");
     }
     PMG_MARK(tm, "gram");
+    }
     // token_proj (:192-193): split-K partial sums, reduced (+bias) by tok_ln_kernel
     const size_t pstride = (size_t)T * 192;
     // G' (upper blocks, hi+lo) · W'hᵀ, then the off-diagonal part of G'hi · W'lᵀ as extra split-K partials

@@ -142,6 +142,7 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
         self.fused_front = True         # fast path: TMA-fed fused conv0+conv1 kernel (bf16 input); False = im2col + GEMMs
         self.fused_encoder = True       # fast path: transformer + pooling + heads in one kernel; False = per-op kernels
         self.fused_mid = True           # fast path: conv2 + chan_proj in one kernel; False = two GEMMs
+        self.fused_midgram = True       # fast path: conv2 + chan_proj + patches + Gram in one kernel; False = mid kernel + Gram kernel
 
     # kernel-side state is rebuilt on demand; keep it out of pickles / deepcopies
     def __getstate__(self):
@@ -291,7 +292,8 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
         return ((_lib.PMG_FLAG_FORCE_GENERIC if self.force_generic else 0)
                 | (0 if self.fused_front else _lib.PMG_FLAG_NO_FUSED_FRONT)
                 | (0 if getattr(self, "fused_encoder", True) else _lib.PMG_FLAG_NO_FUSED_ENCODER)
-                | (0 if getattr(self, "fused_mid", True) else _lib.PMG_FLAG_NO_FUSED_MID))
+                | (0 if getattr(self, "fused_mid", True) else _lib.PMG_FLAG_NO_FUSED_MID)
+                | (0 if getattr(self, "fused_midgram", True) else _lib.PMG_FLAG_NO_FUSED_MIDGRAM))
 
     def launches_per_forward(self, B: int, H: int = 224, W: int = 224) -> int:
         flags = self._flags()

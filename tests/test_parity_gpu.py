@@ -118,6 +118,31 @@ def test_full_size_properties():
     assert rel_fro(tr.cpu().numpy(), e.cpu().numpy()) <= 1e-4
 
 
+@pytest.mark.parametrize("batch", [1, 3, 150, 301])
+def test_fused_midgram_matches_two_kernel_path(batch):
+    """conv2 + chan_proj + Gram in one kernel (tc_midgram.cuh) vs the mid kernel + Gram kernel that pass the chan map
+    through HBM: same MMAs on the same hi/lo operands, so Gram, chan map and logits agree to fp32 summation order.
+    Batches below / just above / twice the SM count exercise the per-CTA image loop and its tail."""
+    _, hp, tasks = load_contract()
+    m = _model(hp, tasks, 3)
+    x = torch.from_numpy(synth.images(21, batch)).cuda().to(torch.bfloat16)
+    with torch.no_grad():
+        fused = m.forward_debug(x)
+        plain = m.forward_packed(x).clone()              # no taps, no fp32 Gram: the production call
+        m.fused_midgram = False
+        two = m.forward_debug(x)
+        m.fused_midgram = True
+    assert m.launches_per_forward(batch) == 5
+    assert torch.equal(fused[0], plain)
+    assert rel_fro(fused[1].cpu().numpy(), two[1].cpu().numpy()) <= 1e-6
+    assert rel_fro(fused[2]["chan"].cpu().numpy(), two[2]["chan"].cpu().numpy()) <= 1e-6
+    assert rel_fro(fused[0].cpu().numpy(), two[0].cpu().numpy()) <= 1e-5
+    ref, inter = pmg_oracle.pmg_forward(synth.images(21, min(batch, 3)), synth.pmg_state_dict(3, hp, tasks), tasks,
+                                        hp["patch_div"], hp["transformer_heads"], return_intermediates=True)
+    n = min(batch, 3)
+    _check_against(fused[0][:n].cpu().numpy(), fused[1][:n].cpu().numpy(), pmg_oracle.pack_logits(ref, tasks), inter["gram"], tasks)
+
+
 def test_gram_microbench_kernel_matches_matmul():
     from pmg_b200.gram import gram_batched
     gen = torch.Generator(device="cuda").manual_seed(0)
