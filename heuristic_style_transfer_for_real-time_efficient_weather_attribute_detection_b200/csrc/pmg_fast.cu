@@ -533,7 +533,8 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
     if (fused_midgram) {
         // conv2 (:124-128) + chan_proj (:136,182) + pad/patches (:157-174) + Gram (:188) in one kernel: neither the
         // 128-channel activation nor the chan_proj map touch HBM (tc_midgram.cuh)
-        CUtensorMap ta_hi, ta_lo, tw2, tw3;
+        CUtensorMap ta_hi, ta_lo, tw2, tw3, tw3d;
+        if ((rc = tc::make_tmap_bf16(&tw3d, Wb(f.w3), 96, 128, 128, 32))) return rc;       // 32-row box: the copy of channels 32..63
         if ((rc = tc::make_tmap_bf16(&ta_hi, Hb(w.act1_hi), P, 64, 64, tc::MG_BOX_ROWS))) return rc;
         if ((rc = tc::make_tmap_bf16(&ta_lo, Hb(w.act1_lo), P, 64, 64, tc::MG_BOX_ROWS))) return rc;
         if ((rc = tc::make_tmap_bf16(&tw2, Wb(f.w2), 128, 64, 64, 128))) return rc;
@@ -545,9 +546,9 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
         }
         tc::MidGramParams mp;
         mp.scale2 = Pf(L.conv_scale[2]); mp.shift2 = Pf(L.conv_shift[2]); mp.g_hi = Hb(w.g_hi); mp.g_lo = Hb(w.g_lo);
-        mp.g_f32 = gram; mp.chan = taps ? taps->chan : nullptr; mp.B = B;
+        mp.g_f32 = gram; mp.chan = taps ? taps->chan : nullptr; mp.B = B; mp.trace = g_enc_trace;
         const int grid = B < tc::num_sms() ? B : tc::num_sms();
-        PMG_CUDA_OK(tc::launch_pdl(tc::midgram_kernel, dim3(grid), dim3(tc::MG_THREADS), tc::MG_SMEM, st, ta_hi, ta_lo, tw2, tw3, mp), "midgram_kernel");
+        PMG_CUDA_OK(tc::launch_pdl(tc::midgram_kernel, dim3(grid), dim3(tc::MG_THREADS), tc::MG_SMEM, st, ta_hi, ta_lo, tw2, tw3, tw3d, mp), "midgram_kernel");
         PMG_MARK(tm, "conv2_chan_gram");
     } else {
     if (!(flags & PMG_FLAG_NO_FUSED_MID)) {

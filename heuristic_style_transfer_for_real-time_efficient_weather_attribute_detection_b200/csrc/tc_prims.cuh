@@ -43,14 +43,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the thread is parked in hardware until the phase completes (or the hint / the
+// system's own limit expires) and wakes as soon as it does.  Without the hint a waiting warp re-issues its
+// TRYWAIT + branch every few dozen cycles, and with 20-28 warps per CTA of which most are waiting at any time those
+// spin loops took a measurable share of the issue slots of the sub-partition they share with the working warps
+// (ncu: 12.5 k instructions per band executed in tc_midgram.cuh against 7.9 k of real work).
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, P;\n\t}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
         : "memory");
     return ok != 0;
 }
@@ -187,6 +192,13 @@ __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uin
     __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
     hi = *reinterpret_cast<uint32_t*>(&h);
     lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+// 256-bit global store (sm_100: STG.E.ENL2.256): one whole 32-byte sector per thread
+__device__ __forceinline__ void st_global_v8(void* gptr, const uint32_t* w) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(gptr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
 }
 
 // ---------------------------------------------------------------- coalescing epilogue staging
