@@ -7,7 +7,7 @@
 For N>1 launch with torchrun (one rank per GPU); rank 0 prints the line.  Workload (config.workload):
 BASELINE.json configs[2] at its largest single-GPU batch — PMG eval forward, committed hparams,
 1024 images / GPU, 3×224×224 bf16, synthetic images + seeded synthetic checkpoint.  Weak scaling: the
-per-GPU batch is fixed, the only collective is one all-gather of the packed logits per step.
+per-GPU batch is fixed, the only collective is an all-gather of the packed logits (one per --gather-steps steps).
 """
 from __future__ import annotations
 
@@ -161,6 +161,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="images per GPU per step")
     ap.add_argument("--e2e-chunk", type=int, default=128)
+    ap.add_argument("--gather-steps", type=int, default=4, help="N>1: steps whose logits share one all_gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--force-generic", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-memory end-to-end leg (ncu runs)")
@@ -176,7 +177,7 @@ def main():
     import torch.distributed as dist
     import pmg_b200
     from pmg_b200 import _lib
-    from pmg_b200.runner import HostPipeline, gather_logits_async
+    from pmg_b200.runner import BucketedGather, HostPipeline
     from oracle import synth   # seeded synthetic checkpoint generator (test infra; weights only, not compute)
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path); use --impl reference for the CPU arm"
@@ -198,24 +199,22 @@ def main():
     x = torch.randn(B, 3, 224, 224, device=dev, generator=gen).to(torch.bfloat16)
     GB = B * world
 
-    pending = [None]
+    # the logits of --gather-steps consecutive steps go out in ONE all_gather (runner.BucketedGather): each forward writes
+    # straight into its slot of the bucket, the gather of a full bucket runs under the forwards that fill the next one, and
+    # drain() gathers what is left and waits for everything, inside the timed region
+    bucket = BucketedGather(B, 52, args.gather_steps, dev) if world > 1 else None
 
     def step():
-        # forward of this step runs under the (async) logits all-gather of the previous one; every gather is
-        # waited for inside the timed region
         with torch.no_grad():
-            lg = model.forward_packed(x)
-            if world > 1:
-                nxt = gather_logits_async(lg, GB)
-                if pending[0] is not None:
-                    pending[0].result()
-                pending[0] = nxt
+            if bucket is None:
+                return model.forward_packed(x)
+            lg = model.forward_packed(x, out=bucket.slot())
+            bucket.commit()
         return lg
 
     def drain():
-        if pending[0] is not None:
-            pending[0].result()
-            pending[0] = None
+        if bucket is not None:
+            bucket.flush()
 
     def fence():
         if world > 1:
@@ -345,7 +344,8 @@ def main():
         "config": {"workload": WORKLOAD, "global_batch": GB, "per_gpu_batch": B, "parallelism": f"dp{world}",
                    "l2_policy": f"input {B * 3 * 224 * 224 * 2 / 1e6:.0f} MB per GPU per step > 126 MB L2",
                    "path": "generic-fp32" if args.force_generic else "default",
-                   "collective": "one all_gather of (B_local,52) fp32 logits per step" if world > 1 else "none"},
+                   "collective": (f"one all_gather_into_tensor of ({args.gather_steps},B_local,52) fp32 logits per {args.gather_steps} steps, "
+                                  "async under the next forwards; all waited for inside the timed region") if world > 1 else "none"},
         "clocks": clocks,
         "e2e": None if not e2e_ms else dict(
             e2e_entry("uint8_nhwc"),

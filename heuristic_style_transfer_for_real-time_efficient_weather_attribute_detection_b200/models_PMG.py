@@ -209,7 +209,7 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
         return packed
 
     # ------------------------------------------------------------------ forward
-    def _run(self, x: torch.Tensor, want_gram: bool = False, taps: bool = False):
+    def _run(self, x: torch.Tensor, want_gram: bool = False, taps: bool = False, out: Optional[torch.Tensor] = None):
         if self.training:
             raise RuntimeError("PMG B200 kernels implement the eval forward only (BatchNorm running stats, "
                                "dropout inert): call model.eval()")
@@ -239,7 +239,13 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
                 raise ValueError(f"input {tuple(x.shape)} is too small for this backbone / patch split")
             if self._ws is None or self._ws.device != x.device or self._ws.numel() < need:
                 self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
-            logits = torch.empty((B, self._n_logits), dtype=torch.float32, device=x.device)
+            if out is not None:
+                if (out.shape != (B, self._n_logits) or out.dtype != torch.float32 or out.device != x.device
+                        or not out.is_contiguous()):
+                    raise ValueError(f"out must be a contiguous ({B}, {self._n_logits}) float32 tensor on {x.device}")
+                logits = out
+            else:
+                logits = torch.empty((B, self._n_logits), dtype=torch.float32, device=x.device)
             gram = None
             extra = {}
             tp = None
@@ -275,9 +281,10 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
         logits, _, _ = self._run(x)
         return self._split(logits)
 
-    def forward_packed(self, x) -> torch.Tensor:
-        """(B, Σncls) fp32 — the dict of ``forward`` as one tensor, columns in Tasks.json order."""
-        return self._run(x)[0]
+    def forward_packed(self, x, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """(B, Σncls) fp32 — the dict of ``forward`` as one tensor, columns in Tasks.json order.  ``out``: write the
+        logits into this (B, Σncls) fp32 tensor (e.g. a slot of a gather bucket, runner.BucketedGather)."""
+        return self._run(x, out=out)[0]
 
     def forward_with_gram(self, x):
         """(dict, G) with G = per-patch Gram (B, patch_div², Cr, Cr) of reference line :188."""

@@ -68,6 +68,78 @@ def gather_logits(local: torch.Tensor, global_batch: int, group=None) -> torch.T
     return torch.cat([out[r * mx: r * mx + (hi - lo)] for r, (lo, hi) in enumerate(sizes)], dim=0)
 
 
+class BucketedGather:
+    """Gathers the logits of several consecutive micro-batches with ONE collective.
+
+    A (B_local, L) logits shard is 213 KB at 1024 images: over NVLink 5 the all-gather is pure launch latency, and a
+    collective kernel that runs beside the next forward also takes SMs away from the persistent 148-CTA kernels.  So the
+    forwards of ``steps`` micro-batches write their logits straight into consecutive slots of one bucket
+    (``slot()`` → ``forward_packed(x, out=slot)`` → ``commit()``); when the bucket is full ``commit()`` starts a single
+    asynchronous all_gather_into_tensor of the whole bucket and a second bucket takes the next micro-batches meanwhile.
+    ``flush()`` gathers a partly filled bucket and waits for everything in flight.  Every rank must use the same
+    ``b_local`` (pad ragged shards; ``gather_logits`` handles the ragged one-shot case).
+
+    With ``keep=True`` the gathered logits are handed out by ``pop()``: a list of (world, B_local, L) tensors in
+    micro-batch order — ``t.reshape(-1, L)`` is the (global_batch, L) tensor ``gather_logits`` returns.  They are views of
+    the receive buffer of their bucket, valid until that bucket is filled again (two buckets later)."""
+
+    def __init__(self, b_local: int, n_logits: int, steps: int, device, group=None, keep: bool = False):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.steps, self.b, self.L, self.keep = int(steps), int(b_local), int(n_logits), keep
+        self.send = [torch.empty((self.steps, self.b, self.L), dtype=torch.float32, device=device) for _ in range(2)]
+        self.recv = [torch.empty((self.world, self.steps, self.b, self.L), dtype=torch.float32, device=device) for _ in range(2)]
+        self.work = [None, None]
+        self.filled = [0, 0]
+        self.cur, self.n = 0, 0
+        self._order = []          # launched buckets whose gather has not been waited for, oldest first
+        self._done = []
+
+    def slot(self) -> torch.Tensor:
+        """The (B_local, L) view the next forward writes its logits into."""
+        if self.n == 0:
+            self._retire(self.cur)          # the previous gather of this bucket must have read the send buffer
+        return self.send[self.cur][self.n]
+
+    def commit(self) -> None:
+        """The forward that fills the current slot has been enqueued on the current stream."""
+        self.n += 1
+        if self.n == self.steps:
+            self._launch()
+
+    def _launch(self) -> None:
+        i = self.cur
+        self.filled[i] = self.n
+        if self.world > 1:
+            self.work[i] = dist.all_gather_into_tensor(self.recv[i].view(self.world * self.steps, self.b, self.L), self.send[i],
+                                                        group=self.group, async_op=True)
+        else:
+            self.recv[i][0].copy_(self.send[i], non_blocking=True)
+        self._order.append(i)
+        self.cur ^= 1
+        self.n = 0
+
+    def _retire(self, i: int) -> None:
+        while i in self._order:
+            j = self._order.pop(0)
+            if self.work[j] is not None:
+                self.work[j].wait()
+                self.work[j] = None
+            if self.keep:
+                self._done.extend(self.recv[j][:, s] for s in range(self.filled[j]))
+
+    def flush(self) -> None:
+        """Gather what is in the current bucket and wait for every gather in flight."""
+        if self.n > 0:
+            self._launch()
+        while self._order:
+            self._retire(self._order[0])
+
+    def pop(self):
+        out, self._done = self._done, []
+        return out
+
+
 class ShardedPMG:
     """Wraps a (replicated) PMG module; ``infer(x_local)`` runs the local shard and gathers the logits."""
 
@@ -87,6 +159,22 @@ class ShardedPMG:
     def infer_async(self, x_local: torch.Tensor, global_batch: int) -> PendingGather:
         """Forward of the local shard + non-blocking gather; call ``.result()`` when the logits are needed."""
         return gather_logits_async(self.infer_local(x_local), global_batch, self.group)
+
+    @torch.no_grad()
+    def infer_stream(self, batches, steps_per_gather: int = 4):
+        """Micro-batches of equal local size → list of (global_batch, L) logits, ``steps_per_gather`` micro-batches per
+        collective (BucketedGather)."""
+        bg, out = None, []
+        for xb in batches:
+            if bg is None:
+                bg = BucketedGather(xb.shape[0], self.model._n_logits, steps_per_gather, xb.device, self.group, keep=True)
+            self.model.forward_packed(xb, out=bg.slot())
+            bg.commit()
+            out.extend(t.reshape(-1, t.shape[-1]).clone() for t in bg.pop())     # the views die when the bucket is reused
+        if bg is not None:
+            bg.flush()
+            out.extend(t.reshape(-1, t.shape[-1]).clone() for t in bg.pop())
+        return out
 
     def split(self, logits: torch.Tensor) -> Dict[str, torch.Tensor]:
         return self.model._split(logits)

@@ -143,6 +143,24 @@ def test_fused_midgram_matches_two_kernel_path(batch):
     _check_against(fused[0][:n].cpu().numpy(), fused[1][:n].cpu().numpy(), pmg_oracle.pack_logits(ref, tasks), inter["gram"], tasks)
 
 
+def test_forward_into_gather_bucket_slots():
+    """forward_packed(x, out=slot) writes the logits into a BucketedGather slot; infer_stream (world 1: the bucket is
+    copied instead of gathered) returns every micro-batch's logits in order, incl. a partly filled last bucket."""
+    from pmg_b200.runner import ShardedPMG
+    _, hp, tasks = load_contract()
+    m = _model(hp, tasks, 2)
+    xs = [torch.from_numpy(synth.images(30 + i, 6)).cuda().to(torch.bfloat16) for i in range(7)]
+    with torch.no_grad():
+        want = [m.forward_packed(x).clone() for x in xs]
+        got = ShardedPMG(m).infer_stream(xs, steps_per_gather=3)
+        bad = torch.empty((6, 51), device="cuda")
+        with pytest.raises(ValueError):
+            m.forward_packed(xs[0], out=bad)
+    assert len(got) == 7
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+
+
 def test_gram_microbench_kernel_matches_matmul():
     from pmg_b200.gram import gram_batched
     gen = torch.Generator(device="cuda").manual_seed(0)

@@ -75,3 +75,40 @@ def test_gather_logits_async_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def _worker_bucket(rank, world, port, n_steps, steps_per_gather, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pmg_b200.runner import BucketedGather
+    b, L = 5, 52
+    bg = BucketedGather(b, L, steps_per_gather, torch.device("cpu"), keep=True)
+    got = []
+    for s in range(n_steps):
+        # stand-in for model.forward_packed(x, out=bg.slot()): micro-batch s of rank r holds 1000 s + 100 r + row
+        bg.slot().copy_((1000 * s + 100 * rank + torch.arange(b, dtype=torch.float32))[:, None].expand(b, L))
+        bg.commit()
+        got.extend(t.reshape(-1, L).clone() for t in bg.pop())     # views live two buckets: clone as a consumer would
+    bg.flush()
+    got.extend(t.reshape(-1, L).clone() for t in bg.pop())
+    ok = len(got) == n_steps
+    for s, t in enumerate(got):
+        want = torch.cat([1000 * s + 100 * r + torch.arange(b, dtype=torch.float32) for r in range(world)])[:, None].expand(world * b, L)
+        ok = ok and bool(torch.equal(t, want))
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_steps,steps_per_gather", [(8, 4), (7, 3), (2, 4), (9, 1)])
+def test_bucketed_gather_world2_gloo(n_steps, steps_per_gather):
+    """Several micro-batches per collective, two buckets in flight, partial last bucket (runner.BucketedGather)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_bucket, args=(r, 2, port, n_steps, steps_per_gather, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True)]
