@@ -91,8 +91,10 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     uint64_t* a0_empty = bars + 3;       // [3]
     uint64_t* d0_full = bars + 6;        // [2]
     uint64_t* d0_empty = bars + 8;       // [2]
-    uint64_t* a1_ready = bars + 10;
-    uint64_t* a1_free = bars + 11;
+    uint64_t* a1_ready = bars + 10;      // hi plane of A1 written
+    uint64_t* a1_free = bars + 11;       // hi plane of A1 read by conv1
+    uint64_t* a1l_ready = bars + 18;     // same for the lo plane
+    uint64_t* a1l_free = bars + 19;
     uint64_t* d1_full = bars + 12;       // [2]
     uint64_t* d1_empty = bars + 14;      // [2]
     uint64_t* w_bar = bars + 16;
@@ -110,6 +112,7 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         for (int i = 0; i < 3; ++i) { mbar_init(&a0_full[i], 1); mbar_init(&a0_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&d0_full[i], 1); mbar_init(&d0_empty[i], 16); }
         mbar_init(a1_ready, 16); mbar_init(a1_free, 1); mbar_init(w_bar, 1);
+        mbar_init(a1l_ready, 16); mbar_init(a1l_free, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], 4); }
         fence_barrier_init();
     }
@@ -205,15 +208,25 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                     mbar_wait(a1_ready, g & 1);
                     if (sy == 0) mbar_wait(&d1_empty[db], ((lt >> 1) & 1) ^ 1);
                     tc_fence_after();
+                    // the hi plane first, then the lo plane, each with its own ready / free pair: epilogue 0 refills the hi
+                    // plane for the next slice while the lo MMAs of this one run (and vice versa), so the single A1 buffer
+                    // no longer serialises "write A1 → 16 MMAs → write A1"
 #pragma unroll
                     for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const uint64_t bd = make_desc_k_sw128(aW1 + (sy * 2 + kb) * 8192 + k * 32);
-                            umma_bf16(tD1 + 64 * db, make_desc_k_sw128(aA1 + kb * 16384 + k * 32), bd, idesc1, (sy > 0 || kb > 0 || k > 0) ? 1u : 0u);
-                            umma_bf16(tD1 + 64 * db, make_desc_k_sw128(aA1 + 32768 + kb * 16384 + k * 32), bd, idesc1, 1u);
-                        }
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tD1 + 64 * db, make_desc_k_sw128(aA1 + kb * 16384 + k * 32),
+                                      make_desc_k_sw128(aW1 + (sy * 2 + kb) * 8192 + k * 32), idesc1, (sy > 0 || kb > 0 || k > 0) ? 1u : 0u);
                     umma_commit(a1_free);
+                    mbar_wait(a1l_ready, g & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tD1 + 64 * db, make_desc_k_sw128(aA1 + 32768 + kb * 16384 + k * 32),
+                                      make_desc_k_sw128(aW1 + (sy * 2 + kb) * 8192 + k * 32), idesc1, 1u);
+                    umma_commit(a1l_free);
                     FR_T(23 + 4 * sy);
                 }
                 umma_commit(&d1_full[db]);
@@ -253,11 +266,7 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                         for (int j = 0; j < 4; ++j) {
                             const int i = 8 * j4 + 2 * j, c = half * 32 + i;
                             const uint32_t a0 = half ? r1[i] : r0[i], a1 = half ? r1[i + 1] : r0[i + 1];
-                            float v0 = fmaf(__uint_as_float(a0), s1[c], h1[c]);
-                            float v1 = fmaf(__uint_as_float(a1), s1[c + 1], h1[c + 1]);
-                            v0 = fmaxf(v0, 0.2f * v0);
-                            v1 = fmaxf(v1, 0.2f * v1);
-                            split_bf16x2(v0, v1, hi[j], lo[j]);
+                            bn_lrelu_split_x2(a0, a1, s1[c], s1[c + 1], h1[c], h1[c + 1], hi[j], lo[j]);
                         }
                         dh[half * 4 + j4] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                         dl[half * 4 + j4] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -294,24 +303,29 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                 for (int j = 0; j < 8; ++j) {
                     const float4 sc = *reinterpret_cast<const float4*>(s0 + 4 * j);
                     const float4 sh = *reinterpret_cast<const float4*>(h0 + 4 * j);
-                    float v0 = fmaf(__uint_as_float(r[4 * j]), sc.x, sh.x), v1 = fmaf(__uint_as_float(r[4 * j + 1]), sc.y, sh.y);
-                    float v2 = fmaf(__uint_as_float(r[4 * j + 2]), sc.z, sh.z), v3 = fmaf(__uint_as_float(r[4 * j + 3]), sc.w, sh.w);
-                    v0 = fmaxf(v0, 0.2f * v0); v1 = fmaxf(v1, 0.2f * v1); v2 = fmaxf(v2, 0.2f * v2); v3 = fmaxf(v3, 0.2f * v3);
-                    split_bf16x2(v0, v1, H[2 * j], L[2 * j]);
-                    split_bf16x2(v2, v3, H[2 * j + 1], L[2 * j + 1]);
+                    bn_lrelu_split_x2(r[4 * j], r[4 * j + 1], sc.x, sc.y, sh.x, sh.y, H[2 * j], L[2 * j]);
+                    bn_lrelu_split_x2(r[4 * j + 2], r[4 * j + 3], sc.z, sc.w, sh.z, sh.w, H[2 * j + 1], L[2 * j + 1]);
                 }
                 if (warp == 2 && lane == 0) FR_T(41 + 4 * sy);
-                if (g > 0) mbar_wait(a1_free, (g - 1) & 1);        // conv1 MMAs of the previous slice have read A1
+                if (g > 0) mbar_wait(a1_free, (g - 1) & 1);        // conv1's hi MMAs of the previous slice have read the hi plane
                 if (warp == 2 && lane == 0) FR_T(42 + 4 * sy);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int sw = (((cg & 1) * 4 + j) ^ (m & 7)) << 4;
                     *reinterpret_cast<uint4*>(a1row + sw) = make_uint4(H[4 * j], H[4 * j + 1], H[4 * j + 2], H[4 * j + 3]);
-                    *reinterpret_cast<uint4*>(a1row + 32768 + sw) = make_uint4(L[4 * j], L[4 * j + 1], L[4 * j + 2], L[4 * j + 3]);
                 }
                 fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(a1_ready);
+                if (g > 0) mbar_wait(a1l_free, (g - 1) & 1);       // ... and the lo MMAs the lo plane
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int sw = (((cg & 1) * 4 + j) ^ (m & 7)) << 4;
+                    *reinterpret_cast<uint4*>(a1row + 32768 + sw) = make_uint4(L[4 * j], L[4 * j + 1], L[4 * j + 2], L[4 * j + 3]);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(a1l_ready);
                 if (warp == 2 && lane == 0) FR_T(43 + 4 * sy);
             }
         }

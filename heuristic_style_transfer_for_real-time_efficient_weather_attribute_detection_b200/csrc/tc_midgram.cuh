@@ -275,11 +275,8 @@ midgram_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             for (int j = 0; j < 8; ++j) {
                 const float4 sc = *reinterpret_cast<const float4*>(s2 + cq * 32 + 4 * j);
                 const float4 sh = *reinterpret_cast<const float4*>(h2 + cq * 32 + 4 * j);
-                float v0 = fmaf(__uint_as_float(rr[4 * j]), sc.x, sh.x), v1 = fmaf(__uint_as_float(rr[4 * j + 1]), sc.y, sh.y);
-                float v2 = fmaf(__uint_as_float(rr[4 * j + 2]), sc.z, sh.z), v3 = fmaf(__uint_as_float(rr[4 * j + 3]), sc.w, sh.w);
-                v0 = fmaxf(v0, 0.2f * v0); v1 = fmaxf(v1, 0.2f * v1); v2 = fmaxf(v2, 0.2f * v2); v3 = fmaxf(v3, 0.2f * v3);
-                split_bf16x2(v0, v1, H[2 * j], L[2 * j]);
-                split_bf16x2(v2, v3, H[2 * j + 1], L[2 * j + 1]);
+                bn_lrelu_split_x2(rr[4 * j], rr[4 * j + 1], sc.x, sc.y, sh.x, sh.y, H[2 * j], L[2 * j]);
+                bn_lrelu_split_x2(rr[4 * j + 2], rr[4 * j + 3], sc.z, sc.w, sh.z, sh.w, H[2 * j + 1], L[2 * j + 1]);
             }
             if (threadIdx.x == 0) MG_T(i, 6);
             mbar_wait(&a3_free[i & 1], ((i >> 1) & 1) ^ 1);   // the chan MMAs of band i-2 have read this A3 buffer
@@ -388,7 +385,11 @@ midgram_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             if (lane == 0) mbar_arrive(&g_empty[as]);
             if (tracer) MG_T(i, 26 + 3 * j);
 #pragma unroll
-            for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) * 0.04f);
+            for (int e = 0; e < 16; ++e) {
+                float g0, g1;
+                unpack_f32x2(mul_f32x2(pack_f32x2(__uint_as_float(r[2 * e]), __uint_as_float(r[2 * e + 1])), pack_f32x2(0.04f, 0.04f)), g0, g1);
+                r[2 * e] = __float_as_uint(g0); r[2 * e + 1] = __float_as_uint(g1);
+            }
             if (p.g_f32) {                                    // full fp32 Gram (tests, forward_with_gram): the block and its mirror image
                 float* g = p.g_f32 + (size_t)tok * 9216;
                 float4* df = reinterpret_cast<float4*>(g + (size_t)(rb * 32 + lane) * 96 + c0);

@@ -184,14 +184,50 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, int a_mn_ma
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- packed fp32 (sm_100: FFMA2 / FMUL2 / FADD2)
+// Two fp32 operations per instruction on a 64-bit register pair.  The BN / LeakyReLU / hi-lo epilogues of this library
+// are bound by instruction issue (≈6 instructions per accumulator value on 16 warps), not by the fp32 pipe, so halving
+// the arithmetic instructions is a direct gain; results are bit-identical to the scalar forms (same .rn operations).
+__device__ __forceinline__ uint64_t pack_f32x2(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t sub_f32x2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+
 // ---------------------------------------------------------------- split-precision helpers
 // v ≈ hi + lo with hi = bf16(v), lo = bf16(v - hi): 16 significant bits through two bf16 MMAs.
 __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    const float ra = a - __low2float(h), rb = b - __high2float(h);
-    __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
     hi = *reinterpret_cast<uint32_t*>(&h);
+    float ra, rb;
+    unpack_f32x2(sub_f32x2(pack_f32x2(a, b), pack_f32x2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u))), ra, rb);
+    __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
     lo = *reinterpret_cast<uint32_t*>(&l);
+}
+// LeakyReLU_0.2(x·scale + shift) of two accumulator values (folded eval BatchNorm), then the hi/lo split
+__device__ __forceinline__ void bn_lrelu_split_x2(uint32_t x0, uint32_t x1, float s0, float s1, float h0, float h1, uint32_t& hi, uint32_t& lo) {
+    const uint64_t v = fma_f32x2(pack_f32x2(__uint_as_float(x0), __uint_as_float(x1)), pack_f32x2(s0, s1), pack_f32x2(h0, h1));
+    const uint64_t w = mul_f32x2(v, pack_f32x2(0.2f, 0.2f));
+    float v0, v1, w0, w1;
+    unpack_f32x2(v, v0, v1);
+    unpack_f32x2(w, w0, w1);
+    split_bf16x2(fmaxf(v0, w0), fmaxf(v1, w1), hi, lo);
 }
 
 // 256-bit global store (sm_100: STG.E.ENL2.256): one whole 32-byte sector per thread
