@@ -174,48 +174,87 @@ __global__ void __launch_bounds__(256) pm_im2col_kernel(const bf16* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------ InstanceNorm
-// conv (B, HW, C) fp32 → LeakyReLU(IN(conv)) as hi/lo planes (and fp32 on request).  Block = (sample, 32 channels),
-// lane = channel, 8 warps stride over the pixels; statistics in two passes (mean, then centred second moment).
+// conv (B, HW, C) fp32 → LeakyReLU(IN(conv)) as hi/lo planes (and fp32 on request).  Block = (sample, 32 channels).
+// A thread owns 4 channels (float4) of every 32nd pixel: 8 lanes cover the block's 128-byte channel slice of one pixel,
+// a warp load covers 4 pixels, and 8 independent loads per thread are in flight — the first version (one 4-byte load per
+// lane per iteration) kept ≈1 KB per block in flight and ran at a fraction of the HBM rate.  Statistics in ONE pass over
+// values shifted by the sample's first pixel (Σd, Σd² with d = x − x₀: no catastrophic cancellation when |mean| ≫ std),
+// then one normalise pass (the slice is re-read, mostly from L2).
 __global__ void __launch_bounds__(256) pm_instnorm_kernel(const float* __restrict__ conv, const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, bf16* __restrict__ o_hi,
                                                           bf16* __restrict__ o_lo, float* __restrict__ o_f32, int HW, int C) {
-    __shared__ float red[8][33];
-    __shared__ float s_mean[32], s_rstd[32];
-    const int b = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float* src = conv + (size_t)b * HW * C + c;
-    float s = 0.f;
-    for (int p = warp; p < HW; p += 8) s += src[(size_t)p * C];
-    red[warp][lane] = s;
-    __syncthreads();
-    if (warp == 0) {
-        float t = 0.f;
+    __shared__ float4 red_s[32][8], red_q[32][8];
+    __shared__ float4 s_scale[8], s_shift[8];
+    const int b = blockIdx.y, c0 = blockIdx.x * 32;
+    const int cl = (threadIdx.x & 7) * 4;                    // this thread's 4 channels inside the block's 32
+    const int pr = threadIdx.x >> 3;                          // pixel phase 0..31
+    const float* src = conv + (size_t)b * HW * C + c0 + cl;
+    const float4 x0 = *reinterpret_cast<const float4*>(src);  // pixel 0 of the sample: the shift
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    int p = pr;
+    for (; p + 7 * 32 < HW; p += 8 * 32) {
+        float4 v[8];
 #pragma unroll
-        for (int w = 0; w < 8; ++w) t += red[w][lane];
-        s_mean[lane] = t / (float)HW;
-    }
-    __syncthreads();
-    const float mu = s_mean[lane];
-    float q = 0.f;
-    for (int p = warp; p < HW; p += 8) { const float d = src[(size_t)p * C] - mu; q = fmaf(d, d, q); }
-    red[warp][lane] = q;
-    __syncthreads();
-    if (warp == 0) {
-        float t = 0.f;
+        for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const float4*>(src + (size_t)(p + 32 * u) * C);
 #pragma unroll
-        for (int w = 0; w < 8; ++w) t += red[w][lane];
-        s_rstd[lane] = 1.f / sqrtf(t / (float)HW + kInEps);
+        for (int u = 0; u < 8; ++u) {
+            const float dx = v[u].x - x0.x, dy = v[u].y - x0.y, dz = v[u].z - x0.z, dw = v[u].w - x0.w;
+            s.x += dx; s.y += dy; s.z += dz; s.w += dw;
+            q.x = fmaf(dx, dx, q.x); q.y = fmaf(dy, dy, q.y); q.z = fmaf(dz, dz, q.z); q.w = fmaf(dw, dw, q.w);
+        }
+    }
+    for (; p < HW; p += 32) {
+        const float4 v = *reinterpret_cast<const float4*>(src + (size_t)p * C);
+        const float dx = v.x - x0.x, dy = v.y - x0.y, dz = v.z - x0.z, dw = v.w - x0.w;
+        s.x += dx; s.y += dy; s.z += dz; s.w += dw;
+        q.x = fmaf(dx, dx, q.x); q.y = fmaf(dy, dy, q.y); q.z = fmaf(dz, dz, q.z); q.w = fmaf(dw, dw, q.w);
+    }
+    red_s[pr][threadIdx.x & 7] = s;
+    red_q[pr][threadIdx.x & 7] = q;
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float4 ts = make_float4(0.f, 0.f, 0.f, 0.f), tq = ts;
+        for (int i = 0; i < 32; ++i) {
+            const float4 a = red_s[i][threadIdx.x], c = red_q[i][threadIdx.x];
+            ts.x += a.x; ts.y += a.y; ts.z += a.z; ts.w += a.w;
+            tq.x += c.x; tq.y += c.y; tq.z += c.z; tq.w += c.w;
+        }
+        const float inv = 1.f / (float)HW;
+        const float4 g = *reinterpret_cast<const float4*>(gamma + c0 + cl), be = *reinterpret_cast<const float4*>(beta + c0 + cl);
+        float4 sc, sh;
+        auto fin = [&](float sd, float sq, float xs, float gg, float bb, float& o_sc, float& o_sh) {
+            const float md = sd * inv;                                   // mean of the shifted values
+            const float var = fmaxf(sq * inv - md * md, 0.f);            // biased variance (InstanceNorm2d)
+            o_sc = gg / sqrtf(var + kInEps);
+            o_sh = bb - (xs + md) * o_sc;
+        };
+        fin(ts.x, tq.x, x0.x, g.x, be.x, sc.x, sh.x); fin(ts.y, tq.y, x0.y, g.y, be.y, sc.y, sh.y);
+        fin(ts.z, tq.z, x0.z, g.z, be.z, sc.z, sh.z); fin(ts.w, tq.w, x0.w, g.w, be.w, sc.w, sh.w);
+        s_scale[threadIdx.x] = sc; s_shift[threadIdx.x] = sh;
     }
     __syncthreads();
-    const float sc = s_rstd[lane] * gamma[c], sh = beta[c] - mu * sc;
-    for (int p = warp; p < HW; p += 8) {
-        float v = fmaf(src[(size_t)p * C], sc, sh);
-        v = fmaxf(v, 0.2f * v);
-        const size_t o = ((size_t)b * HW + p) * C + c;
-        const bf16 h = __float2bfloat16_rn(v);
-        o_hi[o] = h;
-        o_lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
-        if (o_f32) o_f32[o] = v;
+    const float4 sc = s_scale[threadIdx.x & 7], sh = s_shift[threadIdx.x & 7];
+    const size_t obase = (size_t)b * HW * C + c0 + cl;
+    auto emit = [&](int pp, const float4& v) {
+        float y0 = fmaf(v.x, sc.x, sh.x), y1 = fmaf(v.y, sc.y, sh.y), y2 = fmaf(v.z, sc.z, sh.z), y3 = fmaf(v.w, sc.w, sh.w);
+        y0 = fmaxf(y0, 0.2f * y0); y1 = fmaxf(y1, 0.2f * y1); y2 = fmaxf(y2, 0.2f * y2); y3 = fmaxf(y3, 0.2f * y3);
+        uint32_t h0, l0, h1, l1;
+        tc::split_bf16x2(y0, y1, h0, l0);
+        tc::split_bf16x2(y2, y3, h1, l1);
+        const size_t o = obase + (size_t)pp * C;
+        *reinterpret_cast<uint2*>(o_hi + o) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(o_lo + o) = make_uint2(l0, l1);
+        if (o_f32) *reinterpret_cast<float4*>(o_f32 + o) = make_float4(y0, y1, y2, y3);
+    };
+    p = pr;
+    for (; p + 7 * 32 < HW; p += 8 * 32) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const float4*>(src + (size_t)(p + 32 * u) * C);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) emit(p + 32 * u, v[u]);
     }
+    for (; p < HW; p += 32) emit(p, *reinterpret_cast<const float4*>(src + (size_t)p * C));
 }
 
 // ------------------------------------------------------------------------------------------------ heads finish
