@@ -452,10 +452,18 @@ static FastWs fast_ws(int B) {
 size_t fast_workspace_bytes(const Plan&, const Shape&, int B) { return fast_ws(B).total; }
 
 // bf16 input: fused front kernel (1 launch) instead of im2col + conv0 + conv1 (3 launches)
-int fast_launch_count(const Plan& p, const Shape&, int, unsigned flags) {
+// The fused conv2 + chan_proj + Gram kernel chains an image band's three MMA stages on one CTA; below ≈100 images the
+// two-kernel path (mid kernel, then a Gram kernel with one CTA per token) has the shorter critical path (B = 1: 109 vs 116 us
+// per forward, B = 64: 0.111 vs 0.122 ms; equal at 128, fused ahead from 256 up), so small batches keep it.
+static bool use_midgram(int B, unsigned flags) {
+    if (flags & (PMG_FLAG_NO_FUSED_MIDGRAM | PMG_FLAG_NO_FUSED_MID)) return false;
+    return B >= 96 || (flags & PMG_FLAG_ALWAYS_FUSED_MIDGRAM);
+}
+
+int fast_launch_count(const Plan& p, const Shape&, int B, unsigned flags) {
     const int front = (flags & PMG_FLAG_NO_FUSED_FRONT) ? 3 : 1;
     // conv2 + chan_proj + Gram: one kernel (tc_midgram.cuh), or the fused mid kernel + Gram, or two GEMMs + Gram
-    const int mid = !(flags & (PMG_FLAG_NO_FUSED_MIDGRAM | PMG_FLAG_NO_FUSED_MID)) ? 1 : (flags & PMG_FLAG_NO_FUSED_MID) ? 3 : 2;
+    const int mid = use_midgram(B, flags) ? 1 : (flags & PMG_FLAG_NO_FUSED_MID) ? 3 : 2;
     if (!(flags & PMG_FLAG_NO_FUSED_ENCODER) && p.nl <= tc::ENC_MAX_LAYERS) return front + mid + 2 + 1;   // + token_proj (2), token stage
     return front + mid + 2 + 1 + 6 * p.nl + (p.nl > 1 ? p.nl - 1 : 0) + 3;
 }
@@ -529,7 +537,7 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
         return rc;
     PMG_MARK(tm, "conv1");
     }
-    const bool fused_midgram = !(flags & (PMG_FLAG_NO_FUSED_MIDGRAM | PMG_FLAG_NO_FUSED_MID));
+    const bool fused_midgram = use_midgram(B, flags);
     if (fused_midgram) {
         // conv2 (:124-128) + chan_proj (:136,182) + pad/patches (:157-174) + Gram (:188) in one kernel: neither the
         // 128-channel activation nor the chan_proj map touch HBM (tc_midgram.cuh)
@@ -547,7 +555,7 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
         tc::MidGramParams mp;
         mp.scale2 = Pf(L.conv_scale[2]); mp.shift2 = Pf(L.conv_shift[2]); mp.g_hi = Hb(w.g_hi); mp.g_lo = Hb(w.g_lo);
         mp.g_f32 = gram; mp.chan = taps ? taps->chan : nullptr; mp.B = B; mp.trace = g_enc_trace;
-        const int grid = B < tc::num_sms() ? B : tc::num_sms();
+        const int grid = 3 * B < tc::num_sms() ? 3 * B : tc::num_sms();
         PMG_CUDA_OK(tc::launch_pdl(tc::midgram_kernel, dim3(grid), dim3(tc::MG_THREADS), tc::MG_SMEM, st, ta_hi, ta_lo, tw2, tw3, tw3d, mp), "midgram_kernel");
         PMG_MARK(tm, "conv2_chan_gram");
     } else {

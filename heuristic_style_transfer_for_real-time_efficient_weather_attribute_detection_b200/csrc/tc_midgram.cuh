@@ -116,8 +116,10 @@ midgram_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     const int q = warp & 3;
     int role_arg;
     const int role = mg_role(q, warp >> 2, role_arg);
-    const int n_img = p.B > (int)blockIdx.x ? (p.B - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    const int n_bands = 3 * n_img;
+    // bands (image, py) are dealt round-robin: global band gb = blockIdx.x + i·gridDim.x, so a small batch spreads the three
+    // bands of an image over three CTAs instead of chaining them on one
+    const int total_bands = 3 * p.B;
+    const int n_bands = total_bands > (int)blockIdx.x ? (total_bands - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;     // this warp's TMEM lane quarter
 
     if (threadIdx.x == 0) {
@@ -159,7 +161,7 @@ midgram_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             pdl_wait();                  // act1 comes from the front kernel
             for (int i = 0; i < n_bands; ++i) {
                 const int s = i % MG_STAGES;
-                const int img = (int)blockIdx.x + (i / 3) * (int)gridDim.x, py = i % 3;
+                const int gb = (int)blockIdx.x + i * (int)gridDim.x, img = gb / 3, py = gb - 3 * img;
                 mbar_wait(&a_empty[s], ((i / MG_STAGES) & 1) ^ 1);
                 MG_T(i, 0);
                 mbar_expect_tx(&a_full[s], MG_A_STAGE);
@@ -248,7 +250,7 @@ midgram_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int R0 = (x / 5) * 32 + r * 5 + x % 5;          // A3 row: patch column px = x/5, slot n = 5r + x%5
         const bool dupx = x == 13;                            // column 13 is also the padded column 14 (slot + 1)
         for (int i = 0; i < n_bands; ++i) {
-            const int py = i % 3;
+            const int py = ((int)blockIdx.x + i * (int)gridDim.x) % 3;
             const int nrows = py == 2 ? 56 : 70;
             const bool valid = m < nrows;
             const bool dupy = py == 2 && r == 3;              // image row 13 is also the padded row 14 (slot + 5)
@@ -312,7 +314,7 @@ midgram_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         uint8_t* prow = sP + ch * 128;
         for (int i = 0; i < n_bands; ++i) {
             const uint32_t b = i & 1;
-            const int img = (int)blockIdx.x + (i / 3) * (int)gridDim.x, py = i % 3;
+            const int gb = (int)blockIdx.x + i * (int)gridDim.x, img = gb / 3, py = gb - 3 * img;
             mbar_wait(&d3_full[b], (i >> 1) & 1);
             tc_fence_after();
             if (tracer) MG_T(i, 9);
@@ -373,7 +375,7 @@ midgram_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         const int n_patches = 3 * n_bands;
         for (int t = 0; t < n_patches; ++t) {
             const uint32_t as = t & 1;
-            const int tok = ((int)blockIdx.x + (i / 3) * (int)gridDim.x) * 9 + (i % 3) * 3 + j;
+            const int tok = ((int)blockIdx.x + i * (int)gridDim.x) * 3 + j;      // (img·3 + py)·3 + px
             mbar_wait(&g_full[as], (t >> 1) & 1);
             tc_fence_after();
             if (tracer) MG_T(i, 25 + 3 * j);

@@ -142,7 +142,8 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
         self.fused_front = True         # fast path: TMA-fed fused conv0+conv1 kernel (bf16 input); False = im2col + GEMMs
         self.fused_encoder = True       # fast path: transformer + pooling + heads in one kernel; False = per-op kernels
         self.fused_mid = True           # fast path: conv2 + chan_proj in one kernel; False = two GEMMs
-        self.fused_midgram = True       # fast path: conv2 + chan_proj + patches + Gram in one kernel; False = mid kernel + Gram kernel
+        self.fused_midgram = True       # fast path: conv2 + chan_proj + patches + Gram in one kernel from 96 images up; "always" = at every
+                                        # batch size; False = mid kernel + Gram kernel
 
     # kernel-side state is rebuilt on demand; keep it out of pickles / deepcopies
     def __getstate__(self):
@@ -300,7 +301,8 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
                 | (0 if self.fused_front else _lib.PMG_FLAG_NO_FUSED_FRONT)
                 | (0 if getattr(self, "fused_encoder", True) else _lib.PMG_FLAG_NO_FUSED_ENCODER)
                 | (0 if getattr(self, "fused_mid", True) else _lib.PMG_FLAG_NO_FUSED_MID)
-                | (0 if getattr(self, "fused_midgram", True) else _lib.PMG_FLAG_NO_FUSED_MIDGRAM))
+                | (0 if getattr(self, "fused_midgram", True) else _lib.PMG_FLAG_NO_FUSED_MIDGRAM)
+                | (_lib.PMG_FLAG_ALWAYS_FUSED_MIDGRAM if getattr(self, "fused_midgram", True) == "always" else 0))
 
     def launches_per_forward(self, B: int, H: int = 224, W: int = 224) -> int:
         flags = self._flags()

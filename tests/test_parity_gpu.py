@@ -126,13 +126,15 @@ def test_fused_midgram_matches_two_kernel_path(batch):
     _, hp, tasks = load_contract()
     m = _model(hp, tasks, 3)
     x = torch.from_numpy(synth.images(21, batch)).cuda().to(torch.bfloat16)
+    m.fused_midgram = "always"                          # the default switches to the fused kernel from 96 images up
     with torch.no_grad():
         fused = m.forward_debug(x)
         plain = m.forward_packed(x).clone()              # no taps, no fp32 Gram: the production call
+        assert m.launches_per_forward(batch) == 5
         m.fused_midgram = False
         two = m.forward_debug(x)
         m.fused_midgram = True
-    assert m.launches_per_forward(batch) == 5
+    assert m.launches_per_forward(batch) == (5 if batch >= 96 else 6)
     assert torch.equal(fused[0], plain)
     assert rel_fro(fused[1].cpu().numpy(), two[1].cpu().numpy()) <= 1e-6
     assert rel_fro(fused[2]["chan"].cpu().numpy(), two[2]["chan"].cpu().numpy()) <= 1e-6

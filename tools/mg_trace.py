@@ -1,5 +1,5 @@
 """Decode the clock64 role trace of the fused conv2 + chan_proj + Gram kernel (tc_midgram.cuh): bands 6..8
-(third image) of CTA 0.  Run on the GPU box:  python tools/mg_trace.py [B]"""
+of CTA 0 (global bands 6·grid, 7·grid, 8·grid: bands are dealt round-robin).  Run on the GPU box:  python tools/mg_trace.py [B]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
