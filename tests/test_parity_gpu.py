@@ -107,7 +107,10 @@ def test_full_size_properties():
     # order; through the hi/lo bf16 planes (2^-17 relative quantisation) that shows up at ~1e-5 — two orders
     # below the 1e-3 parity gate
     assert rel_fro(full[512:640].cpu().numpy(), part.cpu().numpy()) <= 1e-4
-    assert torch.equal(argmax := full[512:640].argmax(1), part.argmax(1)) or argmax is not None
+    # per-task argmax of the shard run == argmax of the same images inside the full batch (a 1e-5 relative wobble can only
+    # flip an exact near-tie: allow one of the 128 x 12 decisions)
+    am = lambda t: torch.stack([v.argmax(1) for v in torch.split(t, list(tasks.values()), dim=1)], 1)
+    assert (am(full[512:640]) != am(part)).sum().item() <= 1
     g = gram.double()
     assert (g - g.transpose(2, 3)).abs().max().item() <= 1e-6 * g.abs().max().item()
     # trace(G_k) = sum over the patch's 25 (replicate-padded) pixels of |p|^2 / 25
