@@ -12,6 +12,7 @@ PMG_MAX_TASKS = 32
 PMG_F32, PMG_BF16 = 0, 1
 PMG_FLAG_FORCE_GENERIC, PMG_FLAG_FORCE_FAST, PMG_FLAG_NO_FUSED_FRONT, PMG_FLAG_NO_FUSED_ENCODER, PMG_FLAG_NO_FUSED_MID = 1, 2, 4, 8, 16
 PMG_FLAG_NO_FUSED_MIDGRAM, PMG_FLAG_ALWAYS_FUSED_MIDGRAM = 32, 64
+PM_FLAG_NO_IGEMM = 1
 
 
 class PmgConfig(C.Structure):

@@ -420,7 +420,6 @@ size_t pm_workspace_bytes(const pm_config* cfg, int B, int H, int W) {
 
 int pm_forward(const pm_config* cfg, const void* packed, const void* x, int x_dtype, int B, int H, int W, float* logits,
                float* attn, float* feats, void* workspace, size_t workspace_bytes, unsigned flags, pmg_stream_t stream) {
-    (void)flags;
     const PmPlan p = pm_plan(cfg);
     if (!p.ok || !packed || !x || !logits || !workspace) return PMG_ERR_BAD_ARG;
     if (x_dtype != PMG_F32 && x_dtype != PMG_BF16) return PMG_ERR_BAD_ARG;
@@ -451,6 +450,18 @@ int pm_forward(const pm_config* cfg, const void* packed, const void* x, int x_dt
             const PmLayer& y = p.layer[l];
             const int Ho = s.h[l + 1], Wo = s.w[l + 1];
             const int rows = Bc * Ho * Wo;
+            float* conv = reinterpret_cast<float*>(ws + w.conv);
+            // stride-2 layers with ≥ 64 input channels: implicit GEMM straight from the previous layer's NHWC hi/lo planes
+            // (tc_igemm.cuh) — no im2col planes are written or re-read.  Layer 0 (3 input channels, NCHW image) and the
+            // stride-1 last layer (13×13 output: an image-aligned M tile would be 117 + 52 of 256 rows) keep im2col + GEMM.
+            const bool igemm = l > 0 && y.stride == 2 && y.cin % 64 == 0 && y.cout % 128 == 0 && y.cout <= tc::IG_MAX_N &&
+                               Wo <= 128 && !(flags & PM_FLAG_NO_IGEMM);
+            if (igemm) {
+                if ((rc = tc::launch_conv_igemm(Hb(w.act_hi[(l - 1) & 1]), Hb(w.act_lo[(l - 1) & 1]), pk + L.w[l],
+                                                reinterpret_cast<const float*>(pk + L.bias[l]), Bc, s.h[l], s.w[l], y.cin, Ho, Wo,
+                                                y.stride, y.cout, conv, st)))
+                    return rc;
+            } else {
             if (l == 0) {
                 const size_t n = (size_t)rows * (y.Kp / 8);
                 if (x_dtype == PMG_F32)
@@ -463,10 +474,10 @@ int pm_forward(const pm_config* cfg, const void* packed, const void* x, int x_dt
                                                             y.cin, s.h[l], s.w[l], Ho, Wo, y.stride);
             }
             PMG_LAUNCH_OK("pm im2col");
-            float* conv = reinterpret_cast<float*>(ws + w.conv);
             if ((rc = pm_conv_gemm(Hb(w.a_hi), Hb(w.a_lo), y.Kp, reinterpret_cast<const bf16*>(pk + L.w[l]), rows, y.cout, conv,
                                    reinterpret_cast<const float*>(pk + L.bias[l]), st)))
                 return rc;
+            }
             const bool last = l == p.n_layers - 1;
             pm_instnorm_kernel<<<dim3(y.cout / 32, Bc), 256, 0, st>>>(conv, reinterpret_cast<const float*>(pk + L.gamma[l]),
                                                                       reinterpret_cast<const float*>(pk + L.beta[l]), Hb(w.act_hi[l & 1]),

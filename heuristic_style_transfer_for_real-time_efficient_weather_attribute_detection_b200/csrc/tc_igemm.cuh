@@ -1,0 +1,194 @@
+// tc_igemm.cuh — implicit-GEMM convolution (k 4×4, pad 1, stride s) on tcgen05 for the PM trunk: no im2col planes.
+// Reference: models_PM.py:121-132 (Conv2d(k4, s2, p1) layers of the trunk).
+//
+//   conv[b, oy, ox, n] = bias[n] + Σ_{ky,kx,c} (act_hi + act_lo)[b, s·oy+ky-1, s·ox+kx-1, c] · W[n, (ky·4+kx)·C + c]
+//
+// The activation stays where the InstanceNorm kernel left it: two bf16 planes, NHWC.  A K block of the GEMM is one filter
+// tap (ky, kx) × 64 channels, and the A tile of an M tile (bh output rows × Wo pixels ≤ 128 rows) for that K block is ONE
+// TMA box of a 4-D tensor map over the plane — dims (C, W, H, B), box (64, s·Wo, s·bh, 1) walked with element strides
+// (1, s, s, 1) from (c0, kx-1, s·oy0+ky-1, b): the box lands as [bh·Wo rows × 128 B], 128-byte swizzled, exactly the
+// K-major operand tile the MMA wants; the zero padding is TMA's out-of-bounds fill.  Everything else (B tiles, smem ring,
+// single-thread MMA issue, double-buffered TMEM accumulator, smem-staged coalesced epilogue) is tc_gemm.cuh's structure.
+// M tiles never straddle images; rows ≥ valid rows of a tile (bh·Wo < 128, short last tile of an image) are computed on
+// stale smem and never stored.
+#pragma once
+
+#include "tc_prims.cuh"
+
+namespace tc {
+
+struct IgemmParams {
+    int B, Ho, Wo, bh, tiles_per_img;   // M tile = bh output rows of one image
+    int C, N, stride;                   // input channels (multiple of 64), output channels (multiple of BN), conv stride
+    float* out;                         // [B·Ho·Wo, N] fp32
+    const float* bias;                  // [N]
+};
+
+constexpr int IG_THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9 = two epilogue groups
+constexpr int IG_STAGES = 3;
+constexpr int IG_MAX_N = 1024;
+
+__device__ __forceinline__ void tma_load_4d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1,
+                                                 int32_t c2, int32_t c3, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+          "r"(c3), "l"(policy)
+        : "memory");
+}
+
+template <int BN>
+__host__ __device__ constexpr int ig_stage_bytes() { return 2 * 128 * 128 + BN * 128; }
+template <int BN>
+__host__ __device__ constexpr int ig_smem_bytes() {
+    return IG_STAGES * ig_stage_bytes<BN>() + 1024 + 256 + IG_MAX_N * 4 + 8 * 4096;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(IG_THREADS, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                  const __grid_constant__ CUtensorMap tmB, const IgemmParams p) {
+    constexpr int A_BYTES = 128 * 128;
+    constexpr int B_BYTES = BN * 128;
+    constexpr int STAGE_BYTES = ig_stage_bytes<BN>();
+    static_assert(BN == 128 || BN == 64, "accumulator stages are 128 columns apart");
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + IG_STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + IG_STAGES;
+    uint64_t* tmem_full_bar = empty_bar + IG_STAGES;  // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    float* s_bias = reinterpret_cast<float*>(smem + IG_STAGES * STAGE_BYTES + 256);
+    uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_bias + IG_MAX_N);          // 8 × 4 KB
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    const int tiles_m = p.B * p.tiles_per_img;
+    const int tiles_n = p.N / BN;
+    const int cblocks = p.C / 64;                     // K blocks per filter tap
+    const int total_kb = 16 * cblocks;
+    const int total_items = tiles_m * tiles_n;
+    const uint32_t a_box_bytes = (uint32_t)(p.bh * p.Wo) * 128u;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB);
+        for (int s = 0; s < IG_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 256);
+    for (int i = threadIdx.x; i < p.N; i += IG_THREADS) s_bias[i] = p.bias ? p.bias[i] : 0.f;
+    // rows of an A stage beyond the box are read by the MMA (M = 128) without ever being written: clear once
+    for (int i = threadIdx.x; i < IG_STAGES * STAGE_BYTES / 16; i += IG_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            uint32_t it = 0;
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+                const int mt = item % tiles_m, nt = item / tiles_m;
+                const int b = mt / p.tiles_per_img, oy0 = (mt - b * p.tiles_per_img) * p.bh;
+                for (int kb = 0; kb < total_kb; ++kb, ++it) {
+                    const int s = it % IG_STAGES;
+                    const uint32_t ph = (it / IG_STAGES) & 1;
+                    const int tap = kb / cblocks, c0 = (kb - tap * cblocks) * 64, ky = tap >> 2, kx = tap & 3;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* st = smem + s * STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[s], 2 * a_box_bytes + B_BYTES);
+                    tma_load_4d_hint(st, &tmA_hi, &full_bar[s], c0, kx - 1, p.stride * oy0 + ky - 1, b, kEvictLast);
+                    tma_load_4d_hint(st + A_BYTES, &tmA_lo, &full_bar[s], c0, kx - 1, p.stride * oy0 + ky - 1, b, kEvictLast);
+                    tma_load_2d_hint(st + 2 * A_BYTES, &tmB, &full_bar[s], kb * 64, nt * BN, kEvictLast);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+            uint32_t it = 0, li = 0;
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
+                const uint32_t as = li & 1, aph = (li >> 1) & 1;
+                mbar_wait(&tmem_empty_bar[as], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * 128;
+                for (int kb = 0; kb < total_kb; ++kb, ++it) {
+                    const int s = it % IG_STAGES;
+                    const uint32_t ph = (it / IG_STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES);
+                    const uint32_t b_ad = a_hi + 2 * A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t bd = make_desc_k_sw128(b_ad + k * 32);
+                        umma_bf16(d_tmem, make_desc_k_sw128(a_hi + k * 32), bd, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        umma_bf16(d_tmem, make_desc_k_sw128(a_hi + A_BYTES + k * 32), bd, idesc, 1u);
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&tmem_full_bar[as]);
+            }
+        }
+    } else {
+        // ===== epilogue: group g = (warp-2)/4 drains accumulator stage g (items li ≡ g mod 2) =====
+        const int q = warp & 3;
+        const uint32_t grp = (uint32_t)(warp - 2) >> 2;
+        uint8_t* wbuf = s_stage + (warp - 2) * 4096;
+        const int sr = lane >> 3, sc = lane & 7;
+        uint32_t li = 0;
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
+            if ((li & 1) != grp) continue;
+            const int mt = item % tiles_m, nt = item / tiles_m;
+            const int b = mt / p.tiles_per_img, oy0 = (mt - b * p.tiles_per_img) * p.bh;
+            const int valid = min(p.bh, p.Ho - oy0) * p.Wo;                  // rows of this tile that exist
+            const size_t out_row0 = ((size_t)b * p.Ho + oy0) * p.Wo;
+            mbar_wait(&tmem_full_bar[grp], (li >> 1) & 1);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + grp * 128 + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(t_addr + (uint32_t)c0, r);
+                tmem_ld_wait();
+                if (c0 + 32 >= BN) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[grp]);
+                }
+                const int nb = nt * BN + c0;
+                uint32_t w[32];
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(s_bias + nb + i);
+                    w[i] = __float_as_uint(__uint_as_float(r[i]) + b4.x); w[i + 1] = __float_as_uint(__uint_as_float(r[i + 1]) + b4.y);
+                    w[i + 2] = __float_as_uint(__uint_as_float(r[i + 2]) + b4.z); w[i + 3] = __float_as_uint(__uint_as_float(r[i + 3]) + b4.w);
+                }
+                __syncwarp();
+                stage_write_row(wbuf, lane, w);
+                __syncwarp();
+                const int trow = q * 32 + sr;                                // + 4·i per store instruction
+                float* dst = p.out + (out_row0 + trow) * (size_t)p.N + nb + sc * 4;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int rr = 4 * i + sr;
+                    if (trow + 4 * i < valid)
+                        *reinterpret_cast<uint4*>(dst + (size_t)(4 * i) * p.N) = *reinterpret_cast<const uint4*>(wbuf + rr * 128 + ((sc ^ (rr & 7)) << 4));
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
+}  // namespace tc

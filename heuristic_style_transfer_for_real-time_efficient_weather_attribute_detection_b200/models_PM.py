@@ -167,7 +167,8 @@ class MultiTaskPatchGAN(nn.Module):
             rc = _lib.lib.pm_forward(cfgp, packed.data_ptr(), x.data_ptr(), dt, B, H, W, logits.data_ptr(),
                                      attn.data_ptr() if attn is not None else None,
                                      feats.data_ptr() if feats is not None else None,
-                                     self._ws.data_ptr(), self._ws.numel(), 0, stream)
+                                     self._ws.data_ptr(), self._ws.numel(),
+                                     0 if getattr(self, "implicit_gemm", True) else _lib.PM_FLAG_NO_IGEMM, stream)
             _lib.check(rc, "pm_forward")
         return logits, attn, feats
 

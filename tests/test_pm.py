@@ -117,3 +117,23 @@ def test_pm_against_oracle_ragged_batch():
         got = out[t].cpu().numpy()
         assert np.array_equal(got.argmax(1), ref[t].argmax(1)), t
         assert rel_fro(got, ref[t]) <= TOL, t
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch,h,w", [(3, 224, 224), (2, 160, 208), (130, 224, 224)])
+def test_pm_implicit_gemm_matches_im2col_path(batch, h, w):
+    """Stride-2 trunk layers as implicit GEMM (TMA boxes with element strides straight from the NHWC planes, tc_igemm.cuh)
+    vs the im2col + GEMM path: the same products in the same K order.  160×208 gives tiles whose last M tile of an image
+    is short; 130 images cross the internal 128-image chunk."""
+    hp, tasks = synth.PM_HPARAMS, synth.PMG_TASKS
+    m = build_pm(hp, tasks)
+    m.load_state_dict(torch_state_dict(synth.pm_state_dict(4, hp, tasks)))
+    m.to("cuda").eval()
+    x = torch.from_numpy(synth.images(4, batch, h, w)).cuda().to(torch.bfloat16)
+    with torch.no_grad():
+        a = m(x, return_full=True)
+        m.implicit_gemm = False
+        b = m(x, return_full=True)
+    for t in tasks:
+        assert rel_fro(a[t]["logits"].cpu().numpy(), b[t]["logits"].cpu().numpy()) <= 1e-5, t
+        assert rel_fro(a[t]["attn"].cpu().numpy(), b[t]["attn"].cpu().numpy()) <= 1e-5, t
