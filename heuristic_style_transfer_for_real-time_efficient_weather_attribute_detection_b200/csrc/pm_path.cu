@@ -451,10 +451,10 @@ int pm_forward(const pm_config* cfg, const void* packed, const void* x, int x_dt
             const int Ho = s.h[l + 1], Wo = s.w[l + 1];
             const int rows = Bc * Ho * Wo;
             float* conv = reinterpret_cast<float*>(ws + w.conv);
-            // stride-2 layers with ≥ 64 input channels: implicit GEMM straight from the previous layer's NHWC hi/lo planes
-            // (tc_igemm.cuh) — no im2col planes are written or re-read.  Layer 0 (3 input channels, NCHW image) and the
-            // stride-1 last layer (13×13 output: an image-aligned M tile would be 117 + 52 of 256 rows) keep im2col + GEMM.
-            const bool igemm = l > 0 && y.stride == 2 && y.cin % 64 == 0 && y.cout % 128 == 0 && y.cout <= tc::IG_MAX_N &&
+            // layers with ≥ 64 input channels: implicit GEMM straight from the previous layer's NHWC hi/lo planes
+            // (tc_igemm.cuh) — no im2col planes are written or re-read.  Layer 0 (3 input channels, NCHW image) keeps
+            // im2col + GEMM.
+            const bool igemm = l > 0 && y.cin % 64 == 0 && y.cout % 128 == 0 && y.cout <= tc::IG_MAX_N &&
                                Wo <= 128 && !(flags & PM_FLAG_NO_IGEMM);
             if (igemm) {
                 if ((rc = tc::launch_conv_igemm(Hb(w.act_hi[(l - 1) & 1]), Hb(w.act_lo[(l - 1) & 1]), pk + L.w[l],

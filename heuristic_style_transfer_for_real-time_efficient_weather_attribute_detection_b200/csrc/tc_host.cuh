@@ -101,13 +101,13 @@ inline int make_tmap_image_rows(CUtensorMap* m, const void* base, int B) {
 }
 
 // 4-D view of an NHWC bf16 activation plane (B, H, W, C) for the implicit-GEMM convolution (tc_igemm.cuh): one box =
-// 64 channels × Wo pixels (every `stride`-th) × bh rows (every `stride`-th) of one image, 128-byte swizzle, zero OOB fill.
-inline int make_tmap_act4d(CUtensorMap* m, const void* base, int B, int H, int W, int C, int stride, int Wo, int bh) {
+// 64 channels × Wo pixels (every `stride`-th) × bh rows (every `stride`-th) × nb images, 128-byte swizzle, zero OOB fill.
+inline int make_tmap_act4d(CUtensorMap* m, const void* base, int B, int H, int W, int C, int stride, int Wo, int bh, int nb) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { pmg::set_cuda_error(cudaErrorNotSupported, "cuTensorMapEncodeTiled entry point"); return PMG_ERR_CUDA; }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)(stride * Wo), (cuuint32_t)(stride * bh), 1};
+    cuuint32_t box[4] = {64, (cuuint32_t)(stride * Wo), (cuuint32_t)(stride * bh), (cuuint32_t)nb};
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -120,16 +120,21 @@ inline int make_tmap_act4d(CUtensorMap* m, const void* base, int B, int H, int W
 inline int launch_conv_igemm(const void* act_hi, const void* act_lo, const void* wgt, const float* bias, int B, int H, int W, int C,
                              int Ho, int Wo, int stride, int N, float* out, cudaStream_t st) {
     if (C % 64 || N % 128 || N > IG_MAX_N || Wo < 1 || Wo > 128 || stride * Wo > 256) return PMG_ERR_UNSUPPORTED;
-    int bh = 128 / Wo;
-    if (bh > Ho) bh = Ho;
-    if (stride * bh > 256) return PMG_ERR_UNSUPPORTED;
+    // M tile = nb images × bh output rows × Wo ≤ 128 rows: several rows of one image, or one row of several images,
+    // whichever leaves fewer of the 128 MMA rows empty over the whole layer
+    const int per = 128 / Wo;
+    int bh = per < Ho ? per : Ho, nb = 1;
+    const double eff_rows = (double)Ho * Wo / (((Ho + bh - 1) / bh) * 128.0);
+    const double eff_imgs = (double)B * Wo / (((B + per - 1) / per) * 128.0);
+    if (eff_imgs > eff_rows + 1e-9) { bh = 1; nb = per < B ? per : B; }
+    if (stride * bh > 256 || nb > 256) return PMG_ERR_UNSUPPORTED;
     CUtensorMap ta_hi, ta_lo, tb;
     int rc;
-    if ((rc = make_tmap_act4d(&ta_hi, act_hi, B, H, W, C, stride, Wo, bh))) return rc;
-    if ((rc = make_tmap_act4d(&ta_lo, act_lo, B, H, W, C, stride, Wo, bh))) return rc;
+    if ((rc = make_tmap_act4d(&ta_hi, act_hi, B, H, W, C, stride, Wo, bh, nb))) return rc;
+    if ((rc = make_tmap_act4d(&ta_lo, act_lo, B, H, W, C, stride, Wo, bh, nb))) return rc;
     if ((rc = make_tmap_bf16(&tb, wgt, N, (uint64_t)16 * C, (uint64_t)16 * C, 128))) return rc;
     IgemmParams p{};
-    p.B = B; p.Ho = Ho; p.Wo = Wo; p.bh = bh; p.tiles_per_img = (Ho + bh - 1) / bh; p.C = C; p.N = N; p.stride = stride;
+    p.B = B; p.Ho = Ho; p.Wo = Wo; p.bh = bh; p.nb = nb; p.tiles_y = (Ho + bh - 1) / bh; p.C = C; p.N = N; p.stride = stride;
     p.out = out; p.bias = bias;
     constexpr int smem = ig_smem_bytes<128>();
     static bool attr_set = false;
@@ -137,7 +142,7 @@ inline int launch_conv_igemm(const void* act_hi, const void* act_lo, const void*
         PMG_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "igemm smem attr");
         attr_set = true;
     }
-    const long long items = (long long)B * p.tiles_per_img * (N / 128);
+    const long long items = (long long)((B + nb - 1) / nb) * p.tiles_y * (N / 128);
     const int grid = (int)(items < num_sms() ? items : num_sms());
     conv_igemm_kernel<128><<<grid, IG_THREADS, smem, st>>>(ta_hi, ta_lo, tb, p);
     PMG_LAUNCH_OK("conv_igemm");

@@ -9,8 +9,9 @@
 // (1, s, s, 1) from (c0, kx-1, s·oy0+ky-1, b): the box lands as [bh·Wo rows × 128 B], 128-byte swizzled, exactly the
 // K-major operand tile the MMA wants; the zero padding is TMA's out-of-bounds fill.  Everything else (B tiles, smem ring,
 // single-thread MMA issue, double-buffered TMEM accumulator, smem-staged coalesced epilogue) is tc_gemm.cuh's structure.
-// M tiles never straddle images; rows ≥ valid rows of a tile (bh·Wo < 128, short last tile of an image) are computed on
-// stale smem and never stored.
+// An M tile is nb images × bh output rows × Wo pixels (≤ 128 rows, the box's 4th dimension is the image): wide layers use
+// nb = 1 and several rows, the small late layers (14×14, 13×13) one output row of 9 images, whichever fills the 128 MMA rows
+// better.  Tile rows that do not exist (short last tile, batch tail) read TMA's zero fill and are never stored.
 #pragma once
 
 #include "tc_prims.cuh"
@@ -18,7 +19,7 @@
 namespace tc {
 
 struct IgemmParams {
-    int B, Ho, Wo, bh, tiles_per_img;   // M tile = bh output rows of one image
+    int B, Ho, Wo, bh, nb, tiles_y;     // M tile = nb images × bh output rows; tiles_y = ceil(Ho / bh) tiles per image group
     int C, N, stride;                   // input channels (multiple of 64), output channels (multiple of BN), conv stride
     float* out;                         // [B·Ho·Wo, N] fp32
     const float* bias;                  // [N]
@@ -64,12 +65,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_bias + IG_MAX_N);          // 8 × 4 KB
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
-    const int tiles_m = p.B * p.tiles_per_img;
+    const int tiles_m = ((p.B + p.nb - 1) / p.nb) * p.tiles_y;
     const int tiles_n = p.N / BN;
     const int cblocks = p.C / 64;                     // K blocks per filter tap
     const int total_kb = 16 * cblocks;
     const int total_items = tiles_m * tiles_n;
-    const uint32_t a_box_bytes = (uint32_t)(p.bh * p.Wo) * 128u;
+    const int rows_img = p.bh * p.Wo;                 // tile rows per image
+    const uint32_t a_box_bytes = (uint32_t)(p.nb * rows_img) * 128u;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA_hi); prefetch_tmap(&tmA_lo); prefetch_tmap(&tmB);
@@ -93,7 +95,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             uint32_t it = 0;
             for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
                 const int mt = item % tiles_m, nt = item / tiles_m;
-                const int b = mt / p.tiles_per_img, oy0 = (mt - b * p.tiles_per_img) * p.bh;
+                const int g = mt / p.tiles_y, b = g * p.nb, oy0 = (mt - g * p.tiles_y) * p.bh;
                 for (int kb = 0; kb < total_kb; ++kb, ++it) {
                     const int s = it % IG_STAGES;
                     const uint32_t ph = (it / IG_STAGES) & 1;
@@ -141,12 +143,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         const uint32_t grp = (uint32_t)(warp - 2) >> 2;
         uint8_t* wbuf = s_stage + (warp - 2) * 4096;
         const int sr = lane >> 3, sc = lane & 7;
+        // the 8 tile rows this lane stores (q·32 + sr + 4i) as (image of the tile, row inside that image's part): fixed per thread
+        int r_img[8], r_rem[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = q * 32 + sr + 4 * i;
+            r_img[i] = r / rows_img;
+            r_rem[i] = r - r_img[i] * rows_img;
+        }
         uint32_t li = 0;
         for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
             if ((li & 1) != grp) continue;
             const int mt = item % tiles_m, nt = item / tiles_m;
-            const int b = mt / p.tiles_per_img, oy0 = (mt - b * p.tiles_per_img) * p.bh;
-            const int valid = min(p.bh, p.Ho - oy0) * p.Wo;                  // rows of this tile that exist
+            const int g = mt / p.tiles_y, b = g * p.nb, oy0 = (mt - g * p.tiles_y) * p.bh;
+            const int valid_img = min(p.nb, p.B - b);                        // images of this tile that exist
+            const int valid_rem = min(p.bh, p.Ho - oy0) * p.Wo;              // rows per image that exist
             const size_t out_row0 = ((size_t)b * p.Ho + oy0) * p.Wo;
             mbar_wait(&tmem_full_bar[grp], (li >> 1) & 1);
             tc_fence_after();
@@ -172,13 +183,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 __syncwarp();
                 stage_write_row(wbuf, lane, w);
                 __syncwarp();
-                const int trow = q * 32 + sr;                                // + 4·i per store instruction
-                float* dst = p.out + (out_row0 + trow) * (size_t)p.N + nb + sc * 4;
+                float* dst = p.out + out_row0 * (size_t)p.N + nb + sc * 4;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int rr = 4 * i + sr;
-                    if (trow + 4 * i < valid)
-                        *reinterpret_cast<uint4*>(dst + (size_t)(4 * i) * p.N) = *reinterpret_cast<const uint4*>(wbuf + rr * 128 + ((sc ^ (rr & 7)) << 4));
+                    if (r_img[i] < valid_img && r_rem[i] < valid_rem)
+                        *reinterpret_cast<uint4*>(dst + ((size_t)r_img[i] * p.Ho * p.Wo + r_rem[i]) * p.N) =
+                            *reinterpret_cast<const uint4*>(wbuf + rr * 128 + ((sc ^ (rr & 7)) << 4));
                 }
             }
         }
