@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) pm_im2col_first_kernel(const void* __rest
 #pragma unroll
         for (int e = 0; e < 4; ++e) tc::split_bf16x2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
         *reinterpret_cast<uint4*>(a_hi + r * Kp + j * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(a_lo + r * Kp + j * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        if (F32IN) *reinterpret_cast<uint4*>(a_lo + r * Kp + j * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);   // bf16 input: lo ≡ 0, no plane
     }
 }
 
@@ -332,6 +332,7 @@ static int pm_gemm(const void* a_hi, const void* a_lo, int Kp, const void* wgt, 
 }
 
 // N may exceed GEMM_MAX_N (scale/shift staging): run column panels of ≤ 512
+template <int NA>
 static int pm_conv_gemm(const void* a_hi, const void* a_lo, int Kp, const bf16* wgt, int M, int N, float* out, const float* bias,
                         cudaStream_t st) {
     for (int n0 = 0; n0 < N; n0 += 512) {
@@ -339,9 +340,9 @@ static int pm_conv_gemm(const void* a_hi, const void* a_lo, int Kp, const bf16* 
         tc::GemmParams g{};
         g.M = M; g.N = nn; g.K = Kp; g.epi = tc::EPI_F32; g.act = tc::GACT_NONE; g.ldc = N; g.out_f32 = out + n0; g.shift = bias + n0;
         int rc;
-        if (nn % 128 == 0) rc = tc::launch_gemm_t<128, 2, tc::EPI_F32, tc::GACT_NONE>(a_hi, a_lo, Kp, wgt + (size_t)n0 * Kp, Kp, g, 1, Kp, st);
-        else if (nn % 64 == 0) rc = tc::launch_gemm_t<64, 2, tc::EPI_F32, tc::GACT_NONE>(a_hi, a_lo, Kp, wgt + (size_t)n0 * Kp, Kp, g, 1, Kp, st);
-        else if (nn % 32 == 0) rc = tc::launch_gemm_t<32, 2, tc::EPI_F32, tc::GACT_NONE>(a_hi, a_lo, Kp, wgt + (size_t)n0 * Kp, Kp, g, 1, Kp, st);
+        if (nn % 128 == 0) rc = tc::launch_gemm_t<128, NA, tc::EPI_F32, tc::GACT_NONE>(a_hi, a_lo, Kp, wgt + (size_t)n0 * Kp, Kp, g, 1, Kp, st);
+        else if (nn % 64 == 0) rc = tc::launch_gemm_t<64, NA, tc::EPI_F32, tc::GACT_NONE>(a_hi, a_lo, Kp, wgt + (size_t)n0 * Kp, Kp, g, 1, Kp, st);
+        else if (nn % 32 == 0) rc = tc::launch_gemm_t<32, NA, tc::EPI_F32, tc::GACT_NONE>(a_hi, a_lo, Kp, wgt + (size_t)n0 * Kp, Kp, g, 1, Kp, st);
         else rc = PMG_ERR_UNSUPPORTED;
         if (rc) return rc;
     }
@@ -474,9 +475,14 @@ int pm_forward(const pm_config* cfg, const void* packed, const void* x, int x_dt
                                                             y.cin, s.h[l], s.w[l], Ho, Wo, y.stride);
             }
             PMG_LAUNCH_OK("pm im2col");
-            if ((rc = pm_conv_gemm(Hb(w.a_hi), Hb(w.a_lo), y.Kp, reinterpret_cast<const bf16*>(pk + L.w[l]), rows, y.cout, conv,
-                                   reinterpret_cast<const float*>(pk + L.bias[l]), st)))
-                return rc;
+            // a bf16 image is exact in one plane: layer 0 then runs without the (all-zero) lo plane
+            if (l == 0 && x_dtype == PMG_BF16)
+                rc = pm_conv_gemm<1>(Hb(w.a_hi), nullptr, y.Kp, reinterpret_cast<const bf16*>(pk + L.w[l]), rows, y.cout, conv,
+                                     reinterpret_cast<const float*>(pk + L.bias[l]), st);
+            else
+                rc = pm_conv_gemm<2>(Hb(w.a_hi), Hb(w.a_lo), y.Kp, reinterpret_cast<const bf16*>(pk + L.w[l]), rows, y.cout, conv,
+                                     reinterpret_cast<const float*>(pk + L.bias[l]), st);
+            if (rc) return rc;
             }
             const bool last = l == p.n_layers - 1;
             pm_instnorm_kernel<<<dim3(y.cout / 32, Bc), 256, 0, st>>>(conv, reinterpret_cast<const float*>(pk + L.gamma[l]),
