@@ -43,19 +43,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// try_wait with a suspend-time hint: the thread is parked in hardware until the phase completes (or the hint / the
-// system's own limit expires) and wakes as soon as it does.  Without the hint a waiting warp re-issues its
-// TRYWAIT + branch every few dozen cycles, and with 20-28 warps per CTA of which most are waiting at any time those
-// spin loops took a measurable share of the issue slots of the sub-partition they share with the working warps
-// (ncu: 12.5 k instructions per band executed in tc_midgram.cuh against 7.9 k of real work).
+// (A suspend-time hint on try_wait — `…, parity, 0x989680` as CUTLASS's ClusterBarrier::wait uses — was measured: no change
+// in any kernel, the default try_wait already parks the warp; without it the bounded spin below stays a usable deadlock trap.)
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, P;\n\t}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     return ok != 0;
 }
