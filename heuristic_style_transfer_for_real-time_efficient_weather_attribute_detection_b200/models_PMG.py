@@ -221,15 +221,22 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
         if torch.is_grad_enabled() and x.requires_grad:
             raise RuntimeError("the PMG B200 forward is inference-only: no autograd graph is recorded "
                                "(input requires grad). Use torch.no_grad().")
+        if x.dtype in (torch.float16, torch.float64):
+            x = x.float()                      # the reference module takes any float tensor; the kernels read fp32 or bf16
         if x.dtype == torch.bfloat16:
             dt = _lib.PMG_BF16
         elif x.dtype == torch.float32:
             dt = _lib.PMG_F32
         else:
-            raise TypeError(f"input dtype {x.dtype} not supported (float32 or bfloat16)")
+            raise TypeError(f"input dtype {x.dtype} not supported (a floating-point tensor is expected)")
         B, Cin, H, W = x.shape
         if Cin != self._cfg.input_nc:
             raise ValueError(f"expected {self._cfg.input_nc} input channels, got {Cin}")
+        if B == 0:                             # empty batch (e.g. an empty last DataLoader batch): empty outputs, no launch
+            np_ = self.patch_div * self.patch_div
+            logits = out if out is not None else torch.empty((0, self._n_logits), dtype=torch.float32, device=x.device)
+            gram = torch.empty((0, np_, self.Cr, self.Cr), dtype=torch.float32, device=x.device) if want_gram else None
+            return logits, gram, {}
         x = x.contiguous()
         cfgp = ctypes.byref(self._cfg)
         with self._lock, torch.cuda.device(x.device):

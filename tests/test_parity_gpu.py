@@ -148,6 +148,21 @@ def test_fused_midgram_matches_two_kernel_path(batch):
     _check_against(fused[0][:n].cpu().numpy(), fused[1][:n].cpu().numpy(), pmg_oracle.pack_logits(ref, tasks), inter["gram"], tasks)
 
 
+def test_empty_batch_and_other_float_dtypes():
+    """The reference module accepts any float tensor and an empty batch (plain torch ops); so does the boundary."""
+    _, hp, tasks = load_contract()
+    m = _model(hp, tasks, 0)
+    x = torch.from_numpy(synth.images(3, 2)).cuda()
+    with torch.no_grad():
+        e = m(x[:0])
+        a, c = m(x), m(x.double())
+        h, hf = m(x.half()), m(x.half().float())
+    assert [(k, tuple(v.shape)) for k, v in e.items()] == [(t, (0, n)) for t, n in tasks.items()]
+    for t in tasks:
+        assert torch.equal(a[t], c[t])                      # the images are fp32-exact: fp64 → fp32 loses nothing
+        assert torch.equal(h[t], hf[t])                     # fp16 input = its fp32 widening
+
+
 def test_forward_into_gather_bucket_slots():
     """forward_packed(x, out=slot) writes the logits into a BucketedGather slot; infer_stream (world 1: the bucket is
     copied instead of gathered) returns every micro-batch's logits in order, incl. a partly filled last bucket."""
