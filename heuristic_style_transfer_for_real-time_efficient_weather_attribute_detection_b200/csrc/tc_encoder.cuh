@@ -404,9 +404,12 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                     umma_bf16(d, make_desc_k_sw128(a_lo + k * 32), bd, idesc, 1u);
                 }
             };
+            long long w_wait = 0;                        // trace only: cycles this thread spent waiting for weight blocks
             auto wait_w = [&]() -> uint32_t {
                 const int s = wi % ENC_NSTAGE;
+                const long long t0 = p.trace ? clock64() : 0;
                 mbar_wait(&w_full[s], (wi / ENC_NSTAGE) & 1);
+                if (p.trace) w_wait += clock64() - t0;
                 tc_fence_after();
                 return aW + s * ENC_STAGE;
             };
@@ -481,6 +484,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                 }
                 umma_commit(sc_full);
             }
+            if (p.trace && blockIdx.x == 0) p.trace[250] = w_wait;
         }
     } else if (warp >= 4 && wq < 2) {
         // ===================== compute warps: TMEM <-> registers, LayerNorm, epilogues =====================

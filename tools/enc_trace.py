@@ -24,6 +24,8 @@ with torch.no_grad():
     torch.cuda.synchronize()
     _lib.lib.pmg_debug_set_trace(None)
 t = buf.cpu().numpy()
+print(f"MMA thread: {int(t[250])} cycles in total waiting for weight blocks (w_full)")
+t[250] = 0
 t0 = min(v for v in t[:256] if v > 0)
 names = {300: "  aux L1h2 scores done", 301: "  aux L1h2 softmax done", 302: "  aux L1h2 PV done", 303: "  aux L1h2 O stored", 0: "mma start", 100: "cmp pdl_wait done", 101: "cmp x0 loaded", 190: "cmp sc_full seen", 191: "cmp logits done"}
 for l in range(2):
