@@ -29,8 +29,20 @@
 #pragma once
 
 #include "tc_prims.cuh"
+#include "tc_gemm2.cuh"      // cluster helpers (cluster_ctarank, cluster_sync_all)
 
 namespace tc {
+
+// ENC_CLUSTER = 1: weight blocks multicast to CTA pairs.  Every CTA of the grid streams the same 1.2 MB of weights and the
+// MMA thread was measured waiting for them 15 % of the stage.  With clusters of 2, each CTA fetches HALF of every block and
+// the copy lands in both CTAs' shared memory (cp.async.bulk … .multicast::cluster); a stage is refilled when BOTH consumers
+// have released it (tcgen05.commit … .multicast::cluster onto both w_empty barriers).  Parity-green on B200, but NOT faster
+// (weight wait 15.9 k vs 17.2 k cycles, stage 0.077 vs 0.075 ms): the wait is the fixed L2 round trip of a refill that can
+// only be requested once the MMAs reading the stage have completed, not the transfer time — what would help is a 4th stage,
+// which the 227 KB do not have room for.  Kept as a compile-time variant; the default is the single-CTA stream.
+#ifndef ENC_CLUSTER
+#define ENC_CLUSTER 0
+#endif
 
 constexpr int ENC_THREADS = 576;
 constexpr int ENC_IPT = 7;                   // images per tile
@@ -89,6 +101,18 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)), "l"(kEvictLast)
         : "memory");
+}
+// same, delivered to the same smem offset (and signalling the mbarrier at the same offset) in both CTAs of a pair
+__device__ __forceinline__ void bulk_g2s_pair(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint [%0], [%1], %2, [%3], %4, %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)), "h"((uint16_t)3), "l"(kEvictLast)
+        : "memory");
+}
+// all previously issued MMAs of this thread arrive on `bar` (same offset) in both CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 // 16-byte asynchronous copy global → shared; src_bytes = 0 zero-fills
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, uint32_t src_bytes) {
@@ -322,11 +346,19 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int wq = warp & 3;
+    // ENC_CLUSTER: every CTA runs the same number of tile iterations (the CTAs of a pair consume the weight stream in
+    // lockstep); a tile index past the last tile is a dummy: all of its rows fail the `grow < T` / `img < B` guards, so it
+    // reads zeros and stores nothing
+#if ENC_CLUSTER
+    const int n_tiles = (((p.B + ENC_IPT - 1) / ENC_IPT + (int)gridDim.x - 1) / (int)gridDim.x) * (int)gridDim.x;
+    const uint32_t pair_rank = cluster_ctarank();
+#else
     const int n_tiles = (p.B + ENC_IPT - 1) / ENC_IPT;
+#endif
     const int T = p.B * 9;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 3; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+        for (int i = 0; i < 3; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], ENC_CLUSTER ? 2 : 1); }
         mbar_init(a_ready, 8);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&dq_full[i], 1); mbar_init(&dq_empty[i], 6);
@@ -356,6 +388,9 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
     }
     tc_fence_before();
     __syncthreads();
+#if ENC_CLUSTER
+    cluster_sync_all();                 // the peer's barriers exist before any multicast copy / commit can reach them
+#endif
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_trigger();
@@ -368,8 +403,13 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                 const int s = wi % ENC_NSTAGE;
                 const uint32_t ph = (wi / ENC_NSTAGE) & 1;
                 mbar_wait(&w_empty[s], ph ^ 1);
-                mbar_expect_tx(&w_full[s], bytes);
+                mbar_expect_tx(&w_full[s], bytes);          // the whole block: this CTA's half + the peer's
+#if ENC_CLUSTER
+                const uint32_t half = bytes / 2;
+                bulk_g2s_pair(sW + s * ENC_STAGE + pair_rank * half, p.wstream + off + pair_rank * half, half, &w_full[s]);
+#else
                 bulk_g2s(sW + s * ENC_STAGE, p.wstream + off, bytes, &w_full[s]);
+#endif
                 ++wi;
             };
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -413,7 +453,11 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                 tc_fence_after();
                 return aW + s * ENC_STAGE;
             };
+#if ENC_CLUSTER
+            auto free_w = [&]() { umma_commit_pair(&w_empty[wi % ENC_NSTAGE]); ++wi; };
+#else
             auto free_w = [&]() { umma_commit(&w_empty[wi % ENC_NSTAGE]); ++wi; };
+#endif
             auto ffn2 = [&](uint32_t pc) {               // x += H(chunk pc) · W2[:, 128·chunk ..]ᵀ
                 mbar_wait(h_ready, pc & 1);
                 tc_fence_after();
@@ -702,6 +746,9 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                 }
     }
     __syncthreads();
+#if ENC_CLUSTER
+    cluster_sync_all();                 // the peer may still be multicasting into this CTA's smem / signalling its barriers
+#endif
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
