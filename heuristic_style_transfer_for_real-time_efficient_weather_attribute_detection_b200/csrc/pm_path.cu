@@ -15,7 +15,7 @@ namespace pmg {
 
 using bf16 = __nv_bfloat16;
 constexpr int PM_MAX_LAYERS = 8;
-constexpr int PM_CHUNK = 128;          // images per internal pass (bounds the im2col workspace)
+constexpr int PM_CHUNK = 256;          // images per internal pass (bounds the workspace)
 constexpr float kInEps = 1e-5f;        // nn.InstanceNorm2d default
 
 struct PmLayer { int cin, cout, stride, K, Kp; };   // K = cin*16, Kp = K rounded up to 64

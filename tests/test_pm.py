@@ -120,11 +120,11 @@ def test_pm_against_oracle_ragged_batch():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("batch,h,w", [(3, 224, 224), (2, 160, 208), (130, 224, 224)])
+@pytest.mark.parametrize("batch,h,w", [(3, 224, 224), (2, 160, 208), (258, 224, 224)])
 def test_pm_implicit_gemm_matches_im2col_path(batch, h, w):
     """Stride-2 trunk layers as implicit GEMM (TMA boxes with element strides straight from the NHWC planes, tc_igemm.cuh)
     vs the im2col + GEMM path: the same products in the same K order.  160×208 gives tiles whose last M tile of an image
-    is short; 130 images cross the internal 128-image chunk."""
+    is short; 258 images cross the internal 256-image chunk."""
     hp, tasks = synth.PM_HPARAMS, synth.PMG_TASKS
     m = build_pm(hp, tasks)
     m.load_state_dict(torch_state_dict(synth.pm_state_dict(4, hp, tasks)))
