@@ -32,6 +32,41 @@ def install_as_reference_models() -> None:
     setattr(pkg, "models_PMG", models_PMG)
     sys.modules["Models.models_PM"] = models_PM            # test_PM.py:16-21 imports MultiTaskPatchGAN & helpers
     setattr(pkg, "models_PM", models_PM)
+    bind_reference_pm_helpers()
+
+
+_REF_PM_NAME = "_pmg_b200_reference_models_PM"
+
+
+def bind_reference_pm_helpers() -> bool:
+    """test_PM.py:16-21 imports ``TaskSpecificModel, load_model_weights, checkpoint_has_se, print_model_parameters`` from
+    ``Models.models_PM`` next to the model class.  They are host-side helpers (checkpoint loading, parameter printing,
+    a one-task wrapper), not part of the forward path, so the reference's own definitions are used: its
+    ``Models/models_PM.py`` is executed under a private module name and the four names are bound onto this package's
+    ``models_PM``.  Returns False when no reference checkout is on ``sys.path``."""
+    from . import models_PM
+    if all(h in models_PM.__dict__ for h in models_PM._REFERENCE_HELPERS):
+        return True
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    roots = list(getattr(sys.modules.get("Models"), "__path__", [])) + [os.path.join(p or ".", "Models") for p in sys.path]
+    for d in roots:
+        path = os.path.join(d, "models_PM.py")
+        if not os.path.isfile(path) or os.path.dirname(os.path.abspath(path)) == here:
+            continue
+        spec = importlib.util.spec_from_file_location(_REF_PM_NAME, path)
+        ref = importlib.util.module_from_spec(spec)
+        try:
+            spec.loader.exec_module(ref)
+        except Exception:
+            continue
+        if not all(hasattr(ref, h) for h in models_PM._REFERENCE_HELPERS):
+            continue
+        sys.modules[_REF_PM_NAME] = ref
+        for h in models_PM._REFERENCE_HELPERS:
+            setattr(models_PM, h, getattr(ref, h))
+        return True
+    return False
 
 
 def main(argv=None) -> int:

@@ -464,6 +464,7 @@ int pm_forward(const pm_config* cfg, const void* packed, const void* x, int x_dt
     const PmPlan p = pm_plan(cfg);
     if (!p.ok || !packed || !x || !logits || !workspace) return PMG_ERR_BAD_ARG;
     if (x_dtype != PMG_F32 && x_dtype != PMG_BF16) return PMG_ERR_BAD_ARG;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(workspace) | reinterpret_cast<uintptr_t>(packed)) & 15) return PMG_ERR_BAD_ARG;
     if (B < 1) return PMG_ERR_BAD_SHAPE;
     const PmShape s = pm_shape(p, H, W);
     if (!s.ok) return PMG_ERR_BAD_SHAPE;

@@ -24,6 +24,8 @@ __global__ void profile_delay_kernel(long long cycles) {
     while (clock64() - t0 < cycles) {}
 }
 
+static inline bool misaligned(const void* p, uintptr_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) != 0; }
+
 static int check_arch() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return PMG_ERR_CUDA;
@@ -121,6 +123,9 @@ static int forward_impl(const pmg_config* cfg, const void* packed, const void* x
     const Plan p = make_plan(cfg);
     if (!p.ok || !packed || !x || !logits || !workspace) return PMG_ERR_BAD_ARG;
     if (x_dtype != PMG_F32 && x_dtype != PMG_BF16) return PMG_ERR_BAD_ARG;
+    // vector loads / TMA tensor maps: the image batch, workspace and packed weights must be 16-byte aligned, outputs 4-byte
+    if (misaligned(x, 16) || misaligned(workspace, 16) || misaligned(packed, 16) || misaligned(logits, 4) || misaligned(gram, 4))
+        return PMG_ERR_BAD_ARG;
     if (B < 1) return PMG_ERR_BAD_SHAPE;
     const Shape s = make_shape(p, H, W);
     if (!s.ok) return PMG_ERR_BAD_SHAPE;
@@ -172,6 +177,7 @@ int pmg_forward_profile(const pmg_config* cfg, const void* packed, const void* x
 int pmg_gram_batched(const void* F, int f_dtype, int B, int C, int HW, float scale, float* G, pmg_stream_t stream) {
     if (!F || !G) return PMG_ERR_BAD_ARG;
     if (f_dtype != PMG_F32 && f_dtype != PMG_BF16) return PMG_ERR_BAD_ARG;
+    if (misaligned(F, f_dtype == PMG_F32 ? 4 : 2) || misaligned(G, 4)) return PMG_ERR_BAD_ARG;
     if (B < 1 || C < 1 || HW < 1 || B > 65535) return PMG_ERR_BAD_SHAPE;
     int rc = check_arch();
     if (rc) return rc;

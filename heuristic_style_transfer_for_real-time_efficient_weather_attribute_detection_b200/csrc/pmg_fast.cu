@@ -499,10 +499,10 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
         if ((rc = tc::make_tmap_image_rows(&tx, x, B))) return rc;
         if ((rc = tc::make_tmap_bf16(&tw0, Wb(f.w0x), 128, 192, 192, 128))) return rc;
         if ((rc = tc::make_tmap_bf16(&tw1, Wb(f.w1x), 512, 64, 64, 64))) return rc;
-        static bool attr_set = false;
-        if (!attr_set) {
+        static tc::PerDeviceFlag attr_set;
+        if (!attr_set.test()) {
             PMG_CUDA_OK(cudaFuncSetAttribute(tc::front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FRONT_SMEM), "front smem attr");
-            attr_set = true;
+            attr_set.set();
         }
         tc::FrontParams fp;
         fp.scale0 = Pf(L.conv_scale[0]); fp.shift0 = Pf(L.conv_shift[0]); fp.scale1 = Pf(L.conv_scale[1]); fp.shift1 = Pf(L.conv_shift[1]);
@@ -547,10 +547,10 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
         if ((rc = tc::make_tmap_bf16(&ta_lo, Hb(w.act1_lo), P, 64, 64, tc::MG_BOX_ROWS))) return rc;
         if ((rc = tc::make_tmap_bf16(&tw2, Wb(f.w2), 128, 64, 64, 128))) return rc;
         if ((rc = tc::make_tmap_bf16(&tw3, Wb(f.w3), 96, 128, 128, 96))) return rc;
-        static bool attr_set = false;
-        if (!attr_set) {
+        static tc::PerDeviceFlag attr_set;
+        if (!attr_set.test()) {
             PMG_CUDA_OK(cudaFuncSetAttribute(tc::midgram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::MG_SMEM), "midgram smem attr");
-            attr_set = true;
+            attr_set.set();
         }
         tc::MidGramParams mp;
         mp.scale2 = Pf(L.conv_scale[2]); mp.shift2 = Pf(L.conv_shift[2]); mp.g_hi = Hb(w.g_hi); mp.g_lo = Hb(w.g_lo);
@@ -566,10 +566,10 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
         if ((rc = tc::make_tmap_bf16(&ta_lo, Hb(w.act1_lo), P, 64, 64, 128))) return rc;
         if ((rc = tc::make_tmap_bf16(&tw2, Wb(f.w2), 128, 64, 64, 128))) return rc;
         if ((rc = tc::make_tmap_bf16(&tw3, Wb(f.w3), 96, 128, 128, 96))) return rc;
-        static bool attr_set = false;
-        if (!attr_set) {
+        static tc::PerDeviceFlag attr_set;
+        if (!attr_set.test()) {
             PMG_CUDA_OK(cudaFuncSetAttribute(tc::mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::MID_SMEM), "mid smem attr");
-            attr_set = true;
+            attr_set.set();
         }
         tc::MidParams mp;
         mp.scale2 = Pf(L.conv_scale[2]); mp.shift2 = Pf(L.conv_shift[2]); mp.chan = Ff(w.chan); mp.P = P;
@@ -593,10 +593,10 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
         PMG_CUDA_OK(cudaMemcpyAsync(taps->chan, Ff(w.chan), (size_t)P * 96 * 4, cudaMemcpyDeviceToDevice, st), "tap chan");
     // patches + Gram (:185-188)
     {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static tc::PerDeviceFlag attr_set;
+        if (!attr_set.test()) {
             PMG_CUDA_OK(cudaFuncSetAttribute(tc::gram96_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GRAM_SMEM), "gram smem attr");
-            attr_set = true;
+            attr_set.set();
         }
         const int grid = T < tc::num_sms() ? T : tc::num_sms();
         PMG_CUDA_OK(tc::launch_pdl(tc::gram96_tc_kernel, dim3(grid), dim3(tc::GRAM_THREADS), tc::GRAM_SMEM, st,
@@ -618,10 +618,10 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
     PMG_MARK(tm, "token_proj");
     if (!(flags & PMG_FLAG_NO_FUSED_ENCODER) && p.nl <= tc::ENC_MAX_LAYERS) {
         // split-K reduce + bias, the whole transformer, task pooling and the heads: one kernel (tc_encoder.cuh)
-        static bool attr_set = false;
-        if (!attr_set) {
+        static tc::PerDeviceFlag attr_set;
+        if (!attr_set.test()) {
             PMG_CUDA_OK(cudaFuncSetAttribute(tc::encoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::ENC_SMEM), "encoder smem attr");
-            attr_set = true;
+            attr_set.set();
         }
         tc::EncParams e{};
         e.wstream = reinterpret_cast<const uint8_t*>(fb + f.wenc);
@@ -725,10 +725,10 @@ static int launch_gram_tc(const void* F, int B, int C, int HW, float scale, floa
     if ((rc = make_tmap_gram3d(&ta, F, B, C, HW, 128))) return rc;
     if ((rc = make_tmap_gram3d(&tb, F, B, C, HW, BN))) return rc;
     constexpr int smem = tc::gb_smem_bytes<BN>();
-    static bool attr_set = false;
-    if (!attr_set) {
+    static tc::PerDeviceFlag attr_set;
+    if (!attr_set.test()) {
         PMG_CUDA_OK(cudaFuncSetAttribute(tc::gram_batched_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "gram tc smem attr");
-        attr_set = true;
+        attr_set.set();
     }
     tc::GramBParams p{G, B, C, HW, scale};
     const long long items = (long long)B * ((C + 127) / 128) * ((C + BN - 1) / BN);

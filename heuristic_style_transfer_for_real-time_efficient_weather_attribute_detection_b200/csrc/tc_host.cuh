@@ -2,6 +2,8 @@
 // through the runtime, so the library does not link libcuda) and the templated launcher.
 #pragma once
 
+#include <atomic>
+
 #include "pmg_common.cuh"
 #include "tc_gemm.cuh"
 #include "tc_gemm2.cuh"
@@ -52,12 +54,30 @@ inline cudaError_t launch_pdl_cluster2(void (*kernel)(KArgs...), dim3 grid, dim3
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// Kernel attributes (cudaFuncSetAttribute) and the SM count are PER DEVICE: a process that drives several GPUs through this
+// library must set / query them once on each.  One bit per device ordinal, lock-free (a racing thread at worst repeats
+// the idempotent driver call).
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    return dev;
+}
+struct PerDeviceFlag {
+    std::atomic<unsigned long long> bits{0};
+    bool test() const { return (bits.load(std::memory_order_acquire) >> current_device()) & 1ull; }
+    void set() { bits.fetch_or(1ull << current_device(), std::memory_order_release); }
+};
+
 inline int num_sms() {
-    static int n = [] {
-        int dev = 0, v = 148;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-        return v > 0 ? v : 148;
-    }();
+    static std::atomic<int> cache[kMaxDevices];
+    const int dev = current_device();
+    int n = cache[dev].load(std::memory_order_relaxed);
+    if (n <= 0) {
+        int v = 148;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cache[dev].store(n = v, std::memory_order_relaxed);
+    }
     return n;
 }
 
@@ -137,10 +157,10 @@ inline int launch_conv_igemm(const void* act_hi, const void* act_lo, const void*
     p.B = B; p.Ho = Ho; p.Wo = Wo; p.bh = bh; p.nb = nb; p.tiles_y = (Ho + bh - 1) / bh; p.C = C; p.N = N; p.stride = stride;
     p.out = out; p.bias = bias;
     constexpr int smem = ig_smem_bytes<128>();
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceFlag attr_set;
+    if (!attr_set.test()) {
         PMG_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "igemm smem attr");
-        attr_set = true;
+        attr_set.set();
     }
     const long long items = (long long)((B + nb - 1) / nb) * p.tiles_y * (N / 128);
     const int grid = (int)(items < num_sms() ? items : num_sms());
@@ -165,10 +185,10 @@ int launch_gemm_t(const void* A_hi, const void* A_lo, int lda, const void* B, in
     p.kblocks_per_split = (total_kb + splits - 1) / splits;
     const int eff_splits = (total_kb + p.kblocks_per_split - 1) / p.kblocks_per_split;
     constexpr int smem = gemm_smem_bytes<BN, NA>();
-    static bool attr_set = false;   // idempotent; racing threads set the same value
-    if (!attr_set) {
+    static PerDeviceFlag attr_set;
+    if (!attr_set.test()) {
         PMG_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, NA, EPI, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "gemm smem attr");
-        attr_set = true;
+        attr_set.set();
     }
     const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
     const int items = ((tiles_m + gemm_mt<BN>() - 1) / gemm_mt<BN>()) * eff_splits * (p.N / BN);
@@ -193,11 +213,11 @@ int launch_gemm2_t(const void* A_hi, const void* A_lo, int lda, const void* B, i
     p.kblocks_per_split = (total_kb + splits - 1) / splits;
     const int eff_splits = (total_kb + p.kblocks_per_split - 1) / p.kblocks_per_split;
     constexpr int smem = g2_smem_bytes<NA>();
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceFlag attr_set;
+    if (!attr_set.test()) {
         PMG_CUDA_OK(cudaFuncSetAttribute(gemm2_kernel<NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "gemm2 smem attr");
         PMG_CUDA_OK(cudaFuncSetAttribute(gemm2_kernel<NA>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0), "gemm2 cluster attr");
-        attr_set = true;
+        attr_set.set();
     }
     const int items = ((M + 255) / 256) * eff_splits;
     const int max_pairs = num_sms() / 2;

@@ -5,6 +5,8 @@
 (``model(x)``, ``return_full``, ``return_embeddings``, ``return_task_embeddings`` — :159-194).  The arithmetic runs
 in the CUDA library behind ``pm_forward`` of ``include/pmg_b200.h`` (tcgen05 GEMMs over im2col planes,
 InstanceNorm with per-sample statistics, task heads as one GEMM + a warp-shuffle softmax); there is no CPU path.
+One module instance holds ONE workspace: concurrent calls from several Python threads (PM_evaluation.py:845-865) are
+serialised by a lock around the enqueue, so all of them must target the same CUDA stream.
 
 Supported configuration = what test_PM.py builds (:153-164) with hyperparameters_PM.json: ``norm="instance"``,
 ``attn_use_se=False``, ``attn_softmax_spatial=True``; other values raise at construction.
@@ -20,8 +22,7 @@ import torch.nn as nn
 
 from . import _lib
 
-__all__ = ["MultiTaskPatchGAN", "TaskHeadImproved", "TaskSpecificModel", "SE", "load_model_weights",
-           "checkpoint_has_se", "print_model_parameters"]
+__all__ = ["MultiTaskPatchGAN", "TaskHeadImproved", "SE"]
 
 
 class SE(nn.Module):
@@ -139,22 +140,33 @@ class MultiTaskPatchGAN(nn.Module):
         x = x.to(pdev)                                         # reference: x = x.to(self.device), models_PM.py:166
         if not x.is_cuda:
             raise RuntimeError("PM B200 forward needs a CUDA tensor / CUDA model: there is no CPU fallback")
-        if torch.is_grad_enabled() and x.requires_grad:
-            raise RuntimeError("the PM B200 forward is inference-only (input requires grad)")
+        if torch.is_grad_enabled() and (x.requires_grad or self.training):
+            # InstanceNorm has no running statistics, so train() and eval() compute the same forward; what the kernels cannot
+            # give is an autograd graph — refuse the calls that would expect one
+            raise RuntimeError("the PM B200 forward is inference-only: no autograd graph is recorded. Call model.eval() "
+                               "and/or wrap the call in torch.no_grad()")
+        if x.dtype in (torch.float16, torch.float64):
+            x = x.float()                      # the reference module takes any float tensor; the kernels read fp32 or bf16
         if x.dtype == torch.bfloat16:
             dt = _lib.PMG_BF16
         elif x.dtype == torch.float32:
             dt = _lib.PMG_F32
         else:
-            raise TypeError(f"input dtype {x.dtype} not supported (float32 or bfloat16)")
+            raise TypeError(f"input dtype {x.dtype} not supported (a floating-point tensor is expected)")
         B, Cin, H, W = x.shape
         if Cin != self._cfg.input_nc:
             raise ValueError(f"expected {self._cfg.input_nc} input channels, got {Cin}")
         x = x.contiguous()
+        if x.data_ptr() % 16:                  # view at an odd storage offset: the kernels use 16-byte loads
+            x = x.clone(memory_format=torch.contiguous_format)
         cfgp = ctypes.byref(self._cfg)
         hf, wf, cf = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         if _lib.lib.pm_feature_shape(cfgp, H, W, ctypes.byref(hf), ctypes.byref(wf), ctypes.byref(cf)) != 0:
             raise ValueError(f"input {tuple(x.shape)} is too small for this trunk")
+        if B == 0:                             # empty batch: empty outputs, no launch (plain torch ops accept it)
+            e = lambda *shape: torch.empty(shape, dtype=torch.float32, device=x.device)
+            return (e(0, self._n_logits), e(0, len(self.tasks_dict), hf.value, wf.value) if want_attn else None,
+                    e(0, hf.value, wf.value, cf.value) if want_feats else None)
         with self._lock, torch.cuda.device(x.device):
             stream = torch.cuda.current_stream(x.device).cuda_stream
             packed = self._ensure_packed(x.device, stream)
@@ -198,46 +210,18 @@ class MultiTaskPatchGAN(nn.Module):
         return self._split(self._run(x)[0])
 
 
-class TaskSpecificModel(nn.Module):
-    """Logits of one task (reference models_PM.py:197-209; used by Grad-CAM / IG wrappers, forward only here)."""
-
-    def __init__(self, model: MultiTaskPatchGAN, task_name: str):
-        super().__init__()
-        self.model, self.task_name = model, task_name
-
-    def forward(self, x):
-        return self.model(x, return_full=False)[self.task_name]
+_REFERENCE_HELPERS = ("TaskSpecificModel", "load_model_weights", "checkpoint_has_se", "print_model_parameters")
 
 
-def load_model_weights(model: nn.Module, path: str, device, strict: bool = True):
-    """Checkpoint loader with the reference's conventions (models_PM.py:213-230): accepts a bare state_dict or a
-    dict under 'model' / 'state_dict', strips a DataParallel 'module.' prefix."""
-    ckpt = torch.load(path, map_location=device)
-    state = ckpt.get("model", ckpt.get("state_dict", ckpt)) if isinstance(ckpt, dict) else ckpt
-    state = {(k[7:] if k.startswith("module.") else k): v for k, v in state.items()}
-    missing, unexpected = model.load_state_dict(state, strict=strict)
-    if missing:
-        print(f"[load] Missing keys ({len(missing)}): {missing[:8]}{' ...' if len(missing) > 8 else ''}")
-    if unexpected:
-        print(f"[load] Unexpected keys ({len(unexpected)}): {unexpected[:8]}{' ...' if len(unexpected) > 8 else ''}")
-    print(f"[load] strict={strict} -> OK")
-
-
-def checkpoint_has_se(path: str, device="cpu") -> bool:
-    sd = torch.load(path, map_location=device)
-    if isinstance(sd, dict):
-        sd = sd.get("model", sd.get("state_dict", sd))
-    return any(".se.mlp." in k for k in sd.keys())
-
-
-def print_model_parameters(model: MultiTaskPatchGAN):
-    total = sum(p.numel() for p in model.parameters() if p.requires_grad)
-    trunk = sum(p.numel() for p in model.trunk.parameters() if p.requires_grad)
-    print("==== Comptage des paramètres ====")
-    print(f"Paramètres totaux du modèle : {total}")
-    print(f"Paramètres du tronc : {trunk}")
-    print("Paramètres par tête de tâche :")
-    for task, head in model.task_heads.items():
-        n = sum(p.numel() for p in head.parameters() if p.requires_grad)
-        print(f"  - Tâche '{task}' : {n} paramètres (in_channels={head.cls_conv.in_channels}, out_channels={head.cls_conv.out_channels})")
-    print("=================================")
+def __getattr__(name):
+    """``TaskSpecificModel`` / ``load_model_weights`` / ``checkpoint_has_se`` / ``print_model_parameters`` (reference
+    models_PM.py:197-253, imported by test_PM.py:16-21) are host-side helpers that do not touch the forward path.  They
+    are not restated here: ``compat.install_as_reference_models()`` binds the reference's own definitions onto this
+    module when its checkout is importable."""
+    if name in _REFERENCE_HELPERS:
+        from . import compat
+        if compat.bind_reference_pm_helpers():
+            return globals()[name]
+        raise AttributeError(f"{name} lives in the reference's Models/models_PM.py; put the reference checkout on sys.path "
+                             "(python -m pmg_b200.compat <reference>/test_PM.py ...) so it can be bound")
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

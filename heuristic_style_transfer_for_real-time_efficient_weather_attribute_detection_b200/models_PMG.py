@@ -80,6 +80,10 @@ def _backbone_plan(input_nc: int, ndf: int, patch_size: int):
     return plan
 
 
+def _epoch_hook(module, incompatible_keys):   # module-level (picklable) load_state_dict post hook
+    module._bump_epoch()
+
+
 class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
     def __init__(
         self,
@@ -138,6 +142,8 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
         self._packed_key: Optional[Tuple] = None
         self._ws: Optional[torch.Tensor] = None
         self._lock = threading.Lock()
+        self._weights_epoch = 0         # bumped by load_state_dict / .to(): captured CUDA graphs (runner.GraphedPMG) re-capture
+        self.register_load_state_dict_post_hook(_epoch_hook)
         self.force_generic = False      # tests: route through the shape-generic kernels
         self.fused_front = True         # fast path: TMA-fed fused conv0+conv1 kernel (bf16 input); False = im2col + GEMMs
         self.fused_encoder = True       # fast path: transformer + pooling + heads in one kernel; False = per-op kernels
@@ -162,6 +168,13 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
         self._cfg = _lib.make_config(*cfg)
         self._packed = self._packed_key = self._ws = None
         self._lock = threading.Lock()
+
+    def _bump_epoch(self):
+        self._weights_epoch = getattr(self, "_weights_epoch", 0) + 1
+
+    def _apply(self, fn, *args, **kwargs):
+        self._bump_epoch()              # .to() / .cuda() / .float(): parameter storage may move
+        return super()._apply(fn, *args, **kwargs)
 
     # ------------------------------------------------------------------ weight packing
     def _abi_params(self):
@@ -210,7 +223,10 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
         return packed
 
     # ------------------------------------------------------------------ forward
-    def _run(self, x: torch.Tensor, want_gram: bool = False, taps: bool = False, out: Optional[torch.Tensor] = None):
+    def _run(self, x: torch.Tensor, want_gram: bool = False, taps: bool = False, out: Optional[torch.Tensor] = None,
+             ws: Optional[torch.Tensor] = None):
+        """``ws``: caller-owned workspace (uint8, >= pmg_workspace_bytes) used instead of the module's own — a captured
+        CUDA graph must keep replaying into memory nobody reallocates (runner.GraphedPMG)."""
         if self.training:
             raise RuntimeError("PMG B200 kernels implement the eval forward only (BatchNorm running stats, "
                                "dropout inert): call model.eval()")
@@ -238,6 +254,8 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
             gram = torch.empty((0, np_, self.Cr, self.Cr), dtype=torch.float32, device=x.device) if want_gram else None
             return logits, gram, {}
         x = x.contiguous()
+        if x.data_ptr() % 16:                  # a view at an odd storage offset: the kernels use 16-byte loads / TMA
+            x = x.clone(memory_format=torch.contiguous_format)
         cfgp = ctypes.byref(self._cfg)
         with self._lock, torch.cuda.device(x.device):
             stream = torch.cuda.current_stream(x.device).cuda_stream
@@ -245,8 +263,13 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
             need = _lib.lib.pmg_workspace_bytes(cfgp, B, H, W)
             if need == 0:
                 raise ValueError(f"input {tuple(x.shape)} is too small for this backbone / patch split")
-            if self._ws is None or self._ws.device != x.device or self._ws.numel() < need:
-                self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+            if ws is not None:
+                if ws.device != x.device or ws.dtype != torch.uint8 or ws.numel() < need or ws.data_ptr() % 16:
+                    raise ValueError(f"ws must be a 16-byte aligned uint8 tensor of >= {need} bytes on {x.device}")
+            else:
+                if self._ws is None or self._ws.device != x.device or self._ws.numel() < need:
+                    self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+                ws = self._ws
             if out is not None:
                 if (out.shape != (B, self._n_logits) or out.dtype != torch.float32 or out.device != x.device
                         or not out.is_contiguous()):
@@ -274,7 +297,7 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
             rc = _lib.lib.pmg_forward(cfgp, packed.data_ptr(), x.data_ptr(), dt, B, H, W, logits.data_ptr(),
                                       gram.data_ptr() if gram is not None else None,
                                       ctypes.byref(tp) if tp is not None else None,
-                                      self._ws.data_ptr(), self._ws.numel(), flags, stream)
+                                      ws.data_ptr(), ws.numel(), flags, stream)
             _lib.check(rc, "pmg_forward")
         return logits, gram, extra
 
@@ -289,10 +312,14 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
         logits, _, _ = self._run(x)
         return self._split(logits)
 
-    def forward_packed(self, x, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward_packed(self, x, out: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None) -> torch.Tensor:
         """(B, Σncls) fp32 — the dict of ``forward`` as one tensor, columns in Tasks.json order.  ``out``: write the
-        logits into this (B, Σncls) fp32 tensor (e.g. a slot of a gather bucket, runner.BucketedGather)."""
-        return self._run(x, out=out)[0]
+        logits into this (B, Σncls) fp32 tensor (e.g. a slot of a gather bucket, runner.BucketedGather); ``ws``: a
+        caller-owned workspace of ``workspace_bytes(...)`` bytes (graph capture)."""
+        return self._run(x, out=out, ws=ws)[0]
+
+    def workspace_bytes(self, B: int, H: int = 224, W: int = 224) -> int:
+        return int(_lib.lib.pmg_workspace_bytes(ctypes.byref(self._cfg), B, H, W))
 
     def forward_with_gram(self, x):
         """(dict, G) with G = per-patch Gram (B, patch_div², Cr, Cr) of reference line :188."""

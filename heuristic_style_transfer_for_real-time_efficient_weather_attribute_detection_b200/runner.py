@@ -264,17 +264,23 @@ class GraphedPMG:
         self.prob_threshold = float(prob_threshold)
         self.host_outputs = host_outputs
         self._graphs = {}
+        self._epoch = None
 
     def _capture(self, x: torch.Tensor):
+        """Every captured graph owns what its kernels point at: the static input, its OWN workspace (the module's shared
+        ``_ws`` is reallocated whenever a later eager call or a larger capture needs more bytes — a graph replaying into
+        the freed buffer would corrupt memory), the packed-weights tensor of the capture epoch, and the outputs."""
         from . import prepost
         dev = x.device
+        B, _, H, W = x.shape
         static_in = torch.empty_like(x)
         static_in.copy_(x)
+        ws = torch.empty(self.model.workspace_bytes(B, H, W), dtype=torch.uint8, device=dev)
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side), torch.no_grad():
-            for _ in range(2):                       # packs weights, sizes the workspace, sets kernel attributes
-                lg = self.model.forward_packed(static_in)
+            for _ in range(2):                       # packs weights, sets kernel attributes, warms the allocator
+                lg = self.model.forward_packed(static_in, ws=ws)
                 if self.postprocess:
                     prepost.postprocess(lg, self.model.num_classes_per_task, self.prob_threshold)
         torch.cuda.current_stream(dev).wait_stream(side)
@@ -282,17 +288,31 @@ class GraphedPMG:
         host = None
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g), torch.no_grad():
-            logits = self.model.forward_packed(static_in)
+            logits = self.model.forward_packed(static_in, ws=ws)
             post = prepost.postprocess(logits, self.model.num_classes_per_task, self.prob_threshold) if self.postprocess else None
             if self.host_outputs:
                 host = torch.empty(logits.shape, dtype=logits.dtype, pin_memory=True)
                 host.copy_(logits, non_blocking=True)
-        return {"graph": g, "in": static_in, "logits": logits, "post": post, "host": host}
+        return {"graph": g, "in": static_in, "logits": logits, "post": post, "host": host, "ws": ws,
+                "packed": self.model._packed}
+
+    def invalidate(self) -> None:
+        """Drop every captured graph (they re-capture on the next call).  Called automatically after
+        ``load_state_dict`` / ``.to()`` on the module; call it by hand after modifying a parameter in place."""
+        self._graphs.clear()
 
     @torch.no_grad()
     def forward_packed(self, x: torch.Tensor):
         if not x.is_cuda:
             raise RuntimeError("GraphedPMG needs a CUDA tensor: there is no CPU fallback")
+        if self.model.training:
+            raise RuntimeError("PMG B200 kernels implement the eval forward only: call model.eval()")
+        epoch = getattr(self.model, "_weights_epoch", 0)
+        if epoch != self._epoch:                     # weights were reloaded / moved: the graphs point at stale packed weights
+            self._graphs.clear()
+            self._epoch = epoch
+        if x.shape[0] == 0:
+            return self.model.forward_packed(x)
         key = (tuple(x.shape), x.dtype, x.device)
         st = self._graphs.get(key)
         if st is None:

@@ -49,9 +49,11 @@ def test_pm_errors_without_gpu():
 
 @pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="reference checkout only exists in the build container")
 def test_pm_reference_helpers_bind_to_b200_module(tmp_path, capsys):
-    """`from Models.models_PM import MultiTaskPatchGAN, load_model_weights, …` (test_PM.py:16-21) resolves to this package."""
+    """`from Models.models_PM import MultiTaskPatchGAN, load_model_weights, …` (test_PM.py:16-21): the model class resolves to
+    this package, the four host-side helpers to the reference's OWN definitions (bound by compat, not restated here)."""
     import pmg_b200
     saved = {k: sys.modules.get(k) for k in ("Models", "Models.models_PM", "Models.models_PMG")}
+    sys.path.insert(0, REFERENCE)                      # what `python /root/reference/test_PM.py` does
     try:
         for k in saved:
             sys.modules.pop(k, None)
@@ -66,7 +68,9 @@ def test_pm_reference_helpers_bind_to_b200_module(tmp_path, capsys):
         load_model_weights(m, str(ck), torch.device("cpu"), strict=True)
         print_model_parameters(m)
         assert "11215692" in capsys.readouterr().out
+        assert load_model_weights.__module__ == "_pmg_b200_reference_models_PM"
     finally:
+        sys.path.remove(REFERENCE)
         for k, v in saved.items():
             sys.modules.pop(k, None)
             if v is not None:
