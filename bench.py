@@ -241,29 +241,75 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(W):
-        step()
-    drain()
-    fence()
+    def timed(step_fn, drain_fn):
+        """W warm-up + args.steps timed steps of step_fn on this rank; returns this rank's device ms (events on the
+        launching stream, barrier + synchronize on both sides)."""
+        for _ in range(W):
+            step_fn()
+        drain_fn()
+        fence()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            step_fn()
+        drain_fn()
+        b.record()
+        fence()
+        return a.elapsed_time(b)
+
+    def over_ranks(ms_local):
+        """(max, [per-rank ms]) — the job's time is the slowest rank's."""
+        if world == 1:
+            return ms_local, [ms_local]
+        t = torch.zeros(world, device=dev)
+        dist.all_gather_into_tensor(t, torch.tensor([ms_local], device=dev))
+        per = [float(v) for v in t.tolist()]
+        return max(per), per
+
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        out = step()
-    drain()
-    e1.record()
-    fence()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms, rank_ms = over_ranks(timed(step, drain))
     value = GB * args.steps / (ms / 1e3)
+
+    # ---- N > 1: (a) control leg without the collective (same forwards, logits stay on their rank) so that the cost of the
+    # exchange and the rank-to-rank spread are separately visible; (b) correctness of the exchange on the real GPUs: one
+    # gathered bucket must hold, at every rank's slot, exactly the logits that rank computed.
+    multi = None
+    if world > 1:
+        lg_local = torch.empty((B, 52), dtype=torch.float32, device=dev)
+
+        def step_nocoll():
+            with torch.no_grad():
+                model.forward_packed(x, out=lg_local)
+
+        ms_nc, rank_ms_nc = over_ranks(timed(step_nocoll, lambda: None))
+        chk = BucketedGather(B, 52, args.gather_steps, dev, keep=True)
+        with torch.no_grad():
+            for _ in range(args.gather_steps):
+                model.forward_packed(x, out=chk.slot())
+                chk.commit()
+            chk.flush()
+            mine = model.forward_packed(x)
+        got = chk.pop()
+        sums = torch.zeros(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(sums, mine.double().sum().reshape(1))
+        ok = len(got) == args.gather_steps
+        for t in got:                                   # t: (world, B, 52) — slot r = rank r's logits of that micro-batch
+            ok = ok and bool(torch.equal(t[rank], mine))
+            ok = ok and bool(torch.equal(t.double().sum(dim=(1, 2)), sums))
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        assert int(flag.item()) == 1, "gathered logits differ from the per-rank logits"
+        stat = lambda v: {"min": round(min(v) / args.steps, 4), "median": round(statistics.median(v) / args.steps, 4),
+                          "max": round(max(v) / args.steps, 4)}
+        multi = {"rank_ms_per_step": stat(rank_ms),
+                 "no_collective": {"value": round(GB * args.steps / (ms_nc / 1e3), 1), "rank_ms_per_step": stat(rank_ms_nc)},
+                 "gather_check": "every rank: gathered (world,B,52) bucket == own logits at its slot, peers' slots match "
+                                 "their fp64 checksums"}
 
     # ---- end to end through the public API: pinned host batch → H2D → (GPU ToTensor+Normalize) → forward → D2H logits,
     # every step.  Three host input formats: decoded uint8 HWC images (headline: 150 KB/image over PCIe), the
     # normalised bf16 batch, and the fp32 batch the reference's own DataLoader delivers.
-    e2e_ms = {}
+    e2e_ms, h2d_ms = {}, {}
     if not args.no_e2e:
         gcpu = torch.Generator().manual_seed(rank)
         hosts = {
@@ -272,30 +318,41 @@ def main():
             "fp32_nchw": x.float().cpu().pin_memory(),
         }
         pipe = HostPipeline(model, chunk=args.e2e_chunk, device=dev)
-        for name, x_host in hosts.items():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def leg(fn):
             for _ in range(3):
-                pipe.infer(x_host)
+                fn()
             fence()
             e0.record()
             for _ in range(args.steps):
-                pipe.infer(x_host)   # logits land in pinned host memory per rank: the D2H read is the result delivery
+                fn()
             e1.record()
             fence()
-            ms_leg = e0.elapsed_time(e1)
-            if world > 1:
-                t = torch.tensor([ms_leg], device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                ms_leg = float(t.item())
-            e2e_ms[name] = ms_leg
+            return over_ranks(e0.elapsed_time(e1))[0]
+
+        for name, x_host in hosts.items():
+            # logits land in pinned host memory per rank: the D2H read is the result delivery
+            e2e_ms[name] = leg(lambda: pipe.infer(x_host))
+            # the wire itself: a bare pinned -> device copy of the same batch on every rank at once, no compute — the
+            # ceiling any end-to-end number from this host format can reach on this box
+            dbuf = torch.empty(x_host.shape, dtype=x_host.dtype, device=dev)
+            h2d_ms[name] = leg(lambda: dbuf.copy_(x_host, non_blocking=True))
+            del dbuf
         del hosts
     clocks = sampler.stop() if sampler else None
     E2E_BYTES = {"uint8_nhwc": 3 * 224 * 224, "bf16_nchw": 3 * 224 * 224 * 2, "fp32_nchw": 3 * 224 * 224 * 4}
 
     def e2e_entry(name):
         ms_leg = e2e_ms[name]
+        wire = GB * args.steps / (h2d_ms[name] / 1e3)
         return {"value": round(GB * args.steps / (ms_leg / 1e3), 1), "unit": "images/s", "h2d_bytes_per_step": GB * E2E_BYTES[name],
                 "d2h_bytes_per_step": GB * 52 * 4, "ms_per_step": round(ms_leg / args.steps, 4), "host_input": name,
-                "bytes_are": "whole job (all ranks) per step"}
+                "bytes_are": "whole job (all ranks) per step",
+                "h2d_ceiling": {"images_per_s": round(wire, 1), "gb_per_s": round(wire * E2E_BYTES[name] / 1e9, 2),
+                                "what": "bare pinned->device copy of the same batch, all ranks at once, timed in this run"},
+                "frac_of_h2d_ceiling": round(h2d_ms[name] / ms_leg, 4),
+                "reference_contract_format": name == "fp32_nchw"}
 
     if rank != 0:
         if world > 1:
@@ -371,11 +428,16 @@ def main():
             e2e_entry("uint8_nhwc"),
             api="pmg_b200.runner.HostPipeline.infer(pinned host uint8 HWC images) -> GPU ToTensor+Normalize "
                 "(prepost.preprocess_u8) -> forward -> pinned host logits", chunk=args.e2e_chunk,
+            format_note="headline leg = decoded uint8 HWC images (what a DataLoader holds before ToTensor/Normalize, "
+                        "utils/datasets_utils.py:212-214, done on the GPU here); the reference module's own forward(x) "
+                        "contract is the normalised fp32 NCHW batch = other_host_inputs.fp32_nchw",
             host_numa_binding=(f"rank threads bound to the {numa_cpus} cores NVML reports local to the GPU" if numa_cpus else "none"),
             other_host_inputs={k: e2e_entry(k) for k in ("bf16_nchw", "fp32_nchw")}),
         "gpu_launches": launches,
         "roofline": roofline,
     }
+    if multi:
+        line["multi_gpu"] = multi
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = time_cpu_baseline()
     print(json.dumps(line), flush=True)

@@ -1,0 +1,5 @@
+"""TEST-ONLY stub of `matplotlib.path` (not installed in this image) — see tests/stubs/_pmg_stub_base.py."""
+from _pmg_stub_base import Anything, module_getattr
+
+__getattr__ = module_getattr("matplotlib.path")
+Path = Anything
