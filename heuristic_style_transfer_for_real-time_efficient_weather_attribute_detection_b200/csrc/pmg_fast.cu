@@ -251,6 +251,26 @@ __global__ void __launch_bounds__(256) im2col0_kernel(const void* __restrict__ x
 }
 
 // ------------------------------------------------------------------------------------------------
+// fp32 NCHW image (what the reference's DataLoader delivers, Functions/PMG_evaluation.py:126) → two bf16 NCHW planes
+// hi = bf16(x), lo = bf16(x − hi): the fused front kernel reads them as 3 + 3 channels against the same conv0 weights
+// (conv0 is linear in the image), so the fp32 entry format keeps ~16 significant bits and never touches im2col.
+// One thread = 8 pixels: 32 B in, 16 B + 16 B out.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split_image_kernel(const float* __restrict__ x, bf16* __restrict__ hi, bf16* __restrict__ lo, size_t n8) {
+    tc::pdl_wait();
+    tc::pdl_trigger();
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n8; t += (size_t)gridDim.x * blockDim.x) {
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(x) + 2 * t);
+        const float4 b = __ldcs(reinterpret_cast<const float4*>(x) + 2 * t + 1);
+        uint32_t h[4], l[4];
+        tc::split_bf16x2(a.x, a.y, h[0], l[0]); tc::split_bf16x2(a.z, a.w, h[1], l[1]);
+        tc::split_bf16x2(b.x, b.y, h[2], l[2]); tc::split_bf16x2(b.z, b.w, h[3], l[3]);
+        reinterpret_cast<uint4*>(hi)[t] = make_uint4(h[0], h[1], h[2], h[3]);
+        reinterpret_cast<uint4*>(lo)[t] = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // token reduce (+bias) and LayerNorm → hi/lo planes.  One warp per token, d = 192 (6 values per lane).
 //   nsplit > 0: tok = Σ_s partial[s] + bias is written to tok_out first (token_proj epilogue)
 //   nsplit = 0: tok_out already holds the residual stream
@@ -461,7 +481,8 @@ static bool use_midgram(int B, unsigned flags) {
 }
 
 int fast_launch_count(const Plan& p, const Shape&, int B, unsigned flags) {
-    const int front = (flags & PMG_FLAG_NO_FUSED_FRONT) ? 3 : 1;
+    // fused front kernel (+ the hi/lo plane split in front of it for fp32 input), or im2col + conv0 GEMM + conv1 GEMM
+    const int front = (flags & PMG_FLAG_NO_FUSED_FRONT) ? 3 : (flags & PMG_FLAG_COUNT_F32_INPUT) ? 2 : 1;
     // conv2 + chan_proj + Gram: one kernel (tc_midgram.cuh), or the fused mid kernel + Gram, or two GEMMs + Gram
     const int mid = use_midgram(B, flags) ? 1 : (flags & PMG_FLAG_NO_FUSED_MID) ? 3 : 2;
     if (!(flags & PMG_FLAG_NO_FUSED_ENCODER) && p.nl <= tc::ENC_MAX_LAYERS) return front + mid + 2 + 1;   // + token_proj (2), token stage
@@ -492,11 +513,22 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
     const int P = B * 196, T = B * 9;
     int rc;
     PMG_MARK(tm, "start");
-    const bool fused_front = (x_dtype == PMG_BF16) && !(flags & PMG_FLAG_NO_FUSED_FRONT);
+    const bool fused_front = !(flags & PMG_FLAG_NO_FUSED_FRONT);
     if (fused_front) {
         // conv0 + conv1 (+ both BN + LeakyReLU) in one TMA-fed tcgen05 kernel (tc_front.cuh)
-        CUtensorMap tx, tw0, tw1;
-        if ((rc = tc::make_tmap_image_rows(&tx, x, B))) return rc;
+        CUtensorMap tx, txl, tw0, tw1;
+        const void* x_hi = x;
+        const void* x_lo = x;
+        if (x_dtype == PMG_F32) {
+            // the planes live in the im2col buffers of the unfused path (401,408 B per image each, 301,056 needed)
+            const size_t n8 = (size_t)B * 3 * 224 * 224 / 8;
+            const int grid = (int)((n8 + 255) / 256 > (size_t)tc::num_sms() * 16 ? (size_t)tc::num_sms() * 16 : (n8 + 255) / 256);
+            PMG_CUDA_OK(tc::launch_pdl(split_image_kernel, dim3(grid), dim3(256), 0, st, reinterpret_cast<const float*>(x), Hb(w.a0_hi), Hb(w.a0_lo), n8), "split_image");
+            PMG_MARK(tm, "split_image");
+            x_hi = Hb(w.a0_hi); x_lo = Hb(w.a0_lo);
+        }
+        if ((rc = tc::make_tmap_image_rows(&tx, x_hi, B))) return rc;
+        if ((rc = tc::make_tmap_image_rows(&txl, x_lo, B))) return rc;
         if ((rc = tc::make_tmap_bf16(&tw0, Wb(f.w0x), 128, 192, 192, 128))) return rc;
         if ((rc = tc::make_tmap_bf16(&tw1, Wb(f.w1x), 512, 64, 64, 64))) return rc;
         static tc::PerDeviceFlag attr_set;
@@ -506,9 +538,9 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
         }
         tc::FrontParams fp;
         fp.scale0 = Pf(L.conv_scale[0]); fp.shift0 = Pf(L.conv_shift[0]); fp.scale1 = Pf(L.conv_scale[1]); fp.shift1 = Pf(L.conv_shift[1]);
-        fp.act1_hi = Hb(w.act1_hi); fp.act1_lo = Hb(w.act1_lo); fp.B = B; fp.trace = g_enc_trace;
+        fp.act1_hi = Hb(w.act1_hi); fp.act1_lo = Hb(w.act1_lo); fp.B = B; fp.nplanes = x_dtype == PMG_F32 ? 2 : 1; fp.trace = g_enc_trace;
         const int grid = 2 * B < tc::num_sms() ? 2 * B : tc::num_sms();
-        PMG_CUDA_OK(tc::launch_pdl(tc::front_kernel, dim3(grid), dim3(tc::FRONT_THREADS), tc::FRONT_SMEM, st, tx, tw0, tw1, fp), "front_kernel");
+        PMG_CUDA_OK(tc::launch_pdl(tc::front_kernel, dim3(grid), dim3(tc::FRONT_THREADS), tc::FRONT_SMEM, st, tx, txl, tw0, tw1, fp), "front_kernel");
         PMG_MARK(tm, "front_conv0_conv1");
     } else {
     // conv0 (:115-117) = im2col + GEMM [B·3136,48]×[48,32], BN+LeakyReLU epilogue → act0 planes == conv1's A

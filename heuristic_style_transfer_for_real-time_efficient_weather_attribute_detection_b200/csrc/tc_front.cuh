@@ -73,13 +73,15 @@ struct FrontParams {
     const float* scale1; const float* shift1;    // [64]
     __nv_bfloat16* act1_hi; __nv_bfloat16* act1_lo;   // [B·196, 64]
     int B;
+    int nplanes;                                 // 1: bf16 image; 2: fp32 image carried as bf16 hi + lo planes (tmXlo) — conv0 is linear
+                                                 // in the image, so the lo plane is just three more "channels" against the same weights
     long long* trace;                            // optional debug stamps (pmg_debug_set_trace), slots 256..383
 };
 #define FR_T(slot) do { if (p.trace && blockIdx.x == 0 && lt == 2) p.trace[256 + (slot)] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(FRONT_THREADS, 1)
-front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW0,
-             const __grid_constant__ CUtensorMap tmW1, const FrontParams p) {
+front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXlo,
+             const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1, const FrontParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sW0 = smem;
@@ -106,9 +108,10 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int n_tiles = 2 * p.B;
+    const int nc = 3 * p.nplanes;                  // (plane, channel) steps per conv1 kernel row
 
     if (threadIdx.x == 0) {
-        prefetch_tmap(&tmX); prefetch_tmap(&tmW0); prefetch_tmap(&tmW1);
+        prefetch_tmap(&tmX); prefetch_tmap(&tmXlo); prefetch_tmap(&tmW0); prefetch_tmap(&tmW1);
         for (int i = 0; i < 3; ++i) { mbar_init(&a0_full[i], 1); mbar_init(&a0_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&d0_full[i], 1); mbar_init(&d0_empty[i], 16); }
         mbar_init(a1_ready, 16); mbar_init(a1_free, 1); mbar_init(w_bar, 1);
@@ -138,27 +141,26 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             for (int i = 0; i < 3; ++i) tma_load_2d(sW0 + i * 16384, &tmW0, w_bar, i * 64, 0);
             for (int i = 0; i < 8; ++i) tma_load_2d(sW1 + i * 8192, &tmW1, w_bar, 0, i * 64);
             pdl_wait();      // weights are constants; everything below may depend on earlier kernels
-            constexpr int PF = 12;                       // prefetch distance in (sy, c) steps = one tile
+            const uint32_t PF = 4 * nc;                  // prefetch distance in (sy, c) steps = one tile
             auto prefetch = [&](uint32_t j) {             // j-th (tile, sy, c) step of this CTA
-                const int tile = blockIdx.x + (int)(j / 12) * gridDim.x;
+                const int tile = blockIdx.x + (int)(j / PF) * gridDim.x;
                 if (tile >= n_tiles) return;
-                const int r = j % 12, sy = r / 3, c = r - 3 * sy;
-#pragma unroll
-                tma_prefetch_4d(&tmX, 0, (tile & 1) * 7, sy * 4, (tile >> 1) * 3 + c);
+                const int r = j % PF, sy = r / nc, c = r - nc * sy;
+                tma_prefetch_4d(c >= 3 ? &tmXlo : &tmX, 0, (tile & 1) * 7, sy * 4, (tile >> 1) * 3 + (c >= 3 ? c - 3 : c));
             };
             for (uint32_t j = 0; j < PF; ++j) prefetch(j);
             uint32_t it = 0, lt = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
                 const int b = tile >> 1, py0 = (tile & 1) * 7;
                 for (int sy = 0; sy < 4; ++sy)
-                    for (int c = 0; c < 3; ++c, ++it) {
+                    for (int c = 0; c < nc; ++c, ++it) {
                         const int s = it % FR_A0_STAGES;
                         const uint32_t ph = (it / FR_A0_STAGES) & 1;
                         prefetch(it + PF);
                         mbar_wait(&a0_empty[s], ph ^ 1);
-                        FR_T(sy * 3 + c);
+                        if (c < 3) FR_T(sy * 3 + c);
                         mbar_expect_tx(&a0_full[s], FR_BOX_BYTES);
-                        tma_load_4d(sA0 + s * FR_A0_STAGE, &tmX, &a0_full[s], 0, py0, sy * 4, b * 3 + c);
+                        tma_load_4d(sA0 + s * FR_A0_STAGE, c >= 3 ? &tmXlo : &tmX, &a0_full[s], 0, py0, sy * 4, b * 3 + (c >= 3 ? c - 3 : c));
                     }
             }
         }
@@ -175,15 +177,15 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                     mbar_wait(&d0_empty[as], aph ^ 1);
                     tc_fence_after();
                     FR_T(20 + 4 * sy);
-                    for (int c = 0; c < 3; ++c, ++it) {
+                    for (int c = 0; c < nc; ++c, ++it) {
                         const int s = it % FR_A0_STAGES;
                         const uint32_t ph = (it / FR_A0_STAGES) & 1;
                         mbar_wait(&a0_full[s], ph);
                         tc_fence_after();
-                        if (c == 2) FR_T(21 + 4 * sy);
+                        if (c == nc - 1) FR_T(21 + 4 * sy);
 #pragma unroll
                         for (int ky = 0; ky < 4; ++ky) {
-                            const int kk = c * 4 + ky;
+                            const int kk = (c >= 3 ? c - 3 : c) * 4 + ky;     // the lo plane meets the same weights as the hi plane
                             umma_bf16(tD0 + as * 128, make_desc_k_sw32(aA0 + s * FR_A0_STAGE + ky * FR_A0_SLOT),
                                       make_desc_k_sw128(aW0 + (kk >> 2) * 16384 + (kk & 3) * 32), idesc0, (c > 0 || ky > 0) ? 1u : 0u);
                         }

@@ -145,7 +145,7 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
         self._weights_epoch = 0         # bumped by load_state_dict / .to(): captured CUDA graphs (runner.GraphedPMG) re-capture
         self.register_load_state_dict_post_hook(_epoch_hook)
         self.force_generic = False      # tests: route through the shape-generic kernels
-        self.fused_front = True         # fast path: TMA-fed fused conv0+conv1 kernel (bf16 input); False = im2col + GEMMs
+        self.fused_front = True         # fast path: TMA-fed fused conv0+conv1 kernel (fp32 input: + hi/lo plane split); False = im2col + GEMMs
         self.fused_encoder = True       # fast path: transformer + pooling + heads in one kernel; False = per-op kernels
         self.fused_mid = True           # fast path: conv2 + chan_proj in one kernel; False = two GEMMs
         self.fused_midgram = True       # fast path: conv2 + chan_proj + patches + Gram in one kernel from 96 images up; "always" = at every
@@ -338,6 +338,6 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
                 | (0 if getattr(self, "fused_midgram", True) else _lib.PMG_FLAG_NO_FUSED_MIDGRAM)
                 | (_lib.PMG_FLAG_ALWAYS_FUSED_MIDGRAM if getattr(self, "fused_midgram", True) == "always" else 0))
 
-    def launches_per_forward(self, B: int, H: int = 224, W: int = 224) -> int:
-        flags = self._flags()
+    def launches_per_forward(self, B: int, H: int = 224, W: int = 224, dtype: torch.dtype = torch.bfloat16) -> int:
+        flags = self._flags() | (0 if dtype == torch.bfloat16 else _lib.PMG_FLAG_COUNT_F32_INPUT)
         return _lib.lib.pmg_forward_launch_count(ctypes.byref(self._cfg), B, H, W, flags)

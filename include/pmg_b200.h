@@ -59,10 +59,11 @@ typedef struct pmg_config {
 /* pmg_forward flags */
 #define PMG_FLAG_FORCE_GENERIC 1u  /* skip the tcgen05 fast path even when the config/shape allow it */
 #define PMG_FLAG_FORCE_FAST 2u     /* fail with PMG_ERR_UNSUPPORTED instead of using the generic kernels */
-#define PMG_FLAG_NO_FUSED_FRONT 4u /* fast path: run conv0/conv1 as im2col + two GEMMs instead of the fused TMA-fed kernel */
+#define PMG_FLAG_NO_FUSED_FRONT 4u /* fast path: run conv0/conv1 as im2col + two GEMMs instead of the fused TMA-fed kernel (fp32 input: the fused kernel reads it as bf16 hi + lo planes) */
 #define PMG_FLAG_NO_FUSED_MID 16u /* fast path: run conv2 and chan_proj as two GEMMs instead of the fused kernel */
 #define PMG_FLAG_NO_FUSED_MIDGRAM 32u /* fast path: run conv2 + chan_proj and the Gram as two kernels (chan map through HBM) instead of the fused kernel */
 #define PMG_FLAG_ALWAYS_FUSED_MIDGRAM 64u /* fast path: use the fused conv2+chan_proj+Gram kernel at every batch size (default: from 96 images up) */
+#define PMG_FLAG_COUNT_F32_INPUT 128u /* pmg_forward_launch_count only: count for fp32 input (one more launch: the hi/lo plane split) */
 #define PMG_FLAG_NO_FUSED_ENCODER 8u /* fast path: run the transformer / pooling / heads as separate kernels instead of the fused token-stage kernel */
 
 /* Optional taps for parity tests: any non-null member receives that intermediate in fp32.

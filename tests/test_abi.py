@@ -56,6 +56,8 @@ def test_host_side_queries_committed_config():
     assert lc(1024, _lib.PMG_FLAG_NO_FUSED_MIDGRAM) == 6
     assert lc(1024, _lib.PMG_FLAG_NO_FUSED_MID) == 7
     assert lc(1024, _lib.PMG_FLAG_NO_FUSED_FRONT) == 7
+    assert lc(1024, _lib.PMG_FLAG_COUNT_F32_INPUT) == 6          # fp32 input: the hi/lo plane split in front of the fused kernel
+    assert lc(1024, _lib.PMG_FLAG_COUNT_F32_INPUT | _lib.PMG_FLAG_NO_FUSED_FRONT) == 7
 
 
 def test_bad_arguments_are_status_codes_not_crashes():
@@ -64,6 +66,10 @@ def test_bad_arguments_are_status_codes_not_crashes():
     assert _lib.lib.pmg_forward(p, None, None, 0, 1, 224, 224, None, None, None, None, 0, 0, None) == 1
     assert _lib.lib.pmg_pack_weights(p, None, 78, None, 0, None) == 1
     assert _lib.lib.pmg_gram_batched(None, 0, 1, 1, 1, 1.0, None, None) == 1
+    # pointer alignment is validated before anything is launched (16 B for the image / workspace / packed weights)
+    need = _lib.lib.pmg_packed_bytes(p)
+    assert _lib.lib.pmg_forward(p, 4096, 4096 + 2, _lib.PMG_BF16, 1, 224, 224, 8192, None, None, 16384, 1 << 30, 0, None) == 1
+    assert need > 0
     bad = _lib.make_config(3, 32, 64, 3, 96, 190, 2, 4, [2])       # d_model not divisible by heads
     assert _lib.lib.pmg_param_count(ctypes.byref(bad)) == -1
     assert _lib.lib.pmg_status_string(4) == b"device is not sm_100 (B200)"

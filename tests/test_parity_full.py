@@ -50,7 +50,8 @@ def test_bench_batch_every_image_vs_reference_port(in_dtype):
     ref = torch.cat([port(x)[t] for t in tasks], 1).numpy()
     with torch.no_grad():
         got = m.forward_packed(x.cuda().to(in_dtype)).cpu().numpy()
-    assert m.launches_per_forward(B) == 5
+    # front (+ the hi/lo plane split for fp32 input), conv2+chan_proj+Gram, token_proj x2, token stage
+    assert m.launches_per_forward(B, dtype=in_dtype) == (5 if in_dtype == torch.bfloat16 else 6)
     assert np.isfinite(got).all()
     # (1) per-task argmax identical on every one of the 1024 x 12 decisions
     bad = np.argwhere(argmax_table(got, tasks) != argmax_table(ref, tasks))
@@ -119,6 +120,25 @@ def test_fp32_input_matches_bf16_input_on_bf16_exact_images():
         b = m.forward_packed(x.to(torch.bfloat16)).cpu().numpy()
     assert np.array_equal(argmax_table(a, tasks), argmax_table(b, tasks))
     assert rel_fro(a, b) <= 1e-4
+
+
+def test_fp32_fused_front_matches_fp32_im2col_path_on_general_fp32_images():
+    """Pixels that are NOT bf16-representable (what ToTensor + Normalize really produce): the fused front kernel reads the
+    fp32 image as bf16 hi + lo planes (6 "channels" against the same conv0 weights), the unfused path as im2col hi/lo
+    planes — same 16-bit operand precision, so they agree to fp32 summation order, and both agree with the fp32 port."""
+    m, hp, tasks = _model(0)
+    g = torch.Generator().manual_seed(99)
+    x = (torch.rand(150, 3, 224, 224, generator=g) - 0.45) / 0.226           # fp32 with full mantissas
+    port = PMGTorchPort(synth.pmg_state_dict(0, hp, tasks), tasks, hp["patch_div"], hp["transformer_heads"])
+    ref = torch.cat([port(x)[t] for t in tasks], 1).numpy()
+    with torch.no_grad():
+        a = m.forward_packed(x.cuda()).cpu().numpy()
+        m.fused_front = False
+        b = m.forward_packed(x.cuda()).cpu().numpy()
+    assert rel_fro(a, b) <= 1e-4
+    for got in (a, b):
+        assert np.array_equal(argmax_table(got, tasks), argmax_table(ref, tasks))
+        assert max(rel_fro(v, split_packed(ref, tasks)[t]) for t, v in split_packed(got, tasks).items()) <= 2e-4
 
 
 def test_unaligned_input_view_is_accepted():
