@@ -144,6 +144,43 @@ def time_cpu_baseline(budget_s=12.0, batch=64):
                       f"reference's op sequence (oracle/pmg_torch_port.py), {os.cpu_count()} threads"}
 
 
+def extra_block(model, x):
+    """N = 1 only: the other BASELINE.json configs and the library comparator, measured in the same run (each a few
+    hundred ms of GPU time): configs[1] Gram microbench rows, configs[2] batch sweep, configs[3] PM forward B = 1024,
+    the B = 1 latency path, device-resident fp32 input, and the reference's op sequence in eager PyTorch ON
+    THE GPU (cuDNN / cuBLAS, default flags) — the library baseline BASELINE.md section 4 item 6 names."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_extra as bx
+    from oracle import synth
+    from oracle.pmg_torch_port import PMGTorchPort
+    out = {}
+    keep = lambda rows, keys: [{k: r[k] for k in keys if k in r} for r in rows]
+    try:
+        out["batch_sweep_bf16"] = keep(bx.sweep(quiet=True, iters=20), ("batch", "ms", "images_per_s"))
+        out["pm_forward_b1024"] = keep(bx.pm(quiet=True), ("ms", "images_per_s", "tensor_frac_of_measured"))[0]
+        out["gram_microbench_b256"] = keep(bx.gram(quiet=True, Cs=(96, 128, 512), HWs=(25, 196, 3136, 16384)),
+                                           ("C", "HW", "ms", "tflops", "gbs", "bound", "frac_of_roofline"))
+        out["latency"] = keep(bx.latency(quiet=True, batches=(1,)),
+                              ("config", "eager_us", "graph_us", "eager_plus_12_cpu_reads_us", "graph_host_outputs_plus_12_reads_us"))[0]
+        xf = x.float()
+        ms = bx.ev_time(lambda: model.forward_packed(xf), 10)
+        out["fp32_device_input_b1024"] = {"ms": round(ms, 4), "images_per_s": round(x.shape[0] / ms * 1e3, 1),
+                                          "launches": model.launches_per_forward(x.shape[0], dtype=torch.float32)}
+        port = PMGTorchPort(synth.pmg_state_dict(0), synth.PMG_TASKS, 3, 4)
+        port.sd = {k: v.cuda() for k, v in port.sd.items()}
+        port.encoder = port.encoder.cuda()
+        ms = bx.ev_time(lambda: port(xf), 5, warm=2)
+        out["gpu_eager_pytorch_baseline"] = {
+            "ms": round(ms, 3), "images_per_s": round(x.shape[0] / ms * 1e3, 1), "dtype": "fp32 (default flags)",
+            "what": "the reference's ATen op sequence (oracle/pmg_torch_port.py) in eager PyTorch on this B200, B = 1024, "
+                    "cuDNN/cuBLAS kernels — a library comparator, not the reference arm"}
+        del xf
+    except Exception as e:      # the headline line must still print
+        out["error"] = f"{type(e).__name__}: {e}"
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -184,6 +221,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--force-generic", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-memory end-to-end leg (ncu runs)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the `extra` block (other BASELINE configs, N=1 only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -438,6 +476,8 @@ def main():
     }
     if multi:
         line["multi_gpu"] = multi
+    if world == 1 and not args.no_extra:
+        line["extra"] = extra_block(model, x)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = time_cpu_baseline()
     print(json.dumps(line), flush=True)

@@ -174,6 +174,34 @@ int pmg_forward_profile(const pmg_config* cfg, const void* packed, const void* x
     return rc;
 }
 
+int pmg_style_gram_shape(const pmg_config* cfg, int H, int W, int* n_patches, int* C) {
+    const Plan p = make_plan(cfg);
+    if (!p.ok || !n_patches || !C) return PMG_ERR_BAD_ARG;
+    const Shape s = make_shape(p, H, W);
+    if (!s.ok) return PMG_ERR_BAD_SHAPE;
+    const int ph = s.Hc / p.pdiv, pw = s.Wc / p.pdiv;
+    if (ph < 1 || pw < 1) return PMG_ERR_BAD_SHAPE;
+    *n_patches = (s.Hc / ph) * (s.Wc / pw);
+    *C = p.C;
+    return PMG_OK;
+}
+
+int pmg_style_grams(const pmg_config* cfg, const void* packed, const void* x, int x_dtype, int B, int H, int W,
+                    float* grams, void* workspace, size_t workspace_bytes, pmg_stream_t stream) {
+    const Plan p = make_plan(cfg);
+    if (!p.ok || !packed || !x || !grams || !workspace) return PMG_ERR_BAD_ARG;
+    if (x_dtype != PMG_F32 && x_dtype != PMG_BF16) return PMG_ERR_BAD_ARG;
+    if (misaligned(x, 16) || misaligned(workspace, 16) || misaligned(packed, 16) || misaligned(grams, 4)) return PMG_ERR_BAD_ARG;
+    if (B < 1) return PMG_ERR_BAD_SHAPE;
+    const Shape s = make_shape(p, H, W);
+    if (!s.ok) return PMG_ERR_BAD_SHAPE;
+    int rc = check_arch();
+    if (rc) return rc;
+    if (workspace_bytes < generic_workspace_bytes(p, s, B)) return PMG_ERR_WORKSPACE;
+    return style_grams_forward(p, s, make_layout(p), reinterpret_cast<const char*>(packed), x, x_dtype, B, grams,
+                               reinterpret_cast<char*>(workspace), reinterpret_cast<cudaStream_t>(stream));
+}
+
 int pmg_gram_batched(const void* F, int f_dtype, int B, int C, int HW, float scale, float* G, pmg_stream_t stream) {
     if (!F || !G) return PMG_ERR_BAD_ARG;
     if (f_dtype != PMG_F32 && f_dtype != PMG_BF16) return PMG_ERR_BAD_ARG;

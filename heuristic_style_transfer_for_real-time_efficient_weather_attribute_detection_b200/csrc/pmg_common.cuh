@@ -167,6 +167,8 @@ int generic_forward(const Plan& p, const Shape& s, const PackedLayout& L, const 
                     int x_dtype, int B, float* logits, float* gram, const pmg_taps* taps, char* ws,
                     cudaStream_t st, StageTimer* tm);
 int generic_launch_count(const Plan& p);
+int style_grams_forward(const Plan& p, const Shape& s, const PackedLayout& L, const char* packed, const void* x, int x_dtype,
+                        int B, float* grams, char* ws, cudaStream_t st);
 int pack_generic(const Plan& p, const PackedLayout& L, const float* const* prm, char* packed, cudaStream_t st);
 
 // fast path entry points (pmg_fast.cu)

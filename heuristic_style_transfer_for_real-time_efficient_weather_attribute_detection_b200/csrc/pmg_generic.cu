@@ -202,11 +202,11 @@ static int launch_sgemm(int mode, const GemmArgs& g, cudaStream_t st) {
 constexpr int GRAM_CHUNK = 32;
 
 __global__ void __launch_bounds__(256) gram_patch_kernel(const float* __restrict__ chan, float* __restrict__ G, int Hc,
-                                                         int Wc, int Cr, int pdiv, int ph, int pw) {
+                                                         int Wc, int Cr, int npy, int npx, int ph, int pw, int flat_w) {
     extern __shared__ float sP[];   // [GRAM_CHUNK][Cr+1]
-    const int np = pdiv * pdiv, n = ph * pw;
+    const int np = npy * npx, n = ph * pw;
     const int b = blockIdx.x / np, k = blockIdx.x % np;
-    const int py = k / pdiv, px = k % pdiv;
+    const int py = k / npx, px = k % npx;
     const int ld = Cr + 1;
     const int tiles1 = (Cr + 3) / 4, ntiles = tiles1 * tiles1;
     const float inv = 1.f / (float)n;
@@ -220,7 +220,13 @@ __global__ void __launch_bounds__(256) gram_patch_kernel(const float* __restrict
             __syncthreads();
             for (int e = threadIdx.x; e < cn * Cr; e += blockDim.x) {
                 const int pi = c0 + e / Cr, ch = e % Cr;
-                const int y = min(py * ph + pi / pw, Hc - 1), x = min(px * pw + pi % pw, Wc - 1);
+                int y, x;
+                if (flat_w > 0) {       // style-transfer export: "patch" k = pixels [k·n, (k+1)·n) of the cropped map, row-major
+                    const int f = k * n + pi;
+                    y = f / flat_w; x = f - y * flat_w;
+                } else {
+                    y = min(py * ph + pi / pw, Hc - 1); x = min(px * pw + pi % pw, Wc - 1);
+                }
                 sP[(e / Cr) * ld + ch] = chan[(((size_t)b * Hc + y) * Wc + x) * Cr + ch];
             }
             __syncthreads();
@@ -408,20 +414,15 @@ size_t generic_workspace_bytes(const Plan& p, const Shape& s, int B) { return ge
 
 int generic_launch_count(const Plan& p) { return p.n_layers + 3 + 7 * p.nl + 1; }
 
-int generic_forward(const Plan& p, const Shape& s, const PackedLayout& L, const char* packed, const void* x,
-                    int x_dtype, int B, float* logits, float* gram, const pmg_taps* taps, char* ws, cudaStream_t st,
-                    StageTimer* tm) {
-    if (p.layer[0].k != 4) return PMG_ERR_UNSUPPORTED;   // patch_size <= 4: no strided layer (never configured)
-    if (p.nl > 8) return PMG_ERR_UNSUPPORTED;
-    if (p.nl > 0 && p.d / p.nh > ATT_MAX_HD) return PMG_ERR_UNSUPPORTED;
-    const GenericWs w = generic_ws(p, s, B);
+// feature_extractor (models_PMG.py:113-128,178): conv k4 s4 / 1x1 as GEMMs with the folded eval-BatchNorm + LeakyReLU
+// epilogue; *out = the last activation, pixel-major (B, Hc, Wc, C) fp32, inside the workspace
+static int run_backbone(const Plan& p, const Shape& s, const PackedLayout& L, const char* packed, const void* x, int x_dtype,
+                        int B, char* ws, const GenericWs& w, cudaStream_t st, StageTimer* tm, const float** out) {
     auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
     auto P = [&](size_t off) { return reinterpret_cast<const float*>(packed + off); };
-    int rc;
     static const char* kConvName[PMG_MAX_BACKBONE] = {"conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "conv7"};
-    PMG_MARK(tm, "start");
-    // backbone (models_PMG.py:178)
     const float* cur = nullptr;
+    int rc;
     for (int l = 0; l < p.n_layers; ++l) {
         const ConvLayer& c = p.layer[l];
         GemmArgs g{};
@@ -436,6 +437,45 @@ int generic_forward(const Plan& p, const Shape& s, const PackedLayout& L, const 
         PMG_MARK(tm, kConvName[l]);
         cur = g.C;
     }
+    *out = cur;
+    return PMG_OK;
+}
+
+// Style-transfer Gram export (utils/PMG/PMG_style_transfer.py:11-48): Gram over the feature_extractor output (C channels),
+// UNPADDED, (Hc/ph)·(Wc/pw) "patches" of ph·pw pixels each.  The reference's permute + reshape (:37) makes patch k the run
+// of ph·pw consecutive pixels of the cropped map in row-major order (not the k-th spatial window); that behaviour is the
+// contract.  Shape-generic fp32 kernels (the reference calls it one image at a time).
+int style_grams_forward(const Plan& p, const Shape& s, const PackedLayout& L, const char* packed, const void* x, int x_dtype,
+                        int B, float* grams, char* ws, cudaStream_t st) {
+    if (p.layer[0].k != 4) return PMG_ERR_UNSUPPORTED;
+    const GenericWs w = generic_ws(p, s, B);
+    const float* feats = nullptr;
+    int rc;
+    if ((rc = run_backbone(p, s, L, packed, x, x_dtype, B, ws, w, st, nullptr, &feats))) return rc;
+    const int ph = s.Hc / p.pdiv, pw = s.Wc / p.pdiv;
+    if (ph < 1 || pw < 1) return PMG_ERR_BAD_SHAPE;
+    const int npy = s.Hc / ph, npx = s.Wc / pw;
+    const size_t smem = (size_t)GRAM_CHUNK * (p.C + 1) * sizeof(float);
+    if (smem > 48 * 1024) return PMG_ERR_UNSUPPORTED;
+    gram_patch_kernel<<<B * npy * npx, 256, smem, st>>>(feats, grams, s.Hc, s.Wc, p.C, npy, npx, ph, pw, npx * pw);
+    PMG_LAUNCH_OK("style gram_patch");
+    return PMG_OK;
+}
+
+int generic_forward(const Plan& p, const Shape& s, const PackedLayout& L, const char* packed, const void* x,
+                    int x_dtype, int B, float* logits, float* gram, const pmg_taps* taps, char* ws, cudaStream_t st,
+                    StageTimer* tm) {
+    if (p.layer[0].k != 4) return PMG_ERR_UNSUPPORTED;   // patch_size <= 4: no strided layer (never configured)
+    if (p.nl > 8) return PMG_ERR_UNSUPPORTED;
+    if (p.nl > 0 && p.d / p.nh > ATT_MAX_HD) return PMG_ERR_UNSUPPORTED;
+    const GenericWs w = generic_ws(p, s, B);
+    auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
+    auto P = [&](size_t off) { return reinterpret_cast<const float*>(packed + off); };
+    int rc;
+    PMG_MARK(tm, "start");
+    // backbone (models_PMG.py:178)
+    const float* cur = nullptr;
+    if ((rc = run_backbone(p, s, L, packed, x, x_dtype, B, ws, w, st, tm, &cur))) return rc;
     // chan_proj (:182)
     {
         GemmArgs g{};
@@ -451,7 +491,7 @@ int generic_forward(const Plan& p, const Shape& s, const PackedLayout& L, const 
     {
         const size_t smem = (size_t)GRAM_CHUNK * (p.Cr + 1) * sizeof(float);
         if (smem > 48 * 1024) return PMG_ERR_UNSUPPORTED;
-        gram_patch_kernel<<<B * s.np, 256, smem, st>>>(F(w.chan), G, s.Hc, s.Wc, p.Cr, p.pdiv, s.ph, s.pw);
+        gram_patch_kernel<<<B * s.np, 256, smem, st>>>(F(w.chan), G, s.Hc, s.Wc, p.Cr, p.pdiv, p.pdiv, s.ph, s.pw, 0);
         PMG_LAUNCH_OK("gram_patch");
         PMG_MARK(tm, "gram");
     }

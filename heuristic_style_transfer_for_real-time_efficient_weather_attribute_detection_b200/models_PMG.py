@@ -326,6 +326,47 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
         logits, gram, _ = self._run(x, want_gram=True)
         return self._split(logits), gram
 
+    @torch.no_grad()
+    def style_patch_grams(self, x: torch.Tensor) -> torch.Tensor:
+        """Forward-only Gram export of the patch style transfer (utils/PMG/PMG_style_transfer.py:11-48,
+        ``extract_patch_grams_for_image``) for a whole batch: ``feature_extractor(x)`` cropped to ``(Hf // ph)·ph x (Wf // pw)·pw``
+        (``ph = Hf // patch_div``, no padding), cut — exactly as the reference's permute + reshape does (:37) — into runs of
+        ``ph·pw`` consecutive row-major pixels, ``G = F·Fᵀ / (ph·pw)`` per run.  Returns (B, n_patches, C, C) fp32 —
+        ``list(out[0])`` is what the reference's function returns for image 0."""
+        if self.training:
+            raise RuntimeError("PMG B200 kernels implement the eval forward only: call model.eval()")
+        if not isinstance(x, torch.Tensor) or x.dim() != 4:
+            raise ValueError("expected a (B, C, H, W) tensor")
+        if not x.is_cuda:
+            raise RuntimeError("PMG B200 forward needs a CUDA tensor: there is no CPU fallback")
+        if x.dtype in (torch.float16, torch.float64):
+            x = x.float()
+        dt = {torch.bfloat16: _lib.PMG_BF16, torch.float32: _lib.PMG_F32}.get(x.dtype)
+        if dt is None:
+            raise TypeError(f"input dtype {x.dtype} not supported (a floating-point tensor is expected)")
+        B, Cin, H, W = x.shape
+        if Cin != self._cfg.input_nc:
+            raise ValueError(f"expected {self._cfg.input_nc} input channels, got {Cin}")
+        cfgp = ctypes.byref(self._cfg)
+        n, c = ctypes.c_int(), ctypes.c_int()
+        if _lib.lib.pmg_style_gram_shape(cfgp, H, W, ctypes.byref(n), ctypes.byref(c)) != 0:
+            raise ValueError(f"input {tuple(x.shape)} is too small for this backbone / patch split")
+        out = torch.empty((B, n.value, c.value, c.value), dtype=torch.float32, device=x.device)
+        if B == 0:
+            return out
+        x = x.contiguous()
+        if x.data_ptr() % 16:
+            x = x.clone(memory_format=torch.contiguous_format)
+        with self._lock, torch.cuda.device(x.device):
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            packed = self._ensure_packed(x.device, stream)
+            need = _lib.lib.pmg_workspace_bytes(cfgp, B, H, W)
+            if self._ws is None or self._ws.device != x.device or self._ws.numel() < need:
+                self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+            _lib.check(_lib.lib.pmg_style_grams(cfgp, packed.data_ptr(), x.data_ptr(), dt, B, H, W, out.data_ptr(),
+                                                self._ws.data_ptr(), self._ws.numel(), stream), "pmg_style_grams")
+        return out
+
     def forward_debug(self, x):
         """Test hook: (packed logits, gram, {chan, tokens_in, tokens_out})."""
         return self._run(x, want_gram=True, taps=True)

@@ -139,6 +139,17 @@ int pmg_forward_profile(const pmg_config* cfg, const void* packed, const void* x
 int pmg_gram_batched(const void* F, int f_dtype, int B, int C, int HW, float scale, float* G,
                      pmg_stream_t stream);
 
+/* Forward-only Gram export of the patch style transfer — replaces extract_patch_grams_for_image
+ * (utils/PMG/PMG_style_transfer.py:11-48) for a whole batch: features = feature_extractor(x) (the conv / BN / LeakyReLU
+ * stack, C = last conv width; no chan_proj), disjoint ph x pw windows with ph = Hf / patch_div, pw = Wf / patch_div
+ * (feats.unfold: NO padding, a remainder is dropped), G_k = F_k·F_k^T / (ph·pw).  As in the reference (:37, permute +
+ * reshape), "patch" k is the run of ph·pw consecutive pixels [k·N, (k+1)·N) of the cropped map flattened row-major.
+ *   grams (B, n_patches, C, C) fp32; pmg_style_gram_shape gives n_patches = (Hf/ph)·(Wf/pw) and C.
+ * Workspace: pmg_workspace_bytes(cfg, B, H, W). */
+int pmg_style_gram_shape(const pmg_config* cfg, int H, int W, int* n_patches, int* C);
+int pmg_style_grams(const pmg_config* cfg, const void* packed, const void* x, int x_dtype, int B, int H, int W,
+                    float* grams, void* workspace, size_t workspace_bytes, pmg_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Callers' pre/post-processing on the GPU (the steps either side of model(x) in the reference's loops).
  * ------------------------------------------------------------------------------------------------ */

@@ -163,6 +163,32 @@ def pmg_forward(x: np.ndarray, sd: Dict[str, np.ndarray], tasks: Dict[str, int],
     return logits
 
 
+def style_patch_grams(x: np.ndarray, sd: Dict[str, np.ndarray], patch_div: int, dtype=np.float32) -> np.ndarray:
+    """extract_patch_grams_for_image — utils/PMG/PMG_style_transfer.py:11-48, for every image of the batch.
+
+    Features = ``model.feature_extractor(x)`` (:21; the conv/BN/LeakyReLU stack only, C = last conv width — NOT chan_proj);
+    ``patch_h = H // patch_div`` (:29-30); ``feats.unfold(2, ph, ph).unfold(3, pw, pw)`` (:32) keeps ``nH = H // ph`` x
+    ``nW = W // pw`` windows WITHOUT padding (trailing rows / cols that do not fill a window are dropped).  Then (:37)
+    ``permute(0, 1, 2, 4, 3, 5)`` puts the axes back into IMAGE order (nH, ph, nW, pw) and ``reshape(1, C, nb, ph, pw)``
+    re-chunks that row-major image: what the reference calls patch k is the run of ``ph·pw`` CONSECUTIVE pixels
+    ``[k·N, (k+1)·N)`` of the cropped (nH·ph) x (nW·pw) map flattened row-major — not the k-th spatial window.  The
+    reference's results are the contract, so that is what is restated (and what the CUDA export computes).
+    ``G_k = F_k @ F_k.T / (ph·pw)`` (:44-45).  Returns (B, nH·nW, C, C)."""
+    sd = {k: (v.astype(dtype) if v.dtype.kind == "f" else v) for k, v in sd.items()}
+    x = x.astype(dtype)
+    for (i, kind) in _plan_from_state_dict(sd):
+        w = sd[f"feature_extractor.{i}.weight"]
+        x = conv_k4s4(x, w) if kind == "strided" else conv_1x1(x, w)
+        b = f"feature_extractor.{i + 1}"
+        x = leaky_relu(batchnorm_eval(x, sd[f"{b}.weight"], sd[f"{b}.bias"], sd[f"{b}.running_mean"], sd[f"{b}.running_var"]))
+    B, C, H, W = x.shape
+    ph, pw = H // patch_div, W // patch_div
+    ny, nx = H // ph, W // pw
+    flat = np.ascontiguousarray(x[:, :, :ny * ph, :nx * pw]).reshape(B, C, ny * nx, ph * pw)
+    p = flat.transpose(0, 2, 1, 3)
+    return np.matmul(p, p.transpose(0, 1, 3, 2)) / dtype(ph * pw)
+
+
 def pack_logits(logits: Dict[str, np.ndarray], tasks: Dict[str, int]) -> np.ndarray:
     """(B, Σncls) in Tasks.json order — the layout the C-ABI writes."""
     return np.concatenate([logits[t] for t in tasks], axis=1)

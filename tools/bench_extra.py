@@ -39,8 +39,15 @@ def pmg_model():
     return m.cuda().eval()
 
 
-def sweep():
+def emit(rows, r, quiet):
+    rows.append(r)
+    if not quiet:
+        print(json.dumps(r), flush=True)
+
+
+def sweep(quiet=False, iters=40):
     m = pmg_model()
+    rows = []
     for B in (64, 128, 256, 512, 1024):
         # rotate over enough distinct batches that the inputs of consecutive iterations do not sit in the 126 MB L2
         nb = max(2, int(np.ceil(260e6 / (B * 3 * 224 * 224 * 2))))
@@ -49,15 +56,18 @@ def sweep():
         def step():
             with torch.no_grad():
                 m.forward_packed(xs[i[0] % nb]); i[0] += 1
-        ms = ev_time(step, 40)
+        ms = ev_time(step, iters)
         v = B / ms * 1e3
-        print(json.dumps({"config": "PMG full forward bf16 batch sweep (BASELINE configs[2])", "batch": B, "ms": round(ms, 4),
-                          "images_per_s": round(v, 1), "tensor_frac_of_measured": round(v * 77348864 / 1e12 / PEAK["bf16_tflops"], 4),
-                          "hbm_frac_of_measured": round(v * 301264 / 1e9 / PEAK["hbm_gbs"], 4), "l2": f"{nb} rotating input batches"}), flush=True)
+        emit(rows, {"config": "PMG full forward bf16 batch sweep (BASELINE configs[2])", "batch": B, "ms": round(ms, 4),
+                    "images_per_s": round(v, 1), "tensor_frac_of_measured": round(v * 77348864 / 1e12 / PEAK["bf16_tflops"], 4),
+                    "hbm_frac_of_measured": round(v * 301264 / 1e9 / PEAK["hbm_gbs"], 4), "l2": f"{nb} rotating input batches"}, quiet)
+        del xs
+    return rows
 
 
-def pm():
+def pm(quiet=False):
     tasks = synth.PMG_TASKS
+    rows = []
     m = pmg_b200.MultiTaskPatchGAN(tasks_dict=tasks, input_nc=3, ndf=64, norm="instance", patch_size=73, device=torch.device("cuda"), attn_use_se=False)
     m.cuda().eval()
     B, chunk = 1024, 256
@@ -68,30 +78,34 @@ def pm():
                 m(x)
     ms = ev_time(step, 3, warm=1)
     v = B / ms * 1e3
-    print(json.dumps({"config": "PM forward batch 1024 (BASELINE configs[3]; 4 chunks of 256, random-init weights)", "ms": round(ms, 3),
-                      "images_per_s": round(v, 1), "flops_per_image": 5.40e9,
-                      "tensor_frac_of_measured": round(v * 5.40e9 / 1e12 / PEAK["bf16_tflops"], 4)}), flush=True)
+    emit(rows, {"config": "PM forward batch 1024 (BASELINE configs[3]; 4 chunks of 256, random-init weights)", "ms": round(ms, 3),
+                "images_per_s": round(v, 1), "flops_per_image": 5.40e9,
+                "tensor_frac_of_measured": round(v * 5.40e9 / 1e12 / PEAK["bf16_tflops"], 4)}, quiet)
+    return rows
 
 
-def gram():
+def gram(quiet=False, Cs=(64, 96, 128, 256, 512), HWs=(16, 25, 196, 3136, 16384)):
     from pmg_b200.gram import gram_batched
-    for C in (64, 96, 128, 256, 512):
-        for HW in (16, 25, 196, 3136, 16384):
+    rows = []
+    for C in Cs:
+        for HW in HWs:
             F = torch.randn(256, C, HW, device="cuda").to(torch.bfloat16)
             ms = ev_time(lambda: gram_batched(F), 5, warm=2)
             fl, by = 2.0 * C * C * HW * 256, (2.0 * C * HW + 4.0 * C * C) * 256
             bound_ms = max(fl / (PEAK["bf16_tflops"] * 1e12), by / (PEAK["hbm_gbs"] * 1e9)) * 1e3
-            print(json.dumps({"config": "Gram microbench batch 256 (BASELINE configs[1])", "C": C, "HW": HW, "ms": round(ms, 4),
-                              "tflops": round(fl / ms / 1e9, 2), "gbs": round(by / ms / 1e6, 1),
-                              "bound": "tensor" if fl / (PEAK["bf16_tflops"] * 1e12) > by / (PEAK["hbm_gbs"] * 1e9) else "hbm",
-                              "frac_of_roofline": round(bound_ms / ms, 4)}), flush=True)
+            emit(rows, {"config": "Gram microbench batch 256 (BASELINE configs[1])", "C": C, "HW": HW, "ms": round(ms, 4),
+                        "tflops": round(fl / ms / 1e9, 2), "gbs": round(by / ms / 1e6, 1),
+                        "bound": "tensor" if fl / (PEAK["bf16_tflops"] * 1e12) > by / (PEAK["hbm_gbs"] * 1e9) else "hbm",
+                        "frac_of_roofline": round(bound_ms / ms, 4)}, quiet)
             del F
+    return rows
 
 
-def latency():
+def latency(quiet=False, batches=(1, 8)):
     from pmg_b200.runner import GraphedPMG
     m = pmg_model()
-    for B in (1, 8):
+    rows = []
+    for B in batches:
         x = torch.randn(B, 3, 224, 224, device="cuda")     # fp32, as the reference's transform delivers it
         def eager():
             with torch.no_grad():
@@ -114,7 +128,8 @@ def latency():
              "eager_plus_12_cpu_reads_us": round(wall(lambda: ref_style(m), 100), 1),
              "graph_host_outputs_plus_12_reads_us": round(wall(lambda: ref_style(gh), 100), 1),
              "device_ms_eager": round(ev_time(eager, 200), 4), "device_ms_graph": round(ev_time(lambda: g(x), 200), 4)}
-        print(json.dumps(r), flush=True)
+        emit(rows, r, quiet)
+    return rows
 
 
 if __name__ == "__main__":
