@@ -750,34 +750,42 @@ static int make_tmap_gram3d(CUtensorMap* m, const void* base, int B, int C, int 
     return PMG_OK;
 }
 
-template <int BN>
+template <int BN, bool LSU>
 static int launch_gram_tc(const void* F, int B, int C, int HW, float scale, float* G, cudaStream_t st) {
-    CUtensorMap ta, tb;
+    CUtensorMap ta{}, tb{};
     int rc;
-    if ((rc = make_tmap_gram3d(&ta, F, B, C, HW, 128))) return rc;
-    if ((rc = make_tmap_gram3d(&tb, F, B, C, HW, BN))) return rc;
+    if (!LSU) {
+        if ((rc = make_tmap_gram3d(&ta, F, B, C, HW, 128))) return rc;
+        if ((rc = make_tmap_gram3d(&tb, F, B, C, HW, BN))) return rc;
+    }
     constexpr int smem = tc::gb_smem_bytes<BN>();
     static tc::PerDeviceFlag attr_set;
     if (!attr_set.test()) {
-        PMG_CUDA_OK(cudaFuncSetAttribute(tc::gram_batched_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "gram tc smem attr");
+        PMG_CUDA_OK(cudaFuncSetAttribute(tc::gram_batched_tc_kernel<BN, LSU>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "gram tc smem attr");
         attr_set.set();
     }
-    tc::GramBParams p{G, B, C, HW, scale};
+    tc::GramBParams p{G, B, C, HW, scale, reinterpret_cast<const bf16*>(F)};
     const long long items = (long long)B * ((C + 127) / 128) * ((C + BN - 1) / BN);
     const int grid = (int)(items < tc::num_sms() ? items : tc::num_sms());
-    tc::gram_batched_tc_kernel<BN><<<grid, tc::GB_THREADS, smem, st>>>(ta, tb, p);
+    tc::gram_batched_tc_kernel<BN, LSU><<<grid, LSU ? tc::GB_THREADS_LSU : tc::GB_THREADS, smem, st>>>(ta, tb, p);
     PMG_LAUNCH_OK("gram_batched_tc");
     return PMG_OK;
 }
 
-// tcgen05 batched Gram (tc_gramb.cuh): bf16 input whose rows TMA can address (HW % 8 == 0: 16-byte pitch)
+// tcgen05 batched Gram (tc_gramb.cuh), bf16 input: rows TMA can address (HW % 8 == 0: 16-byte pitch, 16-byte aligned base)
+// go through the TMA producer; every other bf16 shape (HW = 25, 196, …) through the loader-warp variant of the same kernel.
+// Long rows that TMA cannot take stay on the CUDA-core kernel: a warp-load per 128-byte row piece is the small-map design.
 int gram_batched_fast(const void* F, int f_dtype, int B, int C, int HW, float scale, float* G, cudaStream_t st) {
-    if (f_dtype != PMG_BF16 || HW % 8 != 0 || C % 4 != 0 || C < 16) return PMG_ERR_UNSUPPORTED;
-    if ((reinterpret_cast<uintptr_t>(F) & 15) || (reinterpret_cast<uintptr_t>(G) & 15)) return PMG_ERR_UNSUPPORTED;
-    if (C <= 32) return launch_gram_tc<32>(F, B, C, HW, scale, G, st);
-    if (C <= 64) return launch_gram_tc<64>(F, B, C, HW, scale, G, st);
-    if (C <= 96) return launch_gram_tc<96>(F, B, C, HW, scale, G, st);
-    return launch_gram_tc<128>(F, B, C, HW, scale, G, st);
+    if (f_dtype != PMG_BF16 || C % 4 != 0 || C < 16) return PMG_ERR_UNSUPPORTED;
+    if (reinterpret_cast<uintptr_t>(G) & 15) return PMG_ERR_UNSUPPORTED;
+    const bool tma_ok = HW % 8 == 0 && !(reinterpret_cast<uintptr_t>(F) & 15);
+    if (!tma_ok && HW > 1024) return PMG_ERR_UNSUPPORTED;
+#define PMG_GRAM_TC(BNV) return tma_ok ? launch_gram_tc<BNV, false>(F, B, C, HW, scale, G, st) : launch_gram_tc<BNV, true>(F, B, C, HW, scale, G, st)
+    if (C <= 32) PMG_GRAM_TC(32);
+    if (C <= 64) PMG_GRAM_TC(64);
+    if (C <= 96) PMG_GRAM_TC(96);
+    PMG_GRAM_TC(128);
+#undef PMG_GRAM_TC
 }
 
 }  // namespace pmg

@@ -9,6 +9,12 @@
 // Persistent CTAs walk work items (batch, m-tile, n-tile); warp 0 = TMA producer, warp 1 = MMA issuer,
 // warps 2..9 = two epilogue groups draining the double-buffered TMEM accumulator with coalesced staged stores.
 // The full C×C matrix is computed (no symmetry shortcut), FLOPs counted as 2·C²·HW.
+//
+// LSU = true: the same kernel for inputs TMA cannot address — HW not a multiple of 8 (row pitch not a multiple of 16
+// bytes: the PMG patch shapes HW = 25 and the 14×14 map HW = 196 of models_PMG.py:188 / PMG_style_transfer.py:44) or a base
+// pointer that is not 16-byte aligned.  Eight loader warps replace the TMA producer: one warp-wide load moves the 64
+// pixels (128 B) of one channel row of a k-block (4-byte lanes when every row start is 4-byte aligned, 2-byte lanes
+// otherwise), the lanes store them straight into the K-major 128B-swizzled operand tile, pixel tail and rows ≥ C zero.
 #pragma once
 
 #include "tc_prims.cuh"
@@ -16,12 +22,65 @@
 namespace tc {
 
 constexpr int GB_THREADS = 320;
+constexpr int GB_LOADER_WARPS = 8;
+constexpr int GB_THREADS_LSU = GB_THREADS + 32 * GB_LOADER_WARPS;
 
 struct GramBParams {
     float* G;
     int B, C, HW;
     float scale;
+    const __nv_bfloat16* F;      // LSU variant only
 };
+
+// LSU staging of one k-block (pixels k0 .. k0+w-1 of every row, w ≤ 64).  The (128 + BN) row pieces are walked as ONE linear
+// index space of VEC-pixel slots (VEC = 4 / 2 / 1 pixels = 8 / 4 / 2-byte loads, the widest the row pitch and the base pointer
+// allow), so a warp-wide load is fully used whatever HW is — for a single k-block (HW ≤ 64: the PMG patch shape HW = 25) the
+// slots of consecutive rows are contiguous in memory.  GB_LOADS_IN_FLIGHT loads are issued before the first store, so every
+// warp keeps that many independent global loads in flight.
+constexpr int GB_LOADS_IN_FLIGHT = 8;
+
+template <int VEC, int BN>
+__device__ __forceinline__ void gb_stage_kblock(uint8_t* st, const __nv_bfloat16* Fb, int mt, int nt, int C, int HW, int k0, int lw, int lane, bool same) {
+    constexpr int A_BYTES = 128 * 128;
+    const int w = min(64, HW - k0);                         // valid pixels of this k-block
+    // a ring stage is reused by k-blocks of different width when HW > 64: then the whole 64-pixel block is written (zeros past
+    // w); with a single k-block every item has the same footprint and the tail stays as cleared at kernel start
+    const int wv = ((HW > 64 ? 64 : w) + VEC - 1) / VEC;    // slots per row
+    const int S = (same ? 128 : 128 + BN) * wv;            // same: the B tile is the head of the A tile (diagonal item)
+    for (int base = lw * 32; base < S; base += GB_LOADER_WARPS * 32 * GB_LOADS_IN_FLIGHT) {
+        uint32_t v[GB_LOADS_IN_FLIGHT][VEC == 4 ? 2 : 1];
+        int rr[GB_LOADS_IN_FLIGHT], ee[GB_LOADS_IN_FLIGHT];
+#pragma unroll
+        for (int j = 0; j < GB_LOADS_IN_FLIGHT; ++j) {
+            const int i = base + j * GB_LOADER_WARPS * 32 + lane;
+            const int r = i / wv, e = (i - r * wv) * VEC;    // tile row (A rows 0..127, then B rows), first pixel of the slot
+            rr[j] = i < S ? r : -1; ee[j] = e;
+            const int row = r >= 128 ? nt * BN + r - 128 : mt * 128 + r;
+            v[j][0] = 0;
+            if (VEC == 4) v[j][1] = 0;
+            if (i < S && row < C && e < w) {
+                const __nv_bfloat16* src = Fb + (size_t)row * HW + k0 + e;
+                if (VEC == 4) {                              // HW % 4 == 0: the slot is whole
+                    const uint2 t = __ldg(reinterpret_cast<const uint2*>(src));
+                    v[j][0] = t.x; v[j][1] = t.y;
+                } else if (VEC == 2) {                       // HW % 2 == 0: the slot is whole
+                    v[j][0] = __ldg(reinterpret_cast<const unsigned int*>(src));
+                } else {
+                    v[j][0] = (uint32_t)__ldg(reinterpret_cast<const unsigned short*>(src));
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < GB_LOADS_IN_FLIGHT; ++j) {
+            if (rr[j] < 0) continue;
+            const int rl = rr[j] >= 128 ? rr[j] - 128 : rr[j], e = ee[j];
+            uint8_t* dst = st + (rr[j] >= 128 ? A_BYTES : 0) + rl * 128 + (((e >> 3) ^ (rl & 7)) << 4) + (e & 7) * 2;
+            if (VEC == 4) *reinterpret_cast<uint2*>(dst) = make_uint2(v[j][0], v[j][1]);
+            else if (VEC == 2) *reinterpret_cast<uint32_t*>(dst) = v[j][0];
+            else *reinterpret_cast<unsigned short*>(dst) = (unsigned short)v[j][0];
+        }
+    }
+}
 
 __device__ __forceinline__ void tma_load_3d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2,
                                                  uint64_t policy) {
@@ -38,8 +97,8 @@ __host__ __device__ constexpr int gb_stages() { return (160 * 1024) / gb_stage_b
 template <int BN>
 __host__ __device__ constexpr int gb_smem_bytes() { return gb_stages<BN>() * gb_stage_bytes<BN>() + 1024 + 256 + 8 * 4096; }
 
-template <int BN>
-__global__ void __launch_bounds__(GB_THREADS, 1)
+template <int BN, bool LSU = false>
+__global__ void __launch_bounds__(LSU ? GB_THREADS_LSU : GB_THREADS, 1)
 gram_batched_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GramBParams p) {
     constexpr int STAGES = gb_stages<BN>();
     constexpr int STAGE_BYTES = gb_stage_bytes<BN>();
@@ -60,19 +119,45 @@ gram_batched_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int total_items = p.B * tiles_m * tiles_n;
 
     if (threadIdx.x == 0) {
-        prefetch_tmap(&tmA); prefetch_tmap(&tmB);
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        if (!LSU) { prefetch_tmap(&tmA); prefetch_tmap(&tmB); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], LSU ? GB_LOADER_WARPS : 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 256);
+    if (LSU) {      // the loaders never write the pixel tail of a k-block: clear the operand stages once (see gb_stage_kblock)
+        for (int i = threadIdx.x; i < STAGES * STAGE_BYTES / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+        fence_proxy_async();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        if (elect_one()) {
+    if (LSU && warp >= GB_THREADS / 32) {
+        // ===== loader warps (LSU variant): warp lw stages rows lw, lw+8, … of the A tile and of the B tile =====
+        const int lw = warp - GB_THREADS / 32;
+        const uintptr_t fa = reinterpret_cast<uintptr_t>(p.F);
+        const int vec = ((p.HW & 3) == 0 && (fa & 7) == 0) ? 4 : ((p.HW & 1) == 0 && (fa & 3) == 0) ? 2 : 1;
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+            const int nt = item % tiles_n, mt = (item / tiles_n) % tiles_m, b = item / (tiles_n * tiles_m);
+            const __nv_bfloat16* Fb = p.F + (size_t)b * p.C * p.HW;
+            for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                const int s = it % STAGES;
+                mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+                uint8_t* st = smem + s * STAGE_BYTES;
+                const bool same = nt * BN == mt * 128;
+                if (vec == 4) gb_stage_kblock<4, BN>(st, Fb, mt, nt, p.C, p.HW, kb * 64, lw, lane, same);
+                else if (vec == 2) gb_stage_kblock<2, BN>(st, Fb, mt, nt, p.C, p.HW, kb * 64, lw, lane, same);
+                else gb_stage_kblock<1, BN>(st, Fb, mt, nt, p.C, p.HW, kb * 64, lw, lane, same);
+                fence_proxy_async();                   // generic-proxy smem writes → visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[s]);
+            }
+        }
+    } else if (warp == 0) {
+        if (!LSU && elect_one()) {
             uint32_t it = 0;
             for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
                 const int nt = item % tiles_n, mt = (item / tiles_n) % tiles_m, b = item / (tiles_n * tiles_m);
@@ -80,9 +165,11 @@ gram_batched_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     const int s = it % STAGES;
                     mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
                     uint8_t* st = smem + s * STAGE_BYTES;
-                    mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                    // diagonal item: the B rows are the first BN rows of the A tile — one load, one operand tile
+                    const bool same = nt * BN == mt * 128;
+                    mbar_expect_tx(&full_bar[s], same ? A_BYTES : STAGE_BYTES);
                     tma_load_3d_hint(st, &tmA, &full_bar[s], kb * 64, mt * 128, b, kEvictFirst);
-                    tma_load_3d_hint(st + A_BYTES, &tmB, &full_bar[s], kb * 64, nt * BN, b, kEvictFirst);
+                    if (!same) tma_load_3d_hint(st + A_BYTES, &tmB, &full_bar[s], kb * 64, nt * BN, b, kEvictFirst);
                 }
             }
         }
@@ -92,6 +179,8 @@ gram_batched_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             uint32_t it = 0, li = 0;
             for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
                 const uint32_t as = li & 1;
+                const int nt = item % tiles_n, mt = (item / tiles_n) % tiles_m;
+                const bool same = nt * BN == mt * 128;
                 mbar_wait(&tmem_empty_bar[as], ((li >> 1) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * 128;
@@ -99,7 +188,7 @@ gram_batched_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     const int s = it % STAGES;
                     mbar_wait(&full_bar[s], (it / STAGES) & 1);
                     tc_fence_after();
-                    const uint32_t a_ad = smem_u32(smem + s * STAGE_BYTES), b_ad = a_ad + A_BYTES;
+                    const uint32_t a_ad = smem_u32(smem + s * STAGE_BYTES), b_ad = same ? a_ad : a_ad + A_BYTES;
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         umma_bf16(d_tmem, make_desc_k_sw128(a_ad + k * 32), make_desc_k_sw128(b_ad + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);

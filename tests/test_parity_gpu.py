@@ -184,17 +184,26 @@ def test_forward_into_gather_bucket_slots():
 def test_gram_microbench_kernel_matches_matmul():
     from pmg_b200.gram import gram_batched
     gen = torch.Generator(device="cuda").manual_seed(0)
-    # HW % 8 == 0 → tcgen05 kernel (tc_gramb.cuh), incl. partial k-block tails (HW 200, 1000), channel counts that
-    # are not a tile multiple (80, 320) and the multi-tile C = 512; HW 25 / fp32 input → CUDA-core kernel
+    # bf16 input → tcgen05 kernel (tc_gramb.cuh): HW % 8 == 0 through the TMA producer (incl. partial k-block tails HW 200 /
+    # 1000, channel counts that are not a tile multiple 80 / 320, multi-tile C = 512); HW % 8 != 0 — the PMG patch shape
+    # HW 25 and the 14x14 map HW 196 (models_PMG.py:188, PMG_style_transfer.py:44) — through the loader-warp variant
+    # (4-byte lanes for even HW, 2-byte lanes for odd HW); fp32 input → CUDA-core kernel
     for (B, C, HW) in [(4, 96, 25), (3, 128, 16), (5, 64, 16), (2, 64, 196), (3, 80, 200), (2, 96, 3136), (2, 256, 1000),
-                       (2, 320, 64), (1, 512, 3136), (150, 128, 64), (2, 512, 16384)]:
+                       (2, 320, 64), (1, 512, 3136), (150, 128, 64), (2, 512, 16384), (256, 128, 196), (3, 512, 25),
+                       (2, 320, 196), (5, 80, 25), (300, 96, 25), (2, 128, 77), (1, 256, 1001)]:
         F = torch.randn(B, C, HW, device="cuda", generator=gen).to(torch.bfloat16)
         ref = torch.matmul(F.double(), F.double().mT) / HW
         got = gram_batched(F)
         # tensor-core fp32 accumulation over K = HW terms: measured 3e-8 (HW 16) … 5.5e-5 (HW 16384); gate 1e-3 (north_star)
-        assert rel_fro(got.cpu().numpy(), ref.cpu().numpy()) <= (2e-4 if HW % 8 == 0 else 1e-5), (B, C, HW)
+        assert rel_fro(got.cpu().numpy(), ref.cpu().numpy()) <= 2e-4, (B, C, HW)
         got2 = gram_batched(F.float(), scale=1.0 / (C * HW))
         assert rel_fro(got2.cpu().numpy(), (ref * HW / (C * HW)).cpu().numpy()) <= 1e-5
+    # a TMA-shaped problem at a base pointer that is only 2-byte aligned takes the loader-warp variant as well
+    base = torch.randn(3 * 128 * 64 + 1, device="cuda", generator=gen).to(torch.bfloat16)
+    F = base[1:].view(3, 128, 64)
+    assert F.data_ptr() % 16 != 0
+    ref = torch.matmul(F.double(), F.double().mT) / 64
+    assert rel_fro(gram_batched(F).cpu().numpy(), ref.cpu().numpy()) <= 2e-4
 
 
 def test_cuda_library_is_the_loaded_path():

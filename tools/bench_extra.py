@@ -90,7 +90,16 @@ def gram(quiet=False, Cs=(64, 96, 128, 256, 512), HWs=(16, 25, 196, 3136, 16384)
     for C in Cs:
         for HW in HWs:
             F = torch.randn(256, C, HW, device="cuda").to(torch.bfloat16)
-            ms = ev_time(lambda: gram_batched(F), 5, warm=2)
+            # small shapes finish in microseconds: time 10 launches replayed from a CUDA graph so that the Python / ctypes call
+            # overhead (~20 us) is not what gets measured
+            gram_batched(F)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for _ in range(10):
+                    out = gram_batched(F)
+            ms = ev_time(g.replay, 5, warm=2) / 10
+            del g, out
             fl, by = 2.0 * C * C * HW * 256, (2.0 * C * HW + 4.0 * C * C) * 256
             bound_ms = max(fl / (PEAK["bf16_tflops"] * 1e12), by / (PEAK["hbm_gbs"] * 1e9)) * 1e3
             emit(rows, {"config": "Gram microbench batch 256 (BASELINE configs[1])", "C": C, "HW": HW, "ms": round(ms, 4),
