@@ -218,6 +218,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="images per GPU per step")
     ap.add_argument("--e2e-chunk", type=int, default=128)
     ap.add_argument("--gather-steps", type=int, default=4, help="N>1: steps whose logits share one all_gather")
+    ap.add_argument("--nccl-gather", action="store_true", help="N>1: use the NCCL all-gather instead of the peer-memory pull")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--force-generic", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-memory end-to-end leg (ncu runs)")
@@ -234,7 +235,7 @@ def main():
     import torch.distributed as dist
     import pmg_b200
     from pmg_b200 import _lib
-    from pmg_b200.runner import BucketedGather, HostPipeline
+    from pmg_b200.runner import BucketedGather, HostPipeline, make_bucketed_gather
     from oracle import synth   # seeded synthetic checkpoint generator (test infra; weights only, not compute)
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU path); use --impl reference for the CPU arm"
@@ -260,7 +261,8 @@ def main():
     # the logits of --gather-steps consecutive steps go out in ONE all_gather (runner.BucketedGather): each forward writes
     # straight into its slot of the bucket, the gather of a full bucket runs under the forwards that fill the next one, and
     # drain() gathers what is left and waits for everything, inside the timed region
-    bucket = BucketedGather(B, 52, args.gather_steps, dev) if world > 1 else None
+    bucket, exchange = (make_bucketed_gather(B, 52, args.gather_steps, dev, prefer_peer=not args.nccl_gather)
+                        if world > 1 else (None, "none"))
 
     def step():
         with torch.no_grad():
@@ -320,7 +322,7 @@ def main():
                 model.forward_packed(x, out=lg_local)
 
         ms_nc, rank_ms_nc = over_ranks(timed(step_nocoll, lambda: None))
-        chk = BucketedGather(B, 52, args.gather_steps, dev, keep=True)
+        chk, _ = make_bucketed_gather(B, 52, args.gather_steps, dev, keep=True, prefer_peer=not args.nccl_gather)
         with torch.no_grad():
             for _ in range(args.gather_steps):
                 model.forward_packed(x, out=chk.slot())
@@ -459,8 +461,9 @@ def main():
         "config": {"workload": WORKLOAD, "global_batch": GB, "per_gpu_batch": B, "parallelism": f"dp{world}",
                    "l2_policy": f"input {B * 3 * 224 * 224 * 2 / 1e6:.0f} MB per GPU per step > 126 MB L2",
                    "path": "generic-fp32" if args.force_generic else "default",
-                   "collective": (f"one all_gather_into_tensor of ({args.gather_steps},B_local,52) fp32 logits per {args.gather_steps} steps, "
-                                  "async under the next forwards; all waited for inside the timed region") if world > 1 else "none"},
+                   "collective": (f"{exchange}: ({args.gather_steps},B_local,52) fp32 logits of every rank on every rank, once per "
+                                  f"{args.gather_steps} steps, async under the next forwards; all waited for inside the timed region")
+                                 if world > 1 else "none"},
         "clocks": clocks,
         "e2e": None if not e2e_ms else dict(
             e2e_entry("uint8_nhwc"),
