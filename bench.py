@@ -264,10 +264,12 @@ def main():
     bucket, exchange = (make_bucketed_gather(B, 52, args.gather_steps, dev, prefer_peer=not args.nccl_gather)
                         if world > 1 else (None, "none"))
 
+    lg_single = torch.empty((B, 52), dtype=torch.float32, device=dev)
+
     def step():
         with torch.no_grad():
             if bucket is None:
-                return model.forward_packed(x)
+                return model.forward_packed(x, out=lg_single)
             lg = model.forward_packed(x, out=bucket.slot())
             bucket.commit()
         return lg
@@ -315,11 +317,9 @@ def main():
     # gathered bucket must hold, at every rank's slot, exactly the logits that rank computed.
     multi = None
     if world > 1:
-        lg_local = torch.empty((B, 52), dtype=torch.float32, device=dev)
-
         def step_nocoll():
             with torch.no_grad():
-                model.forward_packed(x, out=lg_local)
+                model.forward_packed(x, out=lg_single)
 
         ms_nc, rank_ms_nc = over_ranks(timed(step_nocoll, lambda: None))
         chk, _ = make_bucketed_gather(B, 52, args.gather_steps, dev, keep=True, prefer_peer=not args.nccl_gather)
@@ -408,10 +408,13 @@ def main():
     acc = {}
     reps = 5
     lg = torch.empty((B, 52), dtype=torch.float32, device=dev)
+    ws_prof = torch.empty(model.workspace_bytes(B), dtype=torch.uint8, device=dev)
+    with torch.no_grad():
+        model.forward_packed(x, out=lg, ws=ws_prof)      # makes sure the packed weights exist
     flags = _lib.PMG_FLAG_FORCE_GENERIC if args.force_generic else 0
     for _ in range(reps):
         rc = _lib.lib.pmg_forward_profile(cfgp, model._packed.data_ptr(), x.data_ptr(), _lib.PMG_BF16, B, 224, 224,
-                                          lg.data_ptr(), model._ws.data_ptr(), model._ws.numel(), flags,
+                                          lg.data_ptr(), ws_prof.data_ptr(), ws_prof.numel(), flags,
                                           torch.cuda.current_stream().cuda_stream, stages, 64, ctypes.byref(n_st))
         _lib.check(rc, "pmg_forward_profile")
         for i in range(n_st.value):

@@ -533,14 +533,18 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
         if ((rc = tc::make_tmap_bf16(&tw1, Wb(f.w1x), 512, 64, 64, 64))) return rc;
         static tc::PerDeviceFlag attr_set;
         if (!attr_set.test()) {
-            PMG_CUDA_OK(cudaFuncSetAttribute(tc::front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FRONT_SMEM), "front smem attr");
+            PMG_CUDA_OK(cudaFuncSetAttribute(tc::front_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FRONT_SMEM), "front smem attr");
+            PMG_CUDA_OK(cudaFuncSetAttribute(tc::front_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::FRONT_SMEM), "front smem attr");
             attr_set.set();
         }
         tc::FrontParams fp;
         fp.scale0 = Pf(L.conv_scale[0]); fp.shift0 = Pf(L.conv_shift[0]); fp.scale1 = Pf(L.conv_scale[1]); fp.shift1 = Pf(L.conv_shift[1]);
-        fp.act1_hi = Hb(w.act1_hi); fp.act1_lo = Hb(w.act1_lo); fp.B = B; fp.nplanes = x_dtype == PMG_F32 ? 2 : 1; fp.trace = g_enc_trace;
+        fp.act1_hi = Hb(w.act1_hi); fp.act1_lo = Hb(w.act1_lo); fp.B = B; fp.trace = g_enc_trace;
         const int grid = 2 * B < tc::num_sms() ? 2 * B : tc::num_sms();
-        PMG_CUDA_OK(tc::launch_pdl(tc::front_kernel, dim3(grid), dim3(tc::FRONT_THREADS), tc::FRONT_SMEM, st, tx, txl, tw0, tw1, fp), "front_kernel");
+        if (x_dtype == PMG_F32)
+            PMG_CUDA_OK(tc::launch_pdl(tc::front_kernel<2>, dim3(grid), dim3(tc::FRONT_THREADS), tc::FRONT_SMEM, st, tx, txl, tw0, tw1, fp), "front_kernel");
+        else
+            PMG_CUDA_OK(tc::launch_pdl(tc::front_kernel<1>, dim3(grid), dim3(tc::FRONT_THREADS), tc::FRONT_SMEM, st, tx, txl, tw0, tw1, fp), "front_kernel");
         PMG_MARK(tm, "front_conv0_conv1");
     } else {
     // conv0 (:115-117) = im2col + GEMM [B·3136,48]×[48,32], BN+LeakyReLU epilogue → act0 planes == conv1's A
