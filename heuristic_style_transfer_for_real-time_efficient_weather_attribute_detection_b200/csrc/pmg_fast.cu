@@ -39,7 +39,7 @@ struct FastW {
     size_t w0, w1, w2, w3;              // conv0 [32][64] (K 48 zero-padded to 64), conv1 [64][512] (K = (sy,sx,c)), conv2 [128][64], chan [96][128]
     size_t wth, wtl;                     // token_proj folded over the Gram's symmetry: hi [192][6144], lo [192][3072] (off-diagonal blocks)
     size_t win[8], wo[8], wf1[8], wf2[8];
-    size_t w0x, w1x;                     // fused front end: block-sparse conv0 [128][192], conv1 as (sy,kb) blocks [512][64]
+    size_t w0x, w1x;                     // fused front end: conv0 for 8-column units (pack_w0u_kernel, 12 KB), conv1 as (sy,kb) blocks [512][64]
     size_t wq;                           // [64][192]: rows 0..ntask-1 task queries, then the ncls_total classifier rows, zero pad
     size_t wenc;                         // fused token stage: pre-swizzled weight stream (tc_encoder.cuh), nl layers + heads block
     size_t total;
@@ -55,7 +55,7 @@ static FastW fast_w(const Plan& p) {
         f.win[l] = take(576 * 192); f.wo[l] = take(192 * 192); f.wf1[l] = take(384 * 192); f.wf2[l] = take(192 * 384);
     }
     f.wq = take(64 * 192);
-    f.w0x = take(128 * 192); f.w1x = take(512 * 64);
+    f.w0x = take(6 * 2 * 64 * 8); f.w1x = take(512 * 64);
     f.wenc = take(((size_t)(p.nl <= tc::ENC_MAX_LAYERS ? p.nl : 0) * tc::ENC_LAYER_BYTES + tc::ENC_STAGE) / sizeof(bf16));
     f.total = o;
     return f;
@@ -94,13 +94,16 @@ __global__ void pack_w0_kernel(const float* __restrict__ in, bf16* __restrict__ 
     out[i] = __float2bfloat16_rn(k < 48 ? in[co * 48 + k] : 0.f);
 }
 
-// fused front end, conv0 weight block-sparse over the column offset sx:
-//   [n = sx*32 + co][k = (c*4 + ky)*16 + sxp*4 + kx] = (sxp == sx) ? w0[co][c][ky][kx] : 0
-__global__ void pack_w0x_kernel(const float* __restrict__ in, bf16* __restrict__ out) {
+// fused front end, conv0 weight for 8-column units (tc_front.cuh): an MMA row is a 16-byte unit of an image row = two conv0
+// pixels xp = 0, 1; N = 64 = (xp, co), block-sparse over xp.  Stored exactly as the no-swizzle K-major operand the kernel's
+// descriptors walk: K step j = (c, ky pair) | K chunk ck (ky = 2·(j&1) + ck) | 8-row core matrices of 8 rows × 16 bytes:
+//   element e of row n = xp·32 + co  =  (e >> 2 == xp) ? w0[co][c][ky][e & 3] : 0
+__global__ void pack_w0u_kernel(const float* __restrict__ in, bf16* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 128 * 192) return;
-    const int n = i / 192, k = i % 192, sx = n >> 5, co = n & 31, cky = k >> 4, sxp = (k >> 2) & 3, kx = k & 3;
-    out[i] = __float2bfloat16_rn(sxp == sx ? in[(co * 12 + cky) * 4 + kx] : 0.f);
+    if (i >= 6 * 2 * 64 * 8) return;
+    const int e = i & 7, n = (i >> 3) & 63, ck = (i >> 9) & 1, j = i >> 10;
+    const int c = j >> 1, ky = 2 * (j & 1) + ck, xp = n >> 5, co = n & 31;
+    out[i] = __float2bfloat16_rn((e >> 2) == xp ? in[((co * 3 + c) * 4 + ky) * 4 + (e & 3)] : 0.f);
 }
 // fused front end, conv1 weight as 8 blocks (sy, kb): [blk*64 + n][col = (sx&1)*32 + c] = w1[n][c][sy][sx], sx = kb*2 + col/32
 __global__ void pack_w1x_kernel(const float* __restrict__ in, bf16* __restrict__ out) {
@@ -142,7 +145,7 @@ int pack_fast(const Plan& p, const PackedLayout& L, const float* const* prm, cha
     };
     pack_w0_kernel<<<8, 256, 0, st>>>(prm[0], Bp(f.w0));           // (32,3,4,4) == [32][c*16+ky*4+kx], K padded to 64
     pack_w1_kernel<<<(64 * 512 + 255) / 256, 256, 0, st>>>(prm[5], Bp(f.w1));
-    pack_w0x_kernel<<<(128 * 192 + 255) / 256, 256, 0, st>>>(prm[0], Bp(f.w0x));
+    pack_w0u_kernel<<<(6144 + 255) / 256, 256, 0, st>>>(prm[0], Bp(f.w0x));
     pack_w1x_kernel<<<(512 * 64 + 255) / 256, 256, 0, st>>>(prm[5], Bp(f.w1x));
     cvt(prm[10], f.w2, 128 * 64);
     cvt(prm[15], f.w3, 96 * 128);
@@ -516,7 +519,7 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
     const bool fused_front = !(flags & PMG_FLAG_NO_FUSED_FRONT);
     if (fused_front) {
         // conv0 + conv1 (+ both BN + LeakyReLU) in one TMA-fed tcgen05 kernel (tc_front.cuh)
-        CUtensorMap tx, txl, tw0, tw1;
+        CUtensorMap tx, txl, tw1;
         const void* x_hi = x;
         const void* x_lo = x;
         if (x_dtype == PMG_F32) {
@@ -529,7 +532,6 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
         }
         if ((rc = tc::make_tmap_image_rows(&tx, x_hi, B))) return rc;
         if ((rc = tc::make_tmap_image_rows(&txl, x_lo, B))) return rc;
-        if ((rc = tc::make_tmap_bf16(&tw0, Wb(f.w0x), 128, 192, 192, 128))) return rc;
         if ((rc = tc::make_tmap_bf16(&tw1, Wb(f.w1x), 512, 64, 64, 64))) return rc;
         static tc::PerDeviceFlag attr_set;
         if (!attr_set.test()) {
@@ -539,12 +541,12 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
         }
         tc::FrontParams fp;
         fp.scale0 = Pf(L.conv_scale[0]); fp.shift0 = Pf(L.conv_shift[0]); fp.scale1 = Pf(L.conv_scale[1]); fp.shift1 = Pf(L.conv_shift[1]);
-        fp.act1_hi = Hb(w.act1_hi); fp.act1_lo = Hb(w.act1_lo); fp.B = B; fp.trace = g_enc_trace;
+        fp.act1_hi = Hb(w.act1_hi); fp.act1_lo = Hb(w.act1_lo); fp.B = B; fp.trace = g_enc_trace; fp.w0u = reinterpret_cast<const uint8_t*>(Wb(f.w0x));
         const int grid = 2 * B < tc::num_sms() ? 2 * B : tc::num_sms();
         if (x_dtype == PMG_F32)
-            PMG_CUDA_OK(tc::launch_pdl(tc::front_kernel<2>, dim3(grid), dim3(tc::FRONT_THREADS), tc::FRONT_SMEM, st, tx, txl, tw0, tw1, fp), "front_kernel");
+            PMG_CUDA_OK(tc::launch_pdl(tc::front_kernel<2>, dim3(grid), dim3(tc::FRONT_THREADS), tc::FRONT_SMEM, st, tx, txl, tw1, fp), "front_kernel");
         else
-            PMG_CUDA_OK(tc::launch_pdl(tc::front_kernel<1>, dim3(grid), dim3(tc::FRONT_THREADS), tc::FRONT_SMEM, st, tx, txl, tw0, tw1, fp), "front_kernel");
+            PMG_CUDA_OK(tc::launch_pdl(tc::front_kernel<1>, dim3(grid), dim3(tc::FRONT_THREADS), tc::FRONT_SMEM, st, tx, txl, tw1, fp), "front_kernel");
         PMG_MARK(tm, "front_conv0_conv1");
     } else {
     // conv0 (:115-117) = im2col + GEMM [B·3136,48]×[48,32], BN+LeakyReLU epilogue → act0 planes == conv1's A

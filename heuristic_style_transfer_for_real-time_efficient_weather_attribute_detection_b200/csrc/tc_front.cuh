@@ -6,27 +6,30 @@
 // (rows 98..127 are don't-care).  For each of the 4 row offsets sy of conv1's 4×4 window:
 //
 //   * TMA (4-D tensor map over the NCHW bf16 image, dims x|py|y16|b·c, box 224×8×4×1, no swizzle) drops, per
-//     channel c, four slabs (kernel rows ky) of 8 whole image rows each = [98(+14) pixels × 16 input columns]
-//     straight into smem as rows of 32 bytes: no im2col, no register staging, 448-byte runs, ONE bulk tensor
-//     copy per (sy, c) step (the 8th image row is the neighbouring tile's / zero fill: don't-care MMA rows).
-//     The MMA reads the slab as a K-major SWIZZLE_32B operand.  The data are NOT swizzled, so for slab rows with
-//     bit 2 set (r & 4) the hardware's chunk XOR hands the MMA the two 16-byte halves (input columns 0-7 / 8-15)
-//     exchanged.  W0' is block-sparse over the column offset sx (4 columns each), so for those pixels the
-//     accumulator column group cg simply holds the conv0 output of column offset sx = cg ^ 2; epilogue 0
-//     (thread = pixel row) files it under the right K slice of conv1.  Nothing is moved twice.
-//   * conv0 as a GEMM over those slabs:  D0[pixel, (sx,co)] = Σ_{c,ky} A[pixel, 16 cols] · W0'[(sx,co), (c,ky,16 cols)]
-//     with W0' the conv0 weight laid out block-sparse over the 4 column offsets sx (each output column group sx
-//     only sees its own 4 of the 16 input columns).  12 MMAs (M128 N128 K16) per sy; the 4× zero padding is
-//     free: the tensor pipe is far from being the bottleneck of this layer.
+//     channel c, four slabs (kernel rows ky) of 8 whole image rows each straight into smem: no im2col, no register
+//     staging, 448-byte runs, ONE bulk tensor copy per (sy, c) step (the 8th image row is the neighbouring tile's /
+//     zero fill: don't-care MMA rows).  fp32 input arrives as two bf16 planes (hi, lo): 3 more steps per sy against
+//     the same weights (template parameter NPLANES).
+//   * conv0 as a GEMM whose M rows are the 16-BYTE UNITS of a slab (8 image columns = two conv0 pixels xp = 0, 1 of
+//     one conv1 pixel; 28 units per image row, 196 per slab = 2 M tiles): the slab IS a K-major operand in the
+//     no-swizzle core-matrix layout (8 units = 128 contiguous bytes, SBO = 128 B) and the two 16-byte K chunks of a
+//     K = 16 step are the same 8 columns in slabs ky and ky+1 (LBO = slab pitch):
+//         D0[unit, (xp, co)] = Σ_{c, ky} A[unit, 8 cols] · W0u[(xp, co), (c, ky, 8 cols)]
+//     W0u is block-sparse over xp (each pixel sees its 4 of the 8 columns): N = 64, 6 K steps × 2 M tiles = 12 MMAs
+//     (M128 N64 K16) per sy, 12 KB of weights.  (The first formulation used 32-byte rows = one conv1 pixel's 16
+//     columns, N = 128 block-sparse over 4 pixels: twice the MMA time, 48 KB of weights, 33 % more operand bytes.)
 //   * epilogue 0 (16 warps): TMEM → BN scale/shift → LeakyReLU → hi/lo bf16 split → written as conv1's A operand
-//     (K-major, 128-byte swizzle) for the K slice (sy, sx, c).
+//     (K-major, 128-byte swizzle): unit u ↔ conv1 pixel u>>1, K block u&1, 64-byte half xp.
 //   * conv1 accumulates that K slice:  D1[pixel, 64] += A1(hi) · W1[sy] + A1(lo) · W1[sy]   (16 MMAs, M128 N64 K16).
+//     A1 is DOUBLE-BUFFERED (sub-tile pitch 104 rows: the shared memory the smaller W0u freed), so epilogue 0 writes
+//     slice sy+1 while conv1 reads slice sy.
 //
 // After the 4th slice, epilogue 1 (its own 4 warps, D1 double-buffered) applies BN + LeakyReLU and stores act1 as hi/lo
 // bf16 planes [B·196, 64] while the other warps already work on the next tile.  conv0 and conv1 MMAs are issued by two
-// different threads, so neither stream is blocked behind a barrier wait of the other.
-// Both weight tensors stay resident in smem for the life of the CTA.  D0 is double-buffered in TMEM so the
-// conv0 MMAs of slice sy+1 run under epilogue 0 of slice sy.
+// different threads, so neither stream is blocked behind a barrier wait of the other.  Both weight tensors stay
+// resident in smem for the life of the CTA; D0 is double-buffered in TMEM.
+// What bounds it (role trace + tools/load_probe.py): shared-memory bandwidth — per slice the MMAs read 72 + 96 KB of
+// operands, epilogue 0 writes 50 KB, TMA lands 42 KB; the image stream alone runs at 6.4 TB/s with the same boxes.
 #pragma once
 
 #include "tc_prims.cuh"
@@ -34,19 +37,29 @@
 namespace tc {
 
 constexpr int FRONT_THREADS = 736;                 // warp 0 TMA, 1 conv0 MMA issuer, 2-17 epilogue 0 (lane quarter × 32-column group), 18 conv1 MMA issuer, 19-22 epilogue 1
-constexpr int FR_W0_BYTES = 3 * 128 * 128;         // 48 KB: 3 K-blocks × [128 rows × 128 B]
+constexpr int FR_W0_KSTEP = 2 * 64 * 16;           // one conv0 K step (c, ky pair): 2 K chunks × [64 rows × 16 B] as 8×16-byte core matrices
+constexpr int FR_W0_BYTES = 6 * FR_W0_KSTEP;       // 12 KB (the block-sparse [128 × 192] formulation took 48 KB)
 constexpr int FR_W1_BYTES = 8 * 64 * 128;          // 64 KB: (sy, kb) × [64 rows × 128 B]
 constexpr int FR_A0_SLOT = 3584;                   // one kernel row ky: 8 image rows × 448 B (7 used by the tile; 256-byte multiple)
 constexpr int FR_A0_STAGE = 4 * FR_A0_SLOT;        // one channel: 4 kernel rows = ONE TMA box
-constexpr int FR_A0_STAGES = 3;
-constexpr int FR_A1_BYTES = 2 * 2 * 128 * 128;     // 64 KB: [plane hi/lo][kb][128 rows × 128 B]
+constexpr int FR_A0_STAGES = 3;                    // (6 stages measured: no gain — with no compute the same boxes stream at 6.4 TB/s, 22 B/clk
+                                                   // per SM, tools/load_probe.py; inside the kernel the loads are slowed by the shared-memory
+                                                   // traffic of the MMAs and epilogue 0, not by ring depth)
+constexpr int FR_A1_SUB = 104 * 128;               // one [rows × 64 K] sub-tile of conv1's A operand: 98 real rows, pitch 13 × 1024 B; the
+                                                   // M = 128 MMA reads on into the next sub-tile — accumulator rows nobody looks at
+constexpr int FR_A1_BUF = 4 * FR_A1_SUB;           // [plane hi/lo][kb]
+constexpr int FR_A1_BYTES = 2 * FR_A1_BUF;         // double-buffered: epilogue 0 fills slice sy+1 while conv1 reads slice sy
 constexpr int FR_BOX_BYTES = FR_A0_STAGE;        // box 224 × 8 × 4 × 1 bf16 (out-of-range image rows are zero-filled but counted)
 constexpr int FR_OFF_W1 = FR_W0_BYTES;
 constexpr int FR_OFF_A0 = FR_OFF_W1 + FR_W1_BYTES;
 constexpr int FR_OFF_A1 = FR_OFF_A0 + FR_A0_STAGES * FR_A0_STAGE;
 constexpr int FR_OFF_BAR = FR_OFF_A1 + FR_A1_BYTES;
-constexpr int FR_OFF_PRM = FR_OFF_BAR + 256;
-constexpr int FRONT_SMEM = FR_OFF_PRM + (32 + 32 + 64 + 64) * 4 + 1024;
+constexpr int FR_OFF_PRM = FR_OFF_BAR + 384;
+// the M = 128 MMA on the last A1 sub-tile reads 3072 bytes past the end of A1: barriers and parameters live there, the rest is padding
+constexpr int FRONT_SMEM = FR_OFF_BAR + 3072 + 1024;
+static_assert(FR_OFF_PRM + (32 + 32 + 64 + 64) * 4 <= FR_OFF_BAR + 3072, "barriers + parameters must fit the over-read pad");
+static_assert(FRONT_SMEM <= 232448, "front kernel exceeds the 227 KB shared-memory limit");
+static_assert(FR_OFF_W1 % 1024 == 0 && FR_OFF_A0 % 1024 == 0 && FR_OFF_A1 % 1024 == 0, "SW128 tiles need 1024-byte alignment");
 
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1,
                                             int32_t c2, int32_t c3) {
@@ -65,12 +78,18 @@ __device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int32_t c0
                  : "memory");
 }
 
-// K-major operand whose rows are 32 bytes (16 bf16 = one UMMA K step), 32-byte swizzle, 8-row groups 256 B apart
-__device__ __forceinline__ uint64_t make_desc_k_sw32(uint32_t saddr) { return make_smem_desc(saddr, 16, 256, LAYOUT_SW32); }
+// K-major operand WITHOUT swizzle: 8 rows × 16 bytes core matrices (128 contiguous bytes); `sbo` = distance between
+// consecutive 8-row groups, `lbo` = distance between the two 16-byte K chunks of one K = 16 step
+__device__ __forceinline__ uint64_t make_desc_k_none(uint32_t saddr, uint32_t lbo, uint32_t sbo) { return make_smem_desc(saddr, lbo, sbo, LAYOUT_NONE); }
+__device__ __forceinline__ void fr_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 struct FrontParams {
     const float* scale0; const float* shift0;    // [32]  BN(eval) of conv0 folded
     const float* scale1; const float* shift1;    // [64]
+    const uint8_t* w0u;                          // conv0 weights in the core-matrix layout of pack_w0u_kernel (FR_W0_BYTES)
     __nv_bfloat16* act1_hi; __nv_bfloat16* act1_lo;   // [B·196, 64]
     int B;
     // template parameter NPLANES — 1: bf16 image; 2: fp32 image carried as bf16 hi + lo planes (tmXlo): conv0 is linear in the
@@ -82,7 +101,7 @@ struct FrontParams {
 template <int NPLANES>
 __global__ void __launch_bounds__(FRONT_THREADS, 1)
 front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXlo,
-             const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1, const FrontParams p) {
+             const __grid_constant__ CUtensorMap tmW1, const FrontParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sW0 = smem;
@@ -90,14 +109,12 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     uint8_t* sA0 = smem + FR_OFF_A0;
     uint8_t* sA1 = smem + FR_OFF_A1;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + FR_OFF_BAR);
-    uint64_t* a0_full = bars;            // [3]
-    uint64_t* a0_empty = bars + 3;       // [3]
+    uint64_t* a0_full = bars + 24;       // [FR_A0_STAGES]
+    uint64_t* a0_empty = bars + 32;      // [FR_A0_STAGES]
     uint64_t* d0_full = bars + 6;        // [2]
     uint64_t* d0_empty = bars + 8;       // [2]
-    uint64_t* a1_ready = bars + 10;      // hi plane of A1 written
-    uint64_t* a1_free = bars + 11;       // hi plane of A1 read by conv1
-    uint64_t* a1l_ready = bars + 18;     // same for the lo plane
-    uint64_t* a1l_free = bars + 19;
+    uint64_t* a1_ready = bars + 10;      // [2] A1 buffer written (both planes)
+    uint64_t* a1_free = bars + 18;       // [2] A1 buffer read by conv1
     uint64_t* d1_full = bars + 12;       // [2]
     uint64_t* d1_empty = bars + 14;      // [2]
     uint64_t* w_bar = bars + 16;
@@ -114,11 +131,11 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                                                    // in its step loop cost the bf16 path 9 % of the kernel (0.109 -> 0.118 ms)
 
     if (threadIdx.x == 0) {
-        prefetch_tmap(&tmX); prefetch_tmap(&tmXlo); prefetch_tmap(&tmW0); prefetch_tmap(&tmW1);
-        for (int i = 0; i < 3; ++i) { mbar_init(&a0_full[i], 1); mbar_init(&a0_empty[i], 1); }
+        prefetch_tmap(&tmX); prefetch_tmap(&tmXlo); prefetch_tmap(&tmW1);
+        for (int i = 0; i < FR_A0_STAGES; ++i) { mbar_init(&a0_full[i], 1); mbar_init(&a0_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&d0_full[i], 1); mbar_init(&d0_empty[i], 16); }
-        mbar_init(a1_ready, 16); mbar_init(a1_free, 1); mbar_init(w_bar, 1);
-        mbar_init(a1l_ready, 16); mbar_init(a1l_free, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&a1_ready[i], 16); mbar_init(&a1_free[i], 1); }
+        mbar_init(w_bar, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], 4); }
         fence_barrier_init();
     }
@@ -141,7 +158,7 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         // ===================== TMA producer =====================
         if (elect_one()) {      // one elected thread; elect.sync keeps the branch warp-uniform for ptxas (no per-MMA ELECT loops)
             mbar_expect_tx(w_bar, FR_W0_BYTES + FR_W1_BYTES);
-            for (int i = 0; i < 3; ++i) tma_load_2d(sW0 + i * 16384, &tmW0, w_bar, i * 64, 0);
+            fr_bulk_g2s(sW0, p.w0u, FR_W0_BYTES, w_bar);
             for (int i = 0; i < 8; ++i) tma_load_2d(sW1 + i * 8192, &tmW1, w_bar, 0, i * 64);
             pdl_wait();      // weights are constants; everything below may depend on earlier kernels
             constexpr uint32_t PF = 4 * nc;              // prefetch distance in (sy, c) steps = one tile
@@ -170,7 +187,7 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
     } else if (warp == 1) {
         // ===================== conv0 MMA issuer =====================
         if (elect_one()) {      // one elected thread; elect.sync keeps the branch warp-uniform for ptxas (no per-MMA ELECT loops)
-            constexpr uint32_t idesc0 = make_idesc_bf16(128, 128, 0, 0);
+            constexpr uint32_t idesc0 = make_idesc_bf16(128, 64, 0, 0);
             const uint32_t aW0 = smem_u32(sW0), aA0 = smem_u32(sA0);
             mbar_wait(w_bar, 0);
             uint32_t it = 0, g = 0, lt = 0;
@@ -186,12 +203,16 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                         mbar_wait(&a0_full[s], ph);
                         tc_fence_after();
                         if (c == nc - 1) FR_T(21 + 4 * sy);
+                        // K step = (channel, kernel-row pair): the two 16-byte K chunks of an M row are the same 8 image columns
+                        // in slabs ky and ky+1 (LBO = slab pitch); M tile t = 16-byte units 128t.. of the slab (SBO = 128 B)
+                        const uint32_t wj = aW0 + (c >= 3 ? c - 3 : c) * 2 * FR_W0_KSTEP;      // the lo plane meets the same weights as the hi plane
 #pragma unroll
-                        for (int ky = 0; ky < 4; ++ky) {
-                            const int kk = (c >= 3 ? c - 3 : c) * 4 + ky;     // the lo plane meets the same weights as the hi plane
-                            umma_bf16(tD0 + as * 128, make_desc_k_sw32(aA0 + s * FR_A0_STAGE + ky * FR_A0_SLOT),
-                                      make_desc_k_sw128(aW0 + (kk >> 2) * 16384 + (kk & 3) * 32), idesc0, (c > 0 || ky > 0) ? 1u : 0u);
-                        }
+                        for (int kp = 0; kp < 2; ++kp)
+#pragma unroll
+                            for (int t = 0; t < 2; ++t)
+                                umma_bf16(tD0 + as * 128 + t * 64,
+                                          make_desc_k_none(aA0 + s * FR_A0_STAGE + 2 * kp * FR_A0_SLOT + t * 2048, FR_A0_SLOT, 128),
+                                          make_desc_k_none(wj + kp * FR_W0_KSTEP, 1024, 128), idesc0, (c > 0 || kp > 0) ? 1u : 0u);
                         umma_commit(&a0_empty[s]);
                     }
                     umma_commit(&d0_full[as]);
@@ -210,28 +231,19 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
                 const uint32_t db = lt & 1;
                 for (uint32_t sy = 0; sy < 4; ++sy, ++g) {
-                    mbar_wait(a1_ready, g & 1);
+                    const uint32_t ab = g & 1;
+                    mbar_wait(&a1_ready[ab], (g >> 1) & 1);
                     if (sy == 0) mbar_wait(&d1_empty[db], ((lt >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    // the hi plane first, then the lo plane, each with its own ready / free pair: epilogue 0 refills the hi
-                    // plane for the next slice while the lo MMAs of this one run (and vice versa), so the single A1 buffer
-                    // no longer serialises "write A1 → 16 MMAs → write A1"
 #pragma unroll
-                    for (int kb = 0; kb < 2; ++kb)
+                    for (int plane = 0; plane < 2; ++plane)
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_bf16(tD1 + 64 * db, make_desc_k_sw128(aA1 + kb * 16384 + k * 32),
-                                      make_desc_k_sw128(aW1 + (sy * 2 + kb) * 8192 + k * 32), idesc1, (sy > 0 || kb > 0 || k > 0) ? 1u : 0u);
-                    umma_commit(a1_free);
-                    mbar_wait(a1l_ready, g & 1);
-                    tc_fence_after();
+                        for (int kb = 0; kb < 2; ++kb)
 #pragma unroll
-                    for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            umma_bf16(tD1 + 64 * db, make_desc_k_sw128(aA1 + 32768 + kb * 16384 + k * 32),
-                                      make_desc_k_sw128(aW1 + (sy * 2 + kb) * 8192 + k * 32), idesc1, 1u);
-                    umma_commit(a1l_free);
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(tD1 + 64 * db, make_desc_k_sw128(aA1 + ab * FR_A1_BUF + (plane * 2 + kb) * FR_A1_SUB + k * 32),
+                                          make_desc_k_sw128(aW1 + (sy * 2 + kb) * 8192 + k * 32), idesc1, (sy > 0 || plane > 0 || kb > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&a1_free[ab]);
                     FR_T(23 + 4 * sy);
                 }
                 umma_commit(&d1_full[db]);
@@ -283,13 +295,17 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
         tc_fence_before();
     } else if (warp >= 2) {
         // ===================== epilogue 0 warps =====================
-        // 16 warps: TMEM lane quarter q = warp % 4, 32-column group cg = (warp-2)/4 = conv0 column offset sx
+        // 16 warps: TMEM lane quarter q = warp % 4; (warp-2)/4 = 2·t + xp: accumulator tile t (units 128t..128t+127) and pixel xp
+        // of the unit.  D0 row = one 16-byte unit u of the slab = image columns 8·(u%28).. of slab row u/28 = conv0 pixels
+        // (sx = 2h, 2h+1) of conv1 pixel p = u >> 1 with h = u & 1; D0 column = xp·32 + co.
         const int q = warp & 3;
-        const int cg = (warp - 2) >> 2;               // D0 columns cg*32 .. +31
-        const int m = q * 32 + lane;                  // tile row = conv1 pixel index inside the tile
-        const int sx = cg ^ ((m >> 1) & 2);           // conv0 column offset those columns hold for this row (header: half swap)
+        const int tcol = (warp - 2) >> 2;             // 0..3
+        const int t = tcol >> 1, xp = tcol & 1;
+        const int u = t * 128 + q * 32 + lane;        // unit index inside the slab
+        const bool live = u < 196;                    // 7 image rows × 28 units; the rest are don't-care MMA rows
+        const int pix = u >> 1, h = u & 1;            // conv1 pixel (A1 row), K block of conv1's operand (sx >> 1 = h)
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-        uint8_t* a1row = sA1 + (sx >> 1) * 16384 + m * 128;   // conv1 K slice (sy, sx, c): K block sx/2, 64-byte half sx%2
+        uint8_t* a1row = sA1 + h * FR_A1_SUB + pix * 128;   // conv1 K slice (sy, sx = 2h + xp, c): 64-byte half xp of the row
         uint32_t g = 0, lt = 0;
         pdl_wait();          // act1 planes are still being read by the previous forward's conv2 until it completes
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
@@ -299,7 +315,7 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                 tc_fence_after();
                 if (warp == 2 && lane == 0) FR_T(40 + 4 * sy);
                 uint32_t r[32], H[16], L[16];
-                tmem_ld_32x32b_x32(tD0 + as * 128 + lane_addr + (uint32_t)(cg * 32), r);
+                tmem_ld_32x32b_x32(tD0 + as * 128 + lane_addr + (uint32_t)(tcol * 32), r);
                 tmem_ld_wait();
                 tc_fence_before();
                 __syncwarp();
@@ -312,25 +328,21 @@ front_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CU
                     bn_lrelu_split_x2(r[4 * j + 2], r[4 * j + 3], sc.z, sc.w, sh.z, sh.w, H[2 * j + 1], L[2 * j + 1]);
                 }
                 if (warp == 2 && lane == 0) FR_T(41 + 4 * sy);
-                if (g > 0) mbar_wait(a1_free, (g - 1) & 1);        // conv1's hi MMAs of the previous slice have read the hi plane
+                const uint32_t ab = g & 1;
+                mbar_wait(&a1_free[ab], ((g >> 1) & 1) ^ 1);        // conv1 of slice g-2 has read this A1 buffer
                 if (warp == 2 && lane == 0) FR_T(42 + 4 * sy);
+                if (live) {
+                    uint8_t* dst = a1row + ab * FR_A1_BUF;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int sw = (((cg & 1) * 4 + j) ^ (m & 7)) << 4;
-                    *reinterpret_cast<uint4*>(a1row + sw) = make_uint4(H[4 * j], H[4 * j + 1], H[4 * j + 2], H[4 * j + 3]);
+                    for (int j = 0; j < 4; ++j) {
+                        const int sw = ((xp * 4 + j) ^ (pix & 7)) << 4;
+                        *reinterpret_cast<uint4*>(dst + sw) = make_uint4(H[4 * j], H[4 * j + 1], H[4 * j + 2], H[4 * j + 3]);
+                        *reinterpret_cast<uint4*>(dst + 2 * FR_A1_SUB + sw) = make_uint4(L[4 * j], L[4 * j + 1], L[4 * j + 2], L[4 * j + 3]);
+                    }
                 }
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(a1_ready);
-                if (g > 0) mbar_wait(a1l_free, (g - 1) & 1);       // ... and the lo MMAs the lo plane
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int sw = (((cg & 1) * 4 + j) ^ (m & 7)) << 4;
-                    *reinterpret_cast<uint4*>(a1row + 32768 + sw) = make_uint4(L[4 * j], L[4 * j + 1], L[4 * j + 2], L[4 * j + 3]);
-                }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(a1l_ready);
+                if (lane == 0) mbar_arrive(&a1_ready[ab]);
                 if (warp == 2 && lane == 0) FR_T(43 + 4 * sy);
             }
         }

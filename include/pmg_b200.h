@@ -218,6 +218,11 @@ void pmg_debug_set_trace(void* dev_buf_512_i64);
  * operand of the MMA read from tensor memory. */
 int pmg_debug_tmem_a(const void* A, const void* B, float* D, pmg_stream_t stream);
 
+/* Hardware probe (tools/load_probe.py): device time of streaming a (B,3,224,224) bf16 batch into shared memory with one CTA per
+ * SM and `stages` 14,336-byte loads in flight; mode 0 = the front kernel's 4-D tensor-map box, 1 = contiguous cp.async.bulk,
+ * 2 = 2-D tensor map of 32 consecutive rows, 3 = mode 0 without the L2 evict-first hint.  ms_out is a HOST pointer. */
+int pmg_debug_load_probe(const void* x, int B, int mode, int stages, float* ms_out, pmg_stream_t stream);
+
 /* Same contract for N = 192 on CTA PAIRS (tcgen05 cta_group::2, clusters of 2): out[s][M,192] split-K partial sums
  * (s < effective splits, always written as partials, also for splits == 1). */
 int pmg_tc_gemm2(const void* a_hi, const void* a_lo, const void* b, int M, int K, int splits, float* out, pmg_stream_t stream);
