@@ -161,6 +161,15 @@ int pmg_style_grams(const pmg_config* cfg, const void* packed, const void* x, in
  * mean3 / std3 are HOST pointers to 3 floats. */
 int pmg_preprocess_u8(const void* src, int layout, int B, int H, int W, const float* mean3, const float* std3,
                       int out_dtype, void* dst, pmg_stream_t stream);
+/* transforms.Resize(size) + transforms.CenterCrop(crop) (utils/datasets_utils.py:209-210) on decoded uint8 HWC images
+ * src (B,H,W,3), bit-identical to the reference's CPU transform: output size / crop offsets as torchvision, pixel values as
+ * Pillow's 8-bit BILINEAR resample (22-bit fixed-point taps, horizontal pass then vertical pass, each rounded to uint8).
+ * out_mode 0: dst (B,crop,crop,3) uint8 HWC;  1 / 2: ToTensor + Normalize fused, dst (B,3,crop,crop) bf16 / fp32 NCHW (mean3,
+ * std3 HOST pointers, may be NULL for out_mode 0).  scratch: pmg_resize_scratch_bytes() device bytes (tap tables).
+ * Returns PMG_ERR_UNSUPPORTED when the resized image is smaller than the crop (CenterCrop would pad). */
+size_t pmg_resize_scratch_bytes(int H, int W, int size, int crop);
+int pmg_resize_crop_u8(const void* src, int B, int H, int W, int size, int crop, const float* mean3, const float* std3,
+                       int out_mode, void* dst, void* scratch, size_t scratch_bytes, pmg_stream_t stream);
 /* Per-task softmax / max / arg-max / threshold of Functions/PMG_evaluation.py:144-146 on the packed logits
  * (B, sum(ncls)): probs (B, sum(ncls)), preds (B, n_tasks) int32 with -1 where max prob < prob_threshold,
  * max_probs (B, n_tasks); any output may be NULL (not all).  ncls is a HOST array. */

@@ -61,6 +61,35 @@ def test_preprocess_kernel_bit_exact(shape):
         assert np.array_equal(got16, po.to_bf16_rne(ref)), layout
 
 
+RESIZE_SIZES = [(300, 340), (256, 256), (480, 640), (1080, 1920), (257, 511), (1000, 300), (224, 224), (260, 900), (333, 257)]
+
+
+@pytest.mark.parametrize("h,w", RESIZE_SIZES)
+def test_resize_crop_oracle_is_bit_exact_vs_pillow_and_torchvision(h, w):
+    """The oracle restates Pillow's Resample.c + torchvision's size / crop rules: pin it to the libraries themselves."""
+    from PIL import Image
+    from torchvision import transforms
+    x = np.random.default_rng(h * 7 + w).integers(0, 256, (1, h, w, 3), dtype=np.uint8)
+    ref = np.asarray(transforms.Compose([transforms.Resize(256), transforms.CenterCrop(224)])(Image.fromarray(x[0])))
+    assert np.array_equal(po.resize_center_crop_u8(x)[0], ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("h,w", RESIZE_SIZES)
+def test_resize_crop_kernel_is_bit_exact(h, w):
+    """CUDA Resize(256) + CenterCrop(224) == oracle (== Pillow) byte for byte; fused with ToTensor + Normalize it equals
+    build_default_transform (utils/datasets_utils.py:205-215) bit for bit in fp32."""
+    from pmg_b200 import prepost
+    x = np.random.default_rng(h * 7 + w).integers(0, 256, (3, h, w, 3), dtype=np.uint8)
+    ref = po.resize_center_crop_u8(x)
+    xd = torch.from_numpy(x).cuda()
+    assert np.array_equal(prepost.resize_center_crop_u8(xd).cpu().numpy(), ref)
+    f32 = prepost.resize_center_crop_u8(xd, out_dtype=torch.float32).cpu().numpy()
+    assert np.array_equal(f32, po.preprocess_u8(ref))
+    b16 = prepost.resize_center_crop_u8(xd, out_dtype=torch.bfloat16).float().cpu().numpy()
+    assert np.array_equal(b16, po.to_bf16_rne(po.preprocess_u8(ref)))
+
+
 @pytest.mark.gpu
 def test_postprocess_kernel():
     from pmg_b200 import prepost
