@@ -205,7 +205,8 @@ __global__ void __launch_bounds__(256) resize_crop_kernel(const ResizeArgs a) {
     for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
         const int x = (int)(t % a.crop), y = (int)((t / a.crop) % a.crop);
         const size_t b = t / ((size_t)a.crop * a.crop);
-        const int x0 = a.bh[2 * x], nx = a.bh[2 * x + 1], y0 = a.bv[2 * y], ny = a.bv[2 * y + 1];
+        // an axis that keeps its size is not resampled (Pillow skips the pass): its source index is the tap window's first
+        const int x0 = a.bh[2 * x], nx = a.bh[2 * x + 1], y0 = a.bv[2 * y], ny = a.skip_v ? 1 : a.bv[2 * y + 1];
         const int* kx = a.kh + (size_t)x * a.ksh;
         const int* ky = a.kv + (size_t)y * a.ksv;
         const unsigned char* img = a.src + b * (size_t)a.H * a.W * 3;
