@@ -20,6 +20,7 @@ class PmgConfig(C.Structure):
         ("input_nc", C.c_int32), ("ndf", C.c_int32), ("patch_size", C.c_int32), ("patch_div", C.c_int32),
         ("gram_channels", C.c_int32), ("d_model", C.c_int32), ("transformer_layers", C.c_int32),
         ("transformer_heads", C.c_int32), ("n_tasks", C.c_int32), ("ncls", C.c_int32 * PMG_MAX_TASKS),
+        ("norm", C.c_int32), ("use_channel_attention", C.c_int32),
     ]
 
 
@@ -122,7 +123,7 @@ def _load() -> C.CDLL:
     lib.pm_forward.argtypes = [pcfg, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p]
     lib.pm_forward.restype = C.c_int
-    if lib.pmg_abi_version() != 1:
+    if lib.pmg_abi_version() != 2:
         raise ImportError("libpmg_b200.so ABI version mismatch — rebuild")
     return lib
 
@@ -149,8 +150,11 @@ def make_pm_config(input_nc, ndf, patch_size, ncls_list, attn_tau, ablate) -> Pm
     return cfg
 
 
+PMG_NORM = {"batch": 0, "instance": 1}
+
+
 def make_config(input_nc, ndf, patch_size, patch_div, gram_channels, d_model, transformer_layers,
-                transformer_heads, ncls_list) -> PmgConfig:
+                transformer_heads, ncls_list, norm="batch", use_channel_attention=False) -> PmgConfig:
     if len(ncls_list) > PMG_MAX_TASKS:
         raise PmgError(f"at most {PMG_MAX_TASKS} tasks are supported")
     cfg = PmgConfig()
@@ -160,4 +164,6 @@ def make_config(input_nc, ndf, patch_size, patch_div, gram_channels, d_model, tr
     cfg.n_tasks = len(ncls_list)
     for i, n in enumerate(ncls_list):
         cfg.ncls[i] = int(n)
+    cfg.norm = PMG_NORM[norm] if isinstance(norm, str) else int(norm)
+    cfg.use_channel_attention = int(bool(use_channel_attention))
     return cfg

@@ -60,7 +60,7 @@ const char* pmg_last_cuda_error(void) { return g_cuda_err; }
 int pmg_param_count(const pmg_config* cfg) {
     const Plan p = make_plan(cfg);
     if (!p.ok) return -1;
-    return 5 * p.n_layers + 3 + 12 * p.nl + 3 * p.ntask;
+    return (p.norm == PMG_NORM_BATCH ? 5 : 3) * p.n_layers + (p.se ? 2 : 0) + 3 + 12 * p.nl + 3 * p.ntask;
 }
 
 size_t pmg_packed_bytes(const pmg_config* cfg) {

@@ -25,6 +25,8 @@ struct Plan {
     ConvLayer layer[PMG_MAX_BACKBONE];
     int C = 0;                    // channels after the final 1x1 (self.C)
     int Cr = 0, d = 0, nl = 0, nh = 0, ntask = 0, ncls_total = 0, pdiv = 0;
+    int norm = PMG_NORM_BATCH;    // models_PMG.py:100-105
+    int se = 0, se_hidden = 0;    // SEBlock (models_PMG.py:15-30): C -> max(1, C/16) -> C
     int cls_off[PMG_MAX_TASKS + 1];
     bool ok = false;
 };
@@ -44,6 +46,10 @@ inline Plan make_plan(const pmg_config* c) {
     }
     p.layer[p.n_layers++] = {cin, nf, 1};
     p.C = nf;
+    if (c->norm != PMG_NORM_BATCH && c->norm != PMG_NORM_INSTANCE) return p;
+    p.norm = c->norm;
+    p.se = c->use_channel_attention ? 1 : 0;
+    p.se_hidden = p.se ? (p.C / 16 > 1 ? p.C / 16 : 1) : 0;
     p.Cr = c->gram_channels; p.d = c->d_model; p.nl = c->transformer_layers; p.nh = c->transformer_heads;
     p.ntask = c->n_tasks; p.pdiv = c->patch_div;
     int off = 0;
@@ -96,6 +102,7 @@ struct TfLayerOff {
 struct PackedLayout {
     size_t conv_w[PMG_MAX_BACKBONE];   // Wt [K][Cout] fp32; K order (c,ky,kx) for layer 0, (ky,kx,c) after
     size_t conv_scale[PMG_MAX_BACKBONE], conv_shift[PMG_MAX_BACKBONE];
+    size_t se_w1, se_w2;               // SEBlock fc.0.weight [hid][C], fc.2.weight [C][hid] (torch layouts)
     size_t chan_w;                     // Wt [C][Cr]
     size_t tok_w, tok_b;               // Wt [Cr*Cr][d], b [d]
     TfLayerOff tf[8];
@@ -117,6 +124,7 @@ inline PackedLayout make_layout(const Plan& p) {
         L.conv_scale[l] = take(p.layer[l].cout);
         L.conv_shift[l] = take(p.layer[l].cout);
     }
+    if (p.se) { L.se_w1 = take((size_t)p.se_hidden * p.C); L.se_w2 = take((size_t)p.C * p.se_hidden); }
     L.chan_w = take((size_t)p.C * p.Cr);
     L.tok_w = take((size_t)p.Cr * p.Cr * p.d);
     L.tok_b = take(p.d);

@@ -62,7 +62,7 @@ static FastW fast_w(const Plan& p) {
 }
 
 static bool is_committed(const Plan& p) {
-    return p.ok && p.n_layers == 3 && p.layer[0].cin == 3 && p.layer[0].cout == 32 && p.layer[0].k == 4 &&
+    return p.ok && p.norm == PMG_NORM_BATCH && !p.se && p.n_layers == 3 && p.layer[0].cin == 3 && p.layer[0].cout == 32 && p.layer[0].k == 4 &&
            p.layer[1].cout == 64 && p.layer[1].k == 4 && p.layer[2].cout == 128 && p.layer[2].k == 1 && p.Cr == 96 &&
            p.d == 192 && p.nh == 4 && p.pdiv == 3 && p.nl <= 8 && p.ntask + p.ncls_total <= 64;
 }

@@ -51,9 +51,20 @@ int pack_generic(const Plan& p, const PackedLayout& L, const float* const* prm, 
         const int KK = c.k * c.k;
         pack_wt_kernel<<<grid_for((size_t)c.cin * KK * c.cout), 256, 0, st>>>(prm[i], F(L.conv_w[l]), c.cout, c.cin, KK,
                                                                              (l > 0 && c.k == 4) ? 1 : 0);
-        bn_fold_kernel<<<(c.cout + 127) / 128, 128, 0, st>>>(prm[i + 1], prm[i + 2], prm[i + 3], prm[i + 4],
-                                                             F(L.conv_scale[l]), F(L.conv_shift[l]), c.cout, kBnEps);
-        i += 5;
+        if (p.norm == PMG_NORM_BATCH) {
+            bn_fold_kernel<<<(c.cout + 127) / 128, 128, 0, st>>>(prm[i + 1], prm[i + 2], prm[i + 3], prm[i + 4],
+                                                                 F(L.conv_scale[l]), F(L.conv_shift[l]), c.cout, kBnEps);
+            i += 5;
+        } else {                                  // instance / group norm: per-sample statistics at run time; keep gamma, beta
+            copy_f32_kernel<<<grid_for(c.cout), 256, 0, st>>>(prm[i + 1], F(L.conv_scale[l]), c.cout);
+            copy_f32_kernel<<<grid_for(c.cout), 256, 0, st>>>(prm[i + 2], F(L.conv_shift[l]), c.cout);
+            i += 3;
+        }
+    }
+    if (p.se) {
+        copy_f32_kernel<<<grid_for((size_t)p.se_hidden * p.C), 256, 0, st>>>(prm[i], F(L.se_w1), (size_t)p.se_hidden * p.C);
+        copy_f32_kernel<<<grid_for((size_t)p.se_hidden * p.C), 256, 0, st>>>(prm[i + 1], F(L.se_w2), (size_t)p.se_hidden * p.C);
+        i += 2;
     }
     pack_wt_kernel<<<grid_for((size_t)p.C * p.Cr), 256, 0, st>>>(prm[i], F(L.chan_w), p.Cr, p.C, 1, 0); i += 1;
     pack_wt_kernel<<<grid_for((size_t)p.Cr * p.Cr * p.d), 256, 0, st>>>(prm[i], F(L.tok_w), p.d, p.Cr * p.Cr, 1, 0); i += 1;
@@ -412,12 +423,79 @@ static GenericWs generic_ws(const Plan& p, const Shape& s, int B) {
 
 size_t generic_workspace_bytes(const Plan& p, const Shape& s, int B) { return generic_ws(p, s, B).total; }
 
-int generic_launch_count(const Plan& p) { return p.n_layers + 3 + 7 * p.nl + 1; }
+int generic_launch_count(const Plan& p) {
+    return p.n_layers * (p.norm == PMG_NORM_BATCH ? 1 : 2) + (p.se ? 1 : 0) + 3 + 7 * p.nl + 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// norm = "instance" (models_PMG.py:100-101, InstanceNorm2d(affine=True)): per-sample statistics over HW (x cg channels;
+// cg = 1 here), biased variance, eps 1e-5, per-channel affine, then LeakyReLU(0.2); in place on the pixel-major
+// (B, HW, C) fp32 conv output.  One block per (sample, channel group).  Two-pass statistics
+// (mean, then centred sum of squares) in fp32 with a block reduction — a correctness path, not a tuned one.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i];
+    return t;
+}
+
+__global__ void __launch_bounds__(256) sample_norm_lrelu_kernel(float* __restrict__ x, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, int HW, int C, int cg) {
+    __shared__ float red[8];
+    const int groups = C / cg, b = blockIdx.x / groups, g = blockIdx.x % groups;
+    float* base = x + (size_t)b * HW * C + g * cg;
+    const int n = HW * cg;
+    float s = 0.f;
+    for (int e = threadIdx.x; e < n; e += 256) s += base[(size_t)(e / cg) * C + e % cg];
+    const float mean = block_sum_256(s, red) / (float)n;
+    float q = 0.f;
+    for (int e = threadIdx.x; e < n; e += 256) { const float d = base[(size_t)(e / cg) * C + e % cg] - mean; q = fmaf(d, d, q); }
+    const float rstd = 1.f / sqrtf(block_sum_256(q, red) / (float)n + 1e-5f);
+    for (int e = threadIdx.x; e < n; e += 256) {
+        const int c = e % cg;
+        float* px = base + (size_t)(e / cg) * C + c;
+        const float v = (*px - mean) * rstd * gamma[g * cg + c] + beta[g * cg + c];
+        *px = v >= 0.f ? v : v * kLeaky;
+    }
+}
+
+// SEBlock (models_PMG.py:15-30): w = sigmoid(W2 · relu(W1 · mean_hw(x)));  x *= w.  One block per sample.
+__global__ void __launch_bounds__(256) se_scale_kernel(float* __restrict__ x, const float* __restrict__ w1,
+                                                       const float* __restrict__ w2, int HW, int C, int hid) {
+    extern __shared__ float s_se[];          // pooled[C] | hidden[hid] | gate[C]
+    float* pooled = s_se; float* hidden = s_se + C; float* gate = hidden + hid;
+    float* base = x + (size_t)blockIdx.x * HW * C;
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float s = 0.f;
+        for (int p = 0; p < HW; ++p) s += base[(size_t)p * C + c];
+        pooled[c] = s / (float)HW;
+    }
+    __syncthreads();
+    for (int h = threadIdx.x; h < hid; h += 256) {
+        float s = 0.f;
+        for (int c = 0; c < C; ++c) s = fmaf(w1[(size_t)h * C + c], pooled[c], s);
+        hidden[h] = fmaxf(s, 0.f);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += 256) {
+        float s = 0.f;
+        for (int h = 0; h < hid; ++h) s = fmaf(w2[(size_t)c * hid + h], hidden[h], s);
+        gate[c] = 1.f / (1.f + expf(-s));
+    }
+    __syncthreads();
+    for (size_t e = threadIdx.x; e < (size_t)HW * C; e += 256) base[e] *= gate[e % C];
+}
 
 // feature_extractor (models_PMG.py:113-128,178): conv k4 s4 / 1x1 as GEMMs with the folded eval-BatchNorm + LeakyReLU
 // epilogue; *out = the last activation, pixel-major (B, Hc, Wc, C) fp32, inside the workspace
 static int run_backbone(const Plan& p, const Shape& s, const PackedLayout& L, const char* packed, const void* x, int x_dtype,
-                        int B, char* ws, const GenericWs& w, cudaStream_t st, StageTimer* tm, const float** out) {
+                        int B, char* ws, const GenericWs& w, cudaStream_t st, StageTimer* tm, const float** out, bool apply_se) {
     auto F = [&](size_t off) { return reinterpret_cast<float*>(ws + off); };
     auto P = [&](size_t off) { return reinterpret_cast<const float*>(packed + off); };
     static const char* kConvName[PMG_MAX_BACKBONE] = {"conv0", "conv1", "conv2", "conv3", "conv4", "conv5", "conv6", "conv7"};
@@ -426,16 +504,33 @@ static int run_backbone(const Plan& p, const Shape& s, const PackedLayout& L, co
     for (int l = 0; l < p.n_layers; ++l) {
         const ConvLayer& c = p.layer[l];
         GemmArgs g{};
-        g.Wt = P(L.conv_w[l]); g.scale = P(L.conv_scale[l]); g.shift = P(L.conv_shift[l]); g.resid = nullptr;
+        const bool folded = p.norm == PMG_NORM_BATCH;
+        g.Wt = P(L.conv_w[l]); g.scale = folded ? P(L.conv_scale[l]) : nullptr; g.shift = folded ? P(L.conv_shift[l]) : nullptr;
+        g.resid = nullptr;
         g.C = F(w.act[l & 1]);
-        g.M = B * s.h[l + 1] * s.w[l + 1]; g.N = c.cout; g.K = c.cin * c.k * c.k; g.ldc = c.cout; g.act = ACT_LEAKY;
+        g.M = B * s.h[l + 1] * s.w[l + 1]; g.N = c.cout; g.K = c.cin * c.k * c.k; g.ldc = c.cout; g.act = folded ? ACT_LEAKY : ACT_NONE;
         g.Cin = c.cin; g.Hi = s.h[l]; g.Wi = s.w[l]; g.Ho = s.h[l + 1]; g.Wo = s.w[l + 1];
         int mode;
         if (l == 0) { g.A = x; mode = x_dtype == PMG_BF16 ? A_S2D_NCHW_BF16 : A_S2D_NCHW_F32; }
         else { g.A = cur; g.lda = c.cin; mode = c.k == 4 ? A_S2D_NHWC : A_PLAIN; }
         if ((rc = launch_sgemm(mode, g, st))) return rc;
+        if (!folded) {
+            const int cg = 1;
+            sample_norm_lrelu_kernel<<<B * (c.cout / cg), 256, 0, st>>>(g.C, P(L.conv_scale[l]), P(L.conv_shift[l]),
+                                                                        s.h[l + 1] * s.w[l + 1], c.cout, cg);
+            PMG_LAUNCH_OK("sample_norm");
+        }
         PMG_MARK(tm, kConvName[l]);
         cur = g.C;
+    }
+    if (p.se) {                                              // models_PMG.py:179 (style-transfer export: feature_extractor only)
+        const size_t smem = (size_t)(2 * p.C + p.se_hidden) * sizeof(float);
+        if (smem > 48 * 1024) return PMG_ERR_UNSUPPORTED;
+        if (apply_se) {
+            se_scale_kernel<<<B, 256, smem, st>>>(const_cast<float*>(cur), P(L.se_w1), P(L.se_w2), s.Hc * s.Wc, p.C, p.se_hidden);
+            PMG_LAUNCH_OK("se_scale");
+            PMG_MARK(tm, "se");
+        }
     }
     *out = cur;
     return PMG_OK;
@@ -451,7 +546,7 @@ int style_grams_forward(const Plan& p, const Shape& s, const PackedLayout& L, co
     const GenericWs w = generic_ws(p, s, B);
     const float* feats = nullptr;
     int rc;
-    if ((rc = run_backbone(p, s, L, packed, x, x_dtype, B, ws, w, st, nullptr, &feats))) return rc;
+    if ((rc = run_backbone(p, s, L, packed, x, x_dtype, B, ws, w, st, nullptr, &feats, false))) return rc;
     const int ph = s.Hc / p.pdiv, pw = s.Wc / p.pdiv;
     if (ph < 1 || pw < 1) return PMG_ERR_BAD_SHAPE;
     const int npy = s.Hc / ph, npx = s.Wc / pw;
@@ -475,7 +570,7 @@ int generic_forward(const Plan& p, const Shape& s, const PackedLayout& L, const 
     PMG_MARK(tm, "start");
     // backbone (models_PMG.py:178)
     const float* cur = nullptr;
-    if ((rc = run_backbone(p, s, L, packed, x, x_dtype, B, ws, w, st, tm, &cur))) return rc;
+    if ((rc = run_backbone(p, s, L, packed, x, x_dtype, B, ws, w, st, tm, &cur, true))) return rc;
     // chan_proj (:182)
     {
         GemmArgs g{};

@@ -28,14 +28,18 @@ __all__ = ["MultiTaskPatchGANGramModelNonOverlapV2", "TaskAttentionPooling", "Tr
 
 
 class SEBlock(nn.Module):
-    """Channel attention of the reference (models_PMG.py:15-30).  Off-path in every committed config
-    (``use_channel_attention: false``); kept only so the name resolves — the kernels do not implement it."""
+    """Parameter holder of the reference's channel attention (models_PMG.py:15-30: global average pool → Linear(C, C/16,
+    no bias) → ReLU → Linear(C/16, C, no bias) → Sigmoid → x·w); same state_dict keys (``se.fc.0.weight``,
+    ``se.fc.2.weight``).  The arithmetic runs in the CUDA library (shape-generic fp32 kernels; off in the committed config)."""
 
     def __init__(self, C: int, r: int = 16):
         super().__init__()
-        raise NotImplementedError(
-            "use_channel_attention=True (SEBlock) is not implemented by the B200 kernels; the committed "
-            "hyperparameters_PMG.json sets it to false")
+        self.pool = nn.AdaptiveAvgPool2d(1)
+        self.fc = nn.Sequential(nn.Linear(C, max(1, C // r), bias=False), nn.ReLU(True),
+                                nn.Linear(max(1, C // r), C, bias=False), nn.Sigmoid())
+
+    def forward(self, x):  # pragma: no cover - parameter holder
+        raise RuntimeError("SEBlock is fused into the PMG CUDA forward; call the model instead")
 
 
 class TaskAttentionPooling(nn.Module):
@@ -101,10 +105,6 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
         transformer_heads: int = 4,
     ):
         super().__init__()
-        if norm in ("instance", "group"):
-            raise NotImplementedError(
-                f"norm={norm!r}: the B200 kernels fold BatchNorm2d(eval) into the conv epilogue; "
-                "instance/group norm are not implemented (committed config uses 'batch')")
         self.num_classes_per_task = num_classes_per_task or {}
         if not self.num_classes_per_task:
             raise ValueError("num_classes_per_task must name at least one task")
@@ -113,10 +113,20 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
         self.use_token_attention = use_token_attention
         self.gram_channels = gram_channels
 
+        # models_PMG.py:100-105: "instance" → InstanceNorm2d(affine=True); "group" → partial(nn.GroupNorm, num_groups=32) called
+        # as norm_layer(num_filters), which binds num_groups twice: the reference raises TypeError at construction, and so does
+        # this module; anything else means BatchNorm2d
+        if norm == "group":
+            raise TypeError("GroupNorm.__init__() got multiple values for argument 'num_groups' (norm='group' cannot be "
+                            "constructed in the reference either: Models/models_PMG.py:102-103,116)")
+        self._norm = "instance" if norm == "instance" else "batch"
         stack = []
         for cin, cout, k in _backbone_plan(input_nc, ndf, patch_size):
             stack.append(nn.Conv2d(cin, cout, kernel_size=k, stride=k, padding=0, bias=False))
-            stack.append(nn.BatchNorm2d(cout, affine=True))
+            if self._norm == "instance":
+                stack.append(nn.InstanceNorm2d(cout, affine=True))
+            else:
+                stack.append(nn.BatchNorm2d(cout, affine=True))
             stack.append(nn.LeakyReLU(0.2, inplace=True))
         self.feature_extractor = nn.Sequential(*stack)
         self.C = stack[-3].out_channels
@@ -134,7 +144,8 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
 
         # ---- kernel-side state: never part of state_dict ----
         self._cfg = _lib.make_config(input_nc, ndf, int(patch_size), patch_div, gram_channels, d_model, n_tf,
-                                     transformer_heads, list(self.num_classes_per_task.values()))
+                                     transformer_heads, list(self.num_classes_per_task.values()), self._norm,
+                                     use_channel_attention)
         if _lib.lib.pmg_param_count(ctypes.byref(self._cfg)) < 0:
             raise ValueError("configuration rejected by the PMG CUDA library (pmg_param_count < 0)")
         self._n_logits = _lib.lib.pmg_logits_per_image(ctypes.byref(self._cfg))
@@ -158,7 +169,8 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
             st.pop(k, None)
         c = st.pop("_cfg")
         st["_cfg_tuple"] = (c.input_nc, c.ndf, c.patch_size, c.patch_div, c.gram_channels, c.d_model,
-                            c.transformer_layers, c.transformer_heads, [c.ncls[i] for i in range(c.n_tasks)])
+                            c.transformer_layers, c.transformer_heads, [c.ncls[i] for i in range(c.n_tasks)],
+                            c.norm, c.use_channel_attention)
         return st
 
     def __setstate__(self, st):
@@ -183,7 +195,11 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
         mods = list(self.feature_extractor)
         for i in range(0, len(mods), 3):
             conv, bn = mods[i], mods[i + 1]
-            out += [conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+            out += [conv.weight, bn.weight, bn.bias]
+            if self._norm == "batch":
+                out += [bn.running_mean, bn.running_var]
+        if self.use_channel_attention:
+            out += [self.se.fc[0].weight, self.se.fc[2].weight]
         out += [self.chan_proj.weight, self.token_proj.weight, self.token_proj.bias]
         if not isinstance(self.transformer, nn.Identity):
             for layer in self.transformer.encoder.layers:

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define PMG_ABI_VERSION 1
+#define PMG_ABI_VERSION 2
 #define PMG_MAX_TASKS 32
 #define PMG_MAX_BACKBONE 8
 
@@ -41,8 +41,12 @@ typedef enum pmg_status {
 typedef enum pmg_dtype { PMG_F32 = 0, PMG_BF16 = 1 } pmg_dtype;
 
 /* Constructor hyper-parameters — mirrors Models/models_PMG.py:78-92 and the "hparams" block of
- * Model_weights/PMG/hyperparameters_PMG.json:8-33.  norm must be "batch" (eval, running stats),
- * use_channel_attention must be false (se = Identity, models_PMG.py:133), use_token_attention true. */
+ * Model_weights/PMG/hyperparameters_PMG.json:8-33.  The committed configuration (norm "batch", no channel attention) at
+ * 224x224 takes the tcgen05 fast path; norm "instance" (models_PMG.py:100-101) and use_channel_attention (SEBlock,
+ * :15-30,133) run on the shape-generic fp32 kernels.  norm "group" cannot be constructed in the reference either
+ * (:102-103 binds num_groups by keyword and then passes the channel count positionally: TypeError) and is rejected. */
+#define PMG_NORM_BATCH 0     /* BatchNorm2d(affine), eval: running statistics folded into the conv epilogue */
+#define PMG_NORM_INSTANCE 1  /* InstanceNorm2d(affine=True): per-sample, per-channel statistics */
 typedef struct pmg_config {
     int32_t input_nc;            /* 3 */
     int32_t ndf;                 /* 32 */
@@ -54,6 +58,8 @@ typedef struct pmg_config {
     int32_t transformer_heads;   /* 4 */
     int32_t n_tasks;             /* 12 */
     int32_t ncls[PMG_MAX_TASKS]; /* classes per task, Tasks.json order */
+    int32_t norm;                /* PMG_NORM_BATCH or PMG_NORM_INSTANCE */
+    int32_t use_channel_attention; /* 1 = SEBlock between feature_extractor and chan_proj (models_PMG.py:133,179) */
 } pmg_config;
 
 /* pmg_forward flags */
@@ -84,7 +90,8 @@ const char* pmg_last_cuda_error(void);
 /* Number of parameter tensors pmg_pack_weights expects, in this order (all fp32, contiguous, torch
  * layouts; = the reference state_dict order of hyperparameters_PMG.json:53-135 minus the int64
  * num_batches_tracked entries, task queries in Tasks.json order):
- *   per backbone conv l:  conv.weight (Cout,Cin,k,k), bn.weight, bn.bias, bn.running_mean, bn.running_var
+ *   per backbone conv l:  conv.weight (Cout,Cin,k,k), norm.weight, norm.bias [, bn.running_mean, bn.running_var — norm "batch" only]
+ *   [se.fc.0.weight (max(1,C/16), C), se.fc.2.weight (C, max(1,C/16)) — use_channel_attention only]
  *   chan_proj.weight (Cr,C,1,1);  token_proj.weight (d,Cr*Cr), token_proj.bias (d)
  *   per encoder layer:    in_proj_weight (3d,d), in_proj_bias, out_proj.weight (d,d), out_proj.bias,
  *                         linear1.weight (2d,d), linear1.bias, linear2.weight (d,2d), linear2.bias,

@@ -62,6 +62,28 @@ def batchnorm_eval(x, gamma, beta, mean, var, eps=BN_EPS):
     return (x - mean.reshape(1, -1, 1, 1)) * s * gamma.reshape(1, -1, 1, 1) + beta.reshape(1, -1, 1, 1)
 
 
+def instance_norm(x, gamma, beta, eps=1e-5):
+    """nn.InstanceNorm2d(C, affine=True) (models_PMG.py:101; no running stats: per-sample, per-channel statistics in
+    train AND eval), biased variance."""
+    mu = x.mean(axis=(2, 3), keepdims=True)
+    var = ((x - mu) ** 2).mean(axis=(2, 3), keepdims=True)
+    return (x - mu) / np.sqrt(var + x.dtype.type(eps)) * gamma.reshape(1, -1, 1, 1) + beta.reshape(1, -1, 1, 1)
+
+
+def se_block(x, w1, w2):
+    """SEBlock.forward (models_PMG.py:26-30): w = sigmoid(W2·relu(W1·avgpool(x))); x·w."""
+    pooled = x.mean(axis=(2, 3))
+    gate = 1.0 / (1.0 + np.exp(-(np.maximum(pooled @ w1.T, 0) @ w2.T)))
+    return x * gate[:, :, None, None].astype(x.dtype)
+
+
+def _norm(x, sd, b, norm):
+    """norm_layer of the ctor (models_PMG.py:100-105; "group" cannot be constructed in the reference: TypeError at :116)."""
+    if norm == "instance":
+        return instance_norm(x, sd[f"{b}.weight"], sd[f"{b}.bias"])
+    return batchnorm_eval(x, sd[f"{b}.weight"], sd[f"{b}.bias"], sd[f"{b}.running_mean"], sd[f"{b}.running_var"])
+
+
 def leaky_relu(x, slope=LEAKY):
     return np.where(x >= 0, x, x * x.dtype.type(slope))
 
@@ -128,7 +150,7 @@ def task_pool_and_heads(tokens, sd, tasks: Dict[str, int]) -> Dict[str, np.ndarr
 
 
 def pmg_forward(x: np.ndarray, sd: Dict[str, np.ndarray], tasks: Dict[str, int], patch_div: int,
-                nhead: int, dtype=np.float32, return_intermediates: bool = False):
+                nhead: int, dtype=np.float32, return_intermediates: bool = False, norm: str = "batch"):
     """MultiTaskPatchGANGramModelNonOverlapV2.forward — models_PMG.py:176-199.
 
     ``sd`` is a numpy state_dict in the reference's key layout. ``dtype=np.float64`` gives a
@@ -141,9 +163,10 @@ def pmg_forward(x: np.ndarray, sd: Dict[str, np.ndarray], tasks: Dict[str, int],
         w = sd[f"feature_extractor.{i}.weight"]
         x = conv_k4s4(x, w) if kind == "strided" else conv_1x1(x, w)
         b = f"feature_extractor.{i + 1}"
-        x = batchnorm_eval(x, sd[f"{b}.weight"], sd[f"{b}.bias"], sd[f"{b}.running_mean"], sd[f"{b}.running_var"])
-        x = leaky_relu(x)
+        x = leaky_relu(_norm(x, sd, b, norm))
         inter[f"act{i // 3}"] = x
+    if "se.fc.0.weight" in sd:                                                     # :133,179 (use_channel_attention)
+        x = se_block(x, sd["se.fc.0.weight"], sd["se.fc.2.weight"])
     x = conv_1x1(x, sd["chan_proj.weight"])                                        # :182
     inter["chan"] = x
     patches, n = split_patches(x, patch_div)                                       # :185
@@ -163,7 +186,7 @@ def pmg_forward(x: np.ndarray, sd: Dict[str, np.ndarray], tasks: Dict[str, int],
     return logits
 
 
-def style_patch_grams(x: np.ndarray, sd: Dict[str, np.ndarray], patch_div: int, dtype=np.float32) -> np.ndarray:
+def style_patch_grams(x: np.ndarray, sd: Dict[str, np.ndarray], patch_div: int, dtype=np.float32, norm: str = "batch") -> np.ndarray:
     """extract_patch_grams_for_image — utils/PMG/PMG_style_transfer.py:11-48, for every image of the batch.
 
     Features = ``model.feature_extractor(x)`` (:21; the conv/BN/LeakyReLU stack only, C = last conv width — NOT chan_proj);
@@ -180,7 +203,7 @@ def style_patch_grams(x: np.ndarray, sd: Dict[str, np.ndarray], patch_div: int, 
         w = sd[f"feature_extractor.{i}.weight"]
         x = conv_k4s4(x, w) if kind == "strided" else conv_1x1(x, w)
         b = f"feature_extractor.{i + 1}"
-        x = leaky_relu(batchnorm_eval(x, sd[f"{b}.weight"], sd[f"{b}.bias"], sd[f"{b}.running_mean"], sd[f"{b}.running_var"]))
+        x = leaky_relu(_norm(x, sd, b, norm))
     B, C, H, W = x.shape
     ph, pw = H // patch_div, W // patch_div
     ny, nx = H // ph, W // pw

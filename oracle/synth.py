@@ -116,11 +116,16 @@ def pmg_state_dict(seed: int = 0, hparams: dict | None = None, tasks: dict | Non
         b = f"feature_extractor.{idx + 1}"
         sd[f"{b}.weight"] = _t(f"{b}.g", seed, (cout,), kind="uniform", lo=0.6, hi=1.4)
         sd[f"{b}.bias"] = _t(f"{b}.b", seed, (cout,), std=0.15)
-        sd[f"{b}.running_mean"] = _t(f"{b}.m", seed, (cout,), std=0.25)
-        sd[f"{b}.running_var"] = _t(f"{b}.v", seed, (cout,), kind="uniform", lo=0.5, hi=1.5)
-        sd[f"{b}.num_batches_tracked"] = np.array(1234, dtype=np.int64)
+        if hp.get("norm", "batch") != "instance":                       # InstanceNorm2d(affine=True) keeps no statistics
+            sd[f"{b}.running_mean"] = _t(f"{b}.m", seed, (cout,), std=0.25)
+            sd[f"{b}.running_var"] = _t(f"{b}.v", seed, (cout,), kind="uniform", lo=0.5, hi=1.5)
+            sd[f"{b}.num_batches_tracked"] = np.array(1234, dtype=np.int64)
         idx += 3
         c_last = cout
+    if hp.get("use_channel_attention", False):                          # SEBlock, models_PMG.py:15-30
+        hid = max(1, c_last // 16)
+        sd["se.fc.0.weight"] = _t("se.w1", seed, (hid, c_last), std=1.5 / np.sqrt(c_last))
+        sd["se.fc.2.weight"] = _t("se.w2", seed, (c_last, hid), std=1.5 / np.sqrt(hid))
     sd["chan_proj.weight"] = _t("chan_proj.w", seed, (cr, c_last, 1, 1), std=1.0 / np.sqrt(c_last))
     sd["token_proj.weight"] = _t("token_proj.w", seed, (d, cr * cr), std=1.0 / np.sqrt(cr * cr) * 4.0)
     sd["token_proj.bias"] = _t("token_proj.b", seed, (d,), std=0.1)

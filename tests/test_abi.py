@@ -22,7 +22,7 @@ def test_header_symbols_exported():
     for n in names:
         assert hasattr(_lib.lib, n), n
     assert sorted(_lib.EXPORTS) == names
-    assert _lib.lib.pmg_abi_version() == 1
+    assert _lib.lib.pmg_abi_version() == 2
 
 
 def test_library_is_in_tree_shared_object():
