@@ -11,11 +11,17 @@
 #include "pmg_common.cuh"
 #include "tc_host.cuh"
 
+#include <mutex>
+
 namespace pmg {
 
 using bf16 = __nv_bfloat16;
 constexpr int PM_MAX_LAYERS = 8;
-constexpr int PM_CHUNK = 256;          // images per internal pass (bounds the workspace)
+// Images per internal pass (bounds the workspace) and the number of passes in flight.  A pass is a chain of tensor-bound
+// kernels (implicit-GEMM convolutions: persistent, one CTA per SM) and HBM-bound ones (InstanceNorm, layer-0 im2col: small
+// blocks that fit beside a GEMM CTA).  Two passes on two streams let the HBM-bound kernels of one pass run under the
+// convolutions of the other instead of leaving the tensor pipe idle a third of the time.
+static int g_pm_chunk = 128, g_pm_lanes = 2;
 constexpr float kInEps = 1e-5f;        // nn.InstanceNorm2d default
 
 struct PmLayer { int cin, cout, stride, K, Kp; };   // K = cin*16, Kp = K rounded up to 64
@@ -389,6 +395,16 @@ static int pm_conv_gemm(const void* a_hi, const void* a_lo, int Kp, const bf16* 
     return PMG_OK;
 }
 
+// the side stream of the second pass: one per device, created on first use, never destroyed
+static cudaStream_t pm_side_stream() {
+    static std::mutex mu;
+    static cudaStream_t side[tc::kMaxDevices] = {};
+    const int dev = tc::current_device();
+    std::lock_guard<std::mutex> lk(mu);
+    if (!side[dev] && cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking) != cudaSuccess) side[dev] = nullptr;
+    return side[dev];
+}
+
 static int grid1d(size_t n) { size_t g = (n + 255) / 256; return (int)(g > 148 * 32 ? 148 * 32 : (g < 1 ? 1 : g)); }
 
 }  // namespace pmg
@@ -456,7 +472,15 @@ size_t pm_workspace_bytes(const pm_config* cfg, int B, int H, int W) {
     if (!p.ok || B < 1) return 0;
     const PmShape s = pm_shape(p, H, W);
     if (!s.ok) return 0;
-    return pm_ws(p, s, B < PM_CHUNK ? B : PM_CHUNK).total;
+    const int Bc = B < g_pm_chunk ? B : g_pm_chunk;
+    const int lanes = (B > Bc && g_pm_lanes > 1) ? 2 : 1;
+    return lanes * align256(pm_ws(p, s, Bc).total);
+}
+
+// tuning hook (tools/): images per internal pass and passes in flight (1 or 2); affects pm_workspace_bytes
+void pm_debug_set_chunking(int chunk, int lanes) {
+    if (chunk >= 1) g_pm_chunk = chunk;
+    if (lanes >= 1) g_pm_lanes = lanes > 2 ? 2 : lanes;
 }
 
 int pm_forward(const pm_config* cfg, const void* packed, const void* x, int x_dtype, int B, int H, int W, float* logits,
@@ -474,18 +498,35 @@ int pm_forward(const pm_config* cfg, const void* packed, const void* x, int x_dt
         PMG_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev), "attr");
         if (major != 10) return PMG_ERR_ARCH;
     }
-    const int Bc_max = B < PM_CHUNK ? B : PM_CHUNK;
+    const int chunk = g_pm_chunk;
+    const int Bc_max = B < chunk ? B : chunk;
     const PmWs w = pm_ws(p, s, Bc_max);
-    if (workspace_bytes < w.total) return PMG_ERR_WORKSPACE;
+    const int lanes = (B > Bc_max && g_pm_lanes > 1) ? 2 : 1;
+    const size_t lane_bytes = align256(w.total);
+    if (workspace_bytes < lanes * lane_bytes) return PMG_ERR_WORKSPACE;
     const PmPacked L = pm_packed(p);
     const char* pk = reinterpret_cast<const char*>(packed);
-    char* ws = reinterpret_cast<char*>(workspace);
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    auto Hb = [&](size_t off) { return reinterpret_cast<bf16*>(ws + off); };
+    cudaStream_t st0 = reinterpret_cast<cudaStream_t>(stream);
+    // second pass lane: an internal stream forked from / joined to the caller's stream with events (capturable)
+    cudaStream_t lane_st[2] = {st0, st0};
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    if (lanes == 2) {
+        cudaStream_t side = pm_side_stream();
+        if (!side) { set_cuda_error(cudaErrorUnknown, "pm side stream"); return PMG_ERR_CUDA; }
+        PMG_CUDA_OK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming), "pm fork event");
+        PMG_CUDA_OK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming), "pm join event");
+        PMG_CUDA_OK(cudaEventRecord(ev_fork, st0), "pm fork record");
+        PMG_CUDA_OK(cudaStreamWaitEvent(side, ev_fork, 0), "pm fork wait");
+        lane_st[1] = side;
+    }
     const int Hf = s.h[p.n_layers], Wf = s.w[p.n_layers], HWf = Hf * Wf;
     const size_t img_elems = (size_t)cfg->input_nc * H * W;
-    for (int b0 = 0; b0 < B; b0 += PM_CHUNK) {
-        const int Bc = min(PM_CHUNK, B - b0);
+    int ci = 0;
+    for (int b0 = 0; b0 < B; b0 += chunk, ++ci) {
+        const int Bc = min(chunk, B - b0);
+        char* ws = reinterpret_cast<char*>(workspace) + (size_t)(ci % lanes) * lane_bytes;
+        cudaStream_t st = lane_st[ci % lanes];
+        auto Hb = [&](size_t off) { return reinterpret_cast<bf16*>(ws + off); };
         const char* xb = reinterpret_cast<const char*>(x) + (size_t)b0 * img_elems * (x_dtype == PMG_F32 ? 4 : 2);
         int rc;
         for (int l = 0; l < p.n_layers; ++l) {
@@ -551,6 +592,12 @@ int pm_forward(const pm_config* cfg, const void* packed, const void* x, int x_dt
         for (int t = 0; t <= p.ntask; ++t) a.cls_off[t] = p.cls_off[t];
         pm_heads_finish_kernel<<<(Bc * p.ntask + 3) / 4, 128, 0, st>>>(a);
         PMG_LAUNCH_OK("pm heads finish");
+    }
+    if (lanes == 2) {
+        PMG_CUDA_OK(cudaEventRecord(ev_join, lane_st[1]), "pm join record");
+        PMG_CUDA_OK(cudaStreamWaitEvent(st0, ev_join, 0), "pm join wait");
+        cudaEventDestroy(ev_fork);          // released by the runtime once the recorded work has completed
+        cudaEventDestroy(ev_join);
     }
     return PMG_OK;
 }

@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(256) pool_finish_kernel(const FinishArgs a) {
 struct FastWs {
     size_t a0_hi, a0_lo, act0_hi, act0_lo, act1_hi, act1_lo, act2_hi, act2_lo, chan, g_hi, g_lo, partial, tok,
         h_hi, h_lo, qkv, ffh_hi, ffh_lo, sc, total;
-    int splits, splits_lo;               // split-K factors of the two token_proj GEMMs (hi weights K 6144, lo weights K 3072)
+    int splits;                          // split-K factor of token_proj (hi weights K 6144 + lo-weight segment K 3072 in the same launch)
 };
 
 static int token_splits(int T) {
@@ -460,9 +460,8 @@ static FastWs fast_ws(int B) {
     w.act2_hi = take(P * 128 * 2); w.act2_lo = take(P * 128 * 2);
     w.chan = take(P * 96 * 4);
     w.g_hi = take(T * 6144 * 2); w.g_lo = take(T * 6144 * 2);
-    w.splits = tc::effective_splits(6144, token_splits((int)T));
-    w.splits_lo = tc::effective_splits(3072, token_splits((int)T));
-    w.partial = take((size_t)(w.splits + w.splits_lo) * T * 192 * 4);
+    w.splits = tc::effective_splits(6144, token_splits((int)T), 3072);
+    w.partial = take((size_t)w.splits * T * 192 * 4);
     w.tok = take(T * 192 * 4);
     w.h_hi = take(T * 192 * 2); w.h_lo = take(T * 192 * 2);
     w.qkv = take(T * 576 * 4);
@@ -488,8 +487,8 @@ int fast_launch_count(const Plan& p, const Shape&, int B, unsigned flags) {
     const int front = (flags & PMG_FLAG_NO_FUSED_FRONT) ? 3 : (flags & PMG_FLAG_COUNT_F32_INPUT) ? 2 : 1;
     // conv2 + chan_proj + Gram: one kernel (tc_midgram.cuh), or the fused mid kernel + Gram, or two GEMMs + Gram
     const int mid = use_midgram(B, flags) ? 1 : (flags & PMG_FLAG_NO_FUSED_MID) ? 3 : 2;
-    if (!(flags & PMG_FLAG_NO_FUSED_ENCODER) && p.nl <= tc::ENC_MAX_LAYERS) return front + mid + 2 + 1;   // + token_proj (2), token stage
-    return front + mid + 2 + 1 + 6 * p.nl + (p.nl > 1 ? p.nl - 1 : 0) + 3;
+    if (!(flags & PMG_FLAG_NO_FUSED_ENCODER) && p.nl <= tc::ENC_MAX_LAYERS) return front + mid + 1 + 1;   // + token_proj, token stage
+    return front + mid + 1 + 1 + 6 * p.nl + (p.nl > 1 ? p.nl - 1 : 0) + 3;
 }
 
 template <int BN, int NA, int EPI, int ACT>
@@ -644,15 +643,19 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
     }
     // token_proj (:192-193): split-K partial sums, reduced (+bias) by tok_ln_kernel
     const size_t pstride = (size_t)T * 192;
-    // G' (upper blocks, hi+lo) · W'hᵀ, then the off-diagonal part of G'hi · W'lᵀ as extra split-K partials
+    // G' (upper blocks, hi+lo) · W'hᵀ  +  the off-diagonal part of G'hi · W'lᵀ as a second K segment of the SAME launch: one
+    // accumulator, one set of split-K partials (it was a second GEMM with its own partial buffers: 4 buffers for the token
+    // stage to reduce instead of 2, and a second kernel tail).
     // (the CTA-pair variant tc_gemm2.cuh — tcgen05 cta_group::2 — is parity-tested and measured 64 us here vs 60 us
-    // for these cta_group::1 launches: the op is tensor-bound at ~56 % of peak either way, so it is not the default)
-    if ((rc = gemm<192, 2, tc::EPI_PARTIAL, tc::GACT_NONE>(Hb(w.g_hi), Hb(w.g_lo), 6144, Wb(f.wth), T, 192, 6144, 192,
-                   Ff(w.partial), nullptr, nullptr, nullptr, nullptr, nullptr, w.splits, pstride, st)))
-        return rc;
-    if ((rc = gemm<192, 1, tc::EPI_PARTIAL, tc::GACT_NONE>(Hb(w.g_hi) + 3072, nullptr, 6144, Wb(f.wtl), T, 192, 3072, 192,
-                   Ff(w.partial) + (size_t)w.splits * pstride, nullptr, nullptr, nullptr, nullptr, nullptr, w.splits_lo, pstride, st)))
-        return rc;
+    // for the cta_group::1 launches: the op is tensor-bound at ~56 % of peak either way, so it is not the default)
+    {
+        tc::GemmParams g{};
+        g.M = T; g.N = 192; g.K = 6144; g.epi = tc::EPI_PARTIAL; g.act = tc::GACT_NONE; g.ldc = 192; g.out_f32 = Ff(w.partial);
+        g.partial_stride = pstride;
+        if ((rc = tc::launch_gemm_t<192, 2, tc::EPI_PARTIAL, tc::GACT_NONE, true>(Hb(w.g_hi), Hb(w.g_lo), 6144, Wb(f.wth), 6144, g,
+                       token_splits(T), 6144, st, Hb(w.g_hi) + 3072, Wb(f.wtl), 3072)))
+            return rc;
+    }
     PMG_MARK(tm, "token_proj");
     if (!(flags & PMG_FLAG_NO_FUSED_ENCODER) && p.nl <= tc::ENC_MAX_LAYERS) {
         // split-K reduce + bias, the whole transformer, task pooling and the heads: one kernel (tc_encoder.cuh)
@@ -663,7 +666,7 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
         }
         tc::EncParams e{};
         e.wstream = reinterpret_cast<const uint8_t*>(fb + f.wenc);
-        e.partial = Ff(w.partial); e.pstride = pstride; e.nsplit = w.splits + w.splits_lo; e.tok_bias = Pf(L.tok_b);
+        e.partial = Ff(w.partial); e.pstride = pstride; e.nsplit = w.splits; e.tok_bias = Pf(L.tok_b);
         e.cls_bias = Pf(L.cls_b); e.logits = logits;
         e.tok_in = taps ? taps->tokens_in : nullptr; e.tok_out = taps ? taps->tokens_out : nullptr;
         e.nl = p.nl; e.B = B; e.ntask = p.ntask; e.ncls_total = p.ncls_total; e.trace = g_enc_trace;
@@ -688,7 +691,7 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
     }
     {
         const TfLayerOff* t0 = p.nl > 0 ? &L.tf[0] : nullptr;
-        PMG_CUDA_OK(tc::launch_pdl(tok_ln_kernel, dim3((T + 3) / 4), dim3(128), 0, st, (const float*)Ff(w.partial), w.splits + w.splits_lo, pstride,
+        PMG_CUDA_OK(tc::launch_pdl(tok_ln_kernel, dim3((T + 3) / 4), dim3(128), 0, st, (const float*)Ff(w.partial), w.splits, pstride,
                                    Pf(L.tok_b), Ff(w.tok), t0 ? Pf(t0->ln1w) : (const float*)nullptr,
                                    t0 ? Pf(t0->ln1b) : (const float*)nullptr, Hb(w.h_hi), Hb(w.h_lo), T, t0 ? 1 : 0), "tok_ln");
         PMG_MARK(tm, "tok_reduce_ln");
@@ -743,17 +746,11 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
 // test / microbenchmark hooks
 // ------------------------------------------------------------------------------------------------
 static int make_tmap_gram3d(CUtensorMap* m, const void* base, int B, int C, int HW, uint32_t box_rows) {
-    tc::EncodeTiledFn fn = tc::encode_fn();
-    if (!fn) { set_cuda_error(cudaErrorNotSupported, "cuTensorMapEncodeTiled entry point"); return PMG_ERR_CUDA; }
     cuuint64_t dims[3] = {(cuuint64_t)HW, (cuuint64_t)C, (cuuint64_t)B};
     cuuint64_t strides[2] = {(cuuint64_t)HW * 2, (cuuint64_t)C * HW * 2};
     cuuint32_t box[3] = {64, box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(gram 3d)"); return PMG_ERR_CUDA; }
-    return PMG_OK;
+    return tc::encode_tmap_cached(m, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B, "cuTensorMapEncodeTiled(gram 3d)");
 }
 
 template <int BN, bool LSU>

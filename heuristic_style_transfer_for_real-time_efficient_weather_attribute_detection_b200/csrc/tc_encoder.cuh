@@ -7,8 +7,11 @@
 // residual stream x of the tile lives in TMEM (columns 0..191, fp32) for the whole kernel: the out-proj and
 // FFN2 MMAs accumulate straight onto it, so the residual adds cost nothing.  Activations that feed an MMA are
 // written by the epilogue warps as two bf16 planes (hi + lo, DESIGN.md "precision") into K-major 128B-swizzled
-// smem operand tiles; all layer weights stream through a 3-stage ring of 24 KB blocks with cp.async.bulk from a
-// pre-swizzled copy (enc_pack_kernel), so one bulk copy lands a ready-to-use UMMA B tile.  Every small parameter
+// smem operand tiles; all layer weights stream through a 4-stage ring of 24 KB blocks with cp.async.bulk from a
+// pre-swizzled copy (enc_pack_kernel), so one bulk copy lands a ready-to-use UMMA B tile.  The attention output tile
+// O shares its shared memory with the LayerNorm output tile A (same layout; O is written only once every QKV MMA
+// of the layer has read A) — that is what pays for the 4th ring stage: a 24 KB block takes ≈3 k cycles to arrive
+// from L2 while every SM pulls the same lines, so the bytes in flight set the rate at which the MMAs are fed.  Every small parameter
 // (biases, LayerNorm affine, task map) is staged in smem once per CTA, before griddepcontrol.wait, so no global
 // load sits on the per-phase critical path.
 //
@@ -18,7 +21,7 @@
 //
 // Warp roles (18 warps): 0 = weight producer, 1 = MMA issuer (+ TMEM alloc), warps w with w%4 ∈ {0,1}, w ≥ 4
 // = 8 "compute" warps (TMEM lane quarter q = w%4 holds rows 32q..32q+31; column group g = (w-4)/4), warps with
-// w%4 ∈ {2,3} = "aux" warps; three of them (2, 3, 7) run the 9-token attention core out of shared memory.
+// w%4 ∈ {2,3} = 8 "aux" warps that run the 9-token attention core out of shared memory.
 //
 // Per layer:  LN1 → A tile │ per head h: MMA [q_h|k_h|v_h] (N 144, TMEM double-buffered) → compute warps drain
 // (+bias, q·log2e/√48) to smem fp32 → aux warps: scores, softmax, P·V → O tile (hi/lo) │ out-proj MMA onto x │
@@ -29,45 +32,35 @@
 #pragma once
 
 #include "tc_prims.cuh"
-#include "tc_gemm2.cuh"      // cluster helpers (cluster_ctarank, cluster_sync_all)
 
 namespace tc {
 
-// ENC_CLUSTER = 1: weight blocks multicast to CTA pairs.  Every CTA of the grid streams the same 1.2 MB of weights and the
-// MMA thread was measured waiting for them 15 % of the stage.  With clusters of 2, each CTA fetches HALF of every block and
-// the copy lands in both CTAs' shared memory (cp.async.bulk … .multicast::cluster); a stage is refilled when BOTH consumers
-// have released it (tcgen05.commit … .multicast::cluster onto both w_empty barriers).  Parity-green on B200, but NOT faster
-// (weight wait 15.9 k vs 17.2 k cycles, stage 0.077 vs 0.075 ms): the wait is the fixed L2 round trip of a refill that can
-// only be requested once the MMAs reading the stage have completed, not the transfer time — what would help is a 4th stage,
-// which the 227 KB do not have room for.  Kept as a compile-time variant; the default is the single-CTA stream.
-#ifndef ENC_CLUSTER
-#define ENC_CLUSTER 0
-#endif
-
+constexpr int ENC_ATTN_WARPS = 8;
 constexpr int ENC_THREADS = 576;
 constexpr int ENC_IPT = 7;                   // images per tile
 constexpr int ENC_ROWS = 63;                 // token rows per tile
 constexpr int ENC_MAX_LAYERS = 2;            // parameters of every layer stay resident in smem
 constexpr int ENC_STAGE = 24576;             // weight ring stage
-constexpr int ENC_NSTAGE = 3;
+constexpr int ENC_NSTAGE = 4;
 constexpr int ENC_QKV_LD = 148;              // floats per row of the fp32 [q|k|v] head buffer (144 + 4: conflict-free 16-byte row accesses)
 constexpr int ENC_KB = 8192;                 // operand k-block: 64 rows × 128 B
 constexpr int ENC_PLANE = 3 * ENC_KB;        // [64 rows × 192 K] bf16
 constexpr int ENC_OFF_QKV = ENC_NSTAGE * ENC_STAGE;                 // fp32 head buffer; aliased by the FFN hidden tile and the heads result
-constexpr int ENC_QKV_BYTES = 64 * ENC_QKV_LD * 4;                  // 37,888 = 37 KB
+constexpr int ENC_QKV_BYTES = 49152;                                // ≥ 64·ENC_QKV_LD·4 (head buffer) and ≥ 63·192·4 (split-K staging of one partial)
 constexpr int ENC_OFF_A = ENC_OFF_QKV + ENC_QKV_BYTES;              // LN output / final tokens, hi then lo plane
-constexpr int ENC_OFF_O = ENC_OFF_A + 2 * ENC_PLANE;                // attention output, hi then lo plane
+constexpr int ENC_OFF_O = ENC_OFF_A;                                // attention output: SAME tile (written after the layer's last QKV MMA)
 constexpr int ENC_SC_LD = 65;                                       // [64][65] fp32 heads-GEMM result (inside the QKV region)
 // per-layer parameter block (floats): b_in 576 | b_o 192 | b_1 384 | b_2 192 | ln1w | ln1b | ln2w | ln2b (192 each)
 constexpr int ENC_P_BIN = 0, ENC_P_BO = 576, ENC_P_B1 = 768, ENC_P_B2 = 1152, ENC_P_LN1W = 1344, ENC_P_LN1B = 1536,
               ENC_P_LN2W = 1728, ENC_P_LN2B = 1920, ENC_P_LAYER = 2112;
 constexpr int ENC_P_TOKB = ENC_MAX_LAYERS * ENC_P_LAYER, ENC_P_CLSB = ENC_P_TOKB + 192, ENC_P_FLOATS = ENC_P_CLSB + 64;
-constexpr int ENC_OFF_PRM = ENC_OFF_O + 2 * ENC_PLANE;              // also the ≥ 8 KB over-read slack behind the O tile
+constexpr int ENC_OFF_PRM = ENC_OFF_A + 2 * ENC_PLANE;              // also the ≥ 8 KB over-read slack behind the A / O tile
 constexpr int ENC_OFF_TASK = ENC_OFF_PRM + ENC_P_FLOATS * 4;        // task_of[64] bytes
 constexpr int ENC_OFF_RED = ENC_OFF_TASK + 64;                      // LayerNorm partial sums: 2 × [4][64] fp32
 constexpr int ENC_OFF_BAR = ENC_OFF_RED + 2 * 4 * 64 * 4;
 constexpr int ENC_SMEM = ENC_OFF_BAR + 256 + 1024;
 static_assert(ENC_SMEM <= 232448, "token-stage kernel exceeds the 227 KB shared-memory limit");
+static_assert(ENC_QKV_BYTES >= 64 * ENC_QKV_LD * 4 && ENC_QKV_BYTES >= 63 * 192 * 4 && ENC_QKV_BYTES % 1024 == 0, "head buffer / staging");
 
 // weight stream geometry (bytes), per layer, in the order the MMA warp consumes it
 constexpr int ENC_QKV_BLK = 144 * 128;                               // one k-block of one head's [q|k|v] rows
@@ -101,18 +94,6 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
         "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)), "l"(kEvictLast)
         : "memory");
-}
-// same, delivered to the same smem offset (and signalling the mbarrier at the same offset) in both CTAs of a pair
-__device__ __forceinline__ void bulk_g2s_pair(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster.L2::cache_hint [%0], [%1], %2, [%3], %4, %5;"
-        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar)), "h"((uint16_t)3), "l"(kEvictLast)
-        : "memory");
-}
-// all previously issued MMAs of this thread arrive on `bar` (same offset) in both CTAs of the pair
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
 // 16-byte asynchronous copy global → shared; src_bytes = 0 zero-fills
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, uint32_t src_bytes) {
@@ -199,32 +180,6 @@ __device__ __forceinline__ void layer_norm48(float (&v)[48], float* red, int m, 
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// 9-token attention core of one head out of the fp32 [q|k|v] head buffer (models_PMG.py:64: nn.MultiheadAttention,
-// 4 heads × 48, scale 1/sqrt(48) folded into q together with log2 e).  Three warps; a thread owns 3 query rows of one
-// image × 12 of the head's 48 dims, so every K / V chunk it loads serves three rows.  (Spreading the same work over
-// four warps incl. two compute warps measured slower: 83 vs 78 µs per 1024 images.)  The 4 lanes of a row group sum
-// their partial q·k with two xor-shuffles.  Result: O tile columns 48h.. as hi/lo bf16 planes.
-// ------------------------------------------------------------------------------------------------
-struct AttnCtx {
-    const float* qp; const float* kp; const float* vp;
-    int r0, part;
-    bool active;
-};
-__device__ __forceinline__ AttnCtx attn_ctx(const float* sQKV, int ai, int lane) {
-    AttnCtx c;
-    const int q4 = lane >> 2;
-    const int rgi = ai * 8 + q4;                       // 21 row groups (7 images × 3) over 3 warps × 8 lane quads
-    c.active = rgi < 21;
-    const int rg = c.active ? rgi : 20;
-    const int img = rg / 3;
-    c.part = lane & 3;
-    c.r0 = img * 9 + (rg - img * 3) * 3;
-    c.qp = sQKV + c.r0 * ENC_QKV_LD + 12 * c.part;
-    c.kp = sQKV + img * 9 * ENC_QKV_LD + 48 + 12 * c.part;
-    c.vp = c.kp + 48;
-    return c;
-}
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -235,84 +190,81 @@ __device__ __forceinline__ float fast_rcp(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ void attention_head(const AttnCtx& ac, uint8_t* sO, int h, uint64_t* qkv_empty, uint64_t* o_ready, int lane) {
-    float4 qv[3][3];
+// ------------------------------------------------------------------------------------------------
+// 9-token attention core of one head out of the fp32 [q|k|v] head buffer (models_PMG.py:64: nn.MultiheadAttention,
+// 4 heads × 48, scale 1/sqrt(48) folded into q together with log2 e) on the eight aux warps: a thread owns ONE query row
+// × 12 of the head's 48 dims (4 lanes per row, 8 rows per warp); the 4 lanes of a row sum their partial q·k with two
+// xor-shuffles.  (Round 1 ran three rows per thread on three warps, two of them on one SM sub-partition.)
+// ------------------------------------------------------------------------------------------------
+struct AttnCtx1 {
+    const float* qp; const float* kp; const float* vp;
+    int row, part;
+    bool active;
+};
+__device__ __forceinline__ AttnCtx1 attn_ctx1(const float* sQKV, int ai, int lane) {
+    AttnCtx1 c;
+    const int r = ai * 8 + (lane >> 2);
+    c.active = r < ENC_ROWS;
+    c.row = c.active ? r : ENC_ROWS - 1;
+    const int img = c.row / 9;
+    c.part = lane & 3;
+    c.qp = sQKV + c.row * ENC_QKV_LD + 12 * c.part;
+    c.kp = sQKV + img * 9 * ENC_QKV_LD + 48 + 12 * c.part;
+    c.vp = c.kp + 48;
+    return c;
+}
+__device__ __forceinline__ void attention_rows(const AttnCtx1& ac, float (&o)[12], int lane) {
+    float4 qv[3];
 #pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c) qv[r][c] = *reinterpret_cast<const float4*>(ac.qp + r * ENC_QKV_LD + 4 * c);
-    float sc[3][9];
-#pragma unroll
-    for (int j = 0; j < 9; ++j) {
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float4 k4 = *reinterpret_cast<const float4*>(ac.kp + j * ENC_QKV_LD + 4 * c);
-            a0 = fmaf(qv[0][c].x, k4.x, fmaf(qv[0][c].y, k4.y, fmaf(qv[0][c].z, k4.z, fmaf(qv[0][c].w, k4.w, a0))));
-            a1 = fmaf(qv[1][c].x, k4.x, fmaf(qv[1][c].y, k4.y, fmaf(qv[1][c].z, k4.z, fmaf(qv[1][c].w, k4.w, a1))));
-            a2 = fmaf(qv[2][c].x, k4.x, fmaf(qv[2][c].y, k4.y, fmaf(qv[2][c].z, k4.z, fmaf(qv[2][c].w, k4.w, a2))));
-        }
-        sc[0][j] = a0; sc[1][j] = a1; sc[2][j] = a2;
-    }
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-#pragma unroll
-        for (int j = 0; j < 9; ++j) sc[r][j] += __shfl_xor_sync(0xffffffffu, sc[r][j], 1);
-    }
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        float mx = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 9; ++j) { sc[r][j] += __shfl_xor_sync(0xffffffffu, sc[r][j], 2); mx = fmaxf(mx, sc[r][j]); }
-        float den = 0.f;
-#pragma unroll
-        for (int j = 0; j < 9; ++j) { sc[r][j] = fast_exp2(sc[r][j] - mx); den += sc[r][j]; }
-        const float inv = fast_rcp(den);
-#pragma unroll
-        for (int j = 0; j < 9; ++j) sc[r][j] *= inv;
-    }
-    float o[3][12];
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int i = 0; i < 12; ++i) o[r][i] = 0.f;
+    for (int c = 0; c < 3; ++c) qv[c] = *reinterpret_cast<const float4*>(ac.qp + 4 * c);
+    float sc[9];
 #pragma unroll
     for (int j = 0; j < 9; ++j) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;                // three independent chains
+        const float4 k0 = *reinterpret_cast<const float4*>(ac.kp + j * ENC_QKV_LD);
+        const float4 k1 = *reinterpret_cast<const float4*>(ac.kp + j * ENC_QKV_LD + 4);
+        const float4 k2 = *reinterpret_cast<const float4*>(ac.kp + j * ENC_QKV_LD + 8);
+        a0 = fmaf(qv[0].x, k0.x, fmaf(qv[0].y, k0.y, fmaf(qv[0].z, k0.z, qv[0].w * k0.w)));
+        a1 = fmaf(qv[1].x, k1.x, fmaf(qv[1].y, k1.y, fmaf(qv[1].z, k1.z, qv[1].w * k1.w)));
+        a2 = fmaf(qv[2].x, k2.x, fmaf(qv[2].y, k2.y, fmaf(qv[2].z, k2.z, qv[2].w * k2.w)));
+        sc[j] = (a0 + a1) + a2;
+    }
+#pragma unroll
+    for (int j = 0; j < 9; ++j) sc[j] += __shfl_xor_sync(0xffffffffu, sc[j], 1);
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) { sc[j] += __shfl_xor_sync(0xffffffffu, sc[j], 2); mx = fmaxf(mx, sc[j]); }
+    float den = 0.f;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) { sc[j] = fast_exp2(sc[j] - mx); den += sc[j]; }
+    const float inv = fast_rcp(den);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) o[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+        const float pj = sc[j] * inv;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float4 v4 = *reinterpret_cast<const float4*>(ac.vp + j * ENC_QKV_LD + 4 * c);
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const float pj = sc[r][j];
-                o[r][4 * c] = fmaf(pj, v4.x, o[r][4 * c]); o[r][4 * c + 1] = fmaf(pj, v4.y, o[r][4 * c + 1]);
-                o[r][4 * c + 2] = fmaf(pj, v4.z, o[r][4 * c + 2]); o[r][4 * c + 3] = fmaf(pj, v4.w, o[r][4 * c + 3]);
-            }
+            o[4 * c] = fmaf(pj, v4.x, o[4 * c]); o[4 * c + 1] = fmaf(pj, v4.y, o[4 * c + 1]);
+            o[4 * c + 2] = fmaf(pj, v4.z, o[4 * c + 2]); o[4 * c + 3] = fmaf(pj, v4.w, o[4 * c + 3]);
         }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(qkv_empty);            // every lane of this warp has finished reading the head buffer
-    // O tile: columns 48h + 12·part .. +11 of rows r0..r0+2, hi/lo planes, 8-byte pieces
-    if (ac.active) {
+}
+// this thread's 12 output dims of head h → O tile (hi/lo planes, 8-byte pieces of the swizzled 128-byte rows)
+__device__ __forceinline__ void store_o_rows(const AttnCtx1& ac, uint8_t* sO, int h, const float (&o)[12]) {
+    if (!ac.active) return;
 #pragma unroll
-        for (int t = 0; t < 3; ++t) {
-            const int e = 48 * h + 12 * ac.part + 4 * t;         // element column, multiple of 4
-            const int ce = e & 63;
-            uint8_t* col = sO + (e >> 6) * ENC_KB + ((ce & 7) << 1);
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const int row = ac.r0 + r;
-                uint32_t h0, l0, h1, l1;
-                split_bf16x2(o[r][4 * t], o[r][4 * t + 1], h0, l0);
-                split_bf16x2(o[r][4 * t + 2], o[r][4 * t + 3], h1, l1);
-                uint8_t* dst = col + row * 128 + (((ce >> 3) ^ (row & 7)) << 4);
-                *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
-                *reinterpret_cast<uint2*>(dst + ENC_PLANE) = make_uint2(l0, l1);
-            }
-        }
+    for (int t = 0; t < 3; ++t) {
+        const int e = 48 * h + 12 * ac.part + 4 * t;         // element column, multiple of 4
+        const int ce = e & 63;
+        uint32_t h0, l0, h1, l1;
+        split_bf16x2(o[4 * t], o[4 * t + 1], h0, l0);
+        split_bf16x2(o[4 * t + 2], o[4 * t + 3], h1, l1);
+        uint8_t* dst = sO + (e >> 6) * ENC_KB + ((ce & 7) << 1) + ac.row * 128 + (((ce >> 3) ^ (ac.row & 7)) << 4);
+        *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(dst + ENC_PLANE) = make_uint2(l0, l1);
     }
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(o_ready);
 }
 
 __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams p) {
@@ -322,50 +274,45 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
     float* sQKV = reinterpret_cast<float*>(smem + ENC_OFF_QKV);
     uint8_t* sH = smem + ENC_OFF_QKV;               // FFN hidden tile [plane hi/lo][kb 2] × 8 KB (FFN phase only)
     float* sSC = reinterpret_cast<float*>(smem + ENC_OFF_QKV);   // heads result (after the last layer only)
+    uint8_t* sStage2 = smem + ENC_OFF_QKV;          // split-K staging of the second partial (first phase of a tile only)
     uint8_t* sA = smem + ENC_OFF_A;
     uint8_t* sO = smem + ENC_OFF_O;
     float* sPrm = reinterpret_cast<float*>(smem + ENC_OFF_PRM);
     unsigned char* sTask = smem + ENC_OFF_TASK;
     float* sRed = reinterpret_cast<float*>(smem + ENC_OFF_RED);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ENC_OFF_BAR);
-    uint64_t* w_full = bars;            // [3]
-    uint64_t* w_empty = bars + 3;       // [3]
-    uint64_t* a_ready = bars + 6;
-    uint64_t* dq_full = bars + 7;       // [2]
-    uint64_t* dq_empty = bars + 9;      // [2]
-    uint64_t* qkv_full = bars + 11;
-    uint64_t* qkv_empty = bars + 12;
-    uint64_t* o_ready = bars + 13;
-    uint64_t* x_full = bars + 14;
-    uint64_t* dh_full = bars + 15;      // [2]
-    uint64_t* dh_empty = bars + 17;     // [2]
-    uint64_t* h_ready = bars + 19;
-    uint64_t* h_free = bars + 20;
-    uint64_t* sc_full = bars + 21;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
+    uint64_t* w_full = bars;                        // [ENC_NSTAGE]
+    uint64_t* w_empty = bars + ENC_NSTAGE;          // [ENC_NSTAGE]
+    uint64_t* bb = bars + 2 * ENC_NSTAGE;
+    uint64_t* a_ready = bb;
+    uint64_t* dq_full = bb + 1;         // [2]
+    uint64_t* dq_empty = bb + 3;        // [2]
+    uint64_t* qkv_full = bb + 5;
+    uint64_t* qkv_empty = bb + 6;
+    uint64_t* o_ready = bb + 7;
+    uint64_t* x_full = bb + 8;
+    uint64_t* dh_full = bb + 9;         // [2]
+    uint64_t* dh_empty = bb + 11;       // [2]
+    uint64_t* h_ready = bb + 13;
+    uint64_t* h_free = bb + 14;
+    uint64_t* sc_full = bb + 15;
+    uint64_t* qkv_done = bb + 16;       // every QKV MMA of the layer has completed: the A tile may be overwritten by O
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bb + 17);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int wq = warp & 3;
-    // ENC_CLUSTER: every CTA runs the same number of tile iterations (the CTAs of a pair consume the weight stream in
-    // lockstep); a tile index past the last tile is a dummy: all of its rows fail the `grow < T` / `img < B` guards, so it
-    // reads zeros and stores nothing
-#if ENC_CLUSTER
-    const int n_tiles = (((p.B + ENC_IPT - 1) / ENC_IPT + (int)gridDim.x - 1) / (int)gridDim.x) * (int)gridDim.x;
-    const uint32_t pair_rank = cluster_ctarank();
-#else
     const int n_tiles = (p.B + ENC_IPT - 1) / ENC_IPT;
-#endif
     const int T = p.B * 9;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 3; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], ENC_CLUSTER ? 2 : 1); }
+        for (int i = 0; i < ENC_NSTAGE; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
         mbar_init(a_ready, 8);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&dq_full[i], 1); mbar_init(&dq_empty[i], 6);
             mbar_init(&dh_full[i], 1); mbar_init(&dh_empty[i], 8);
         }
         mbar_init(h_ready, 8); mbar_init(h_free, 1);
-        mbar_init(qkv_full, 6); mbar_init(qkv_empty, 3); mbar_init(o_ready, 12); mbar_init(x_full, 1); mbar_init(sc_full, 1);
+        mbar_init(qkv_full, 6); mbar_init(qkv_empty, ENC_ATTN_WARPS); mbar_init(o_ready, 4 * ENC_ATTN_WARPS); mbar_init(x_full, 1); mbar_init(sc_full, 1); mbar_init(qkv_done, 1);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -388,9 +335,6 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
     }
     tc_fence_before();
     __syncthreads();
-#if ENC_CLUSTER
-    cluster_sync_all();                 // the peer's barriers exist before any multicast copy / commit can reach them
-#endif
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_trigger();
@@ -404,12 +348,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                 const uint32_t ph = (wi / ENC_NSTAGE) & 1;
                 mbar_wait(&w_empty[s], ph ^ 1);
                 mbar_expect_tx(&w_full[s], bytes);          // the whole block: this CTA's half + the peer's
-#if ENC_CLUSTER
-                const uint32_t half = bytes / 2;
-                bulk_g2s_pair(sW + s * ENC_STAGE + pair_rank * half, p.wstream + off + pair_rank * half, half, &w_full[s]);
-#else
                 bulk_g2s(sW + s * ENC_STAGE, p.wstream + off, bytes, &w_full[s]);
-#endif
                 ++wi;
             };
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -453,11 +392,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                 tc_fence_after();
                 return aW + s * ENC_STAGE;
             };
-#if ENC_CLUSTER
-            auto free_w = [&]() { umma_commit_pair(&w_empty[wi % ENC_NSTAGE]); ++wi; };
-#else
             auto free_w = [&]() { umma_commit(&w_empty[wi % ENC_NSTAGE]); ++wi; };
-#endif
             auto ffn2 = [&](uint32_t pc) {               // x += H(chunk pc) · W2[:, 128·chunk ..]ᵀ
                 mbar_wait(h_ready, pc & 1);
                 tc_fence_after();
@@ -486,6 +421,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                         umma_commit(&dq_full[b]);
                         ENC_T(2 + 40 * l + h);
                     }
+                    umma_commit(qkv_done);
                     mbar_wait(o_ready, no & 1); ++no;                          // x += O · Woᵀ
                     tc_fence_after();
                     ENC_T(6 + 40 * l);
@@ -548,7 +484,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
             const bool valid = m < ENC_ROWS && grow < T;
             // ---- x0 = Σ_s partial[s] + bias (token_proj epilogue, models_PMG.py:193) ----
             // the 256 compute threads pull the tile's [63 × 192] fp32 block of two split-K partials at a time with
-            // 16-byte cp.async into the (idle) O and A regions, chunk-swizzled per row; then every thread adds up
+            // 16-byte cp.async into the (idle) A / O tile and head-buffer regions, chunk-swizzled per row; then every thread adds up
             // its own 48-column slice.  One global round trip, no registers held across it.
             {
 #pragma unroll
@@ -566,7 +502,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                         const uint32_t so = (uint32_t)(r * 48 + (c4 ^ (r & 7))) * 16;
                         const float* src = p.partial + (size_t)s0 * p.pstride + (ok ? (size_t)gr * 192 + 4 * c4 : 0);
                         cp_async16(sO + so, src, ok ? 16u : 0u);
-                        if (nb == 2) cp_async16(sA + so, src + p.pstride, ok ? 16u : 0u);
+                        if (nb == 2) cp_async16(sStage2 + so, src + p.pstride, ok ? 16u : 0u);
                     }
                     cp_async_wait_all();
                     named_bar_sync(1, 256);
@@ -576,7 +512,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                         const float4 a = *reinterpret_cast<const float4*>(sO + so);
                         v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
                         if (nb == 2) {
-                            const float4 c = *reinterpret_cast<const float4*>(sA + so);
+                            const float4 c = *reinterpret_cast<const float4*>(sStage2 + so);
                             v[4 * j] += c.x; v[4 * j + 1] += c.y; v[4 * j + 2] += c.z; v[4 * j + 3] += c.w;
                         }
                     }
@@ -732,23 +668,40 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
             ENC_TC(191);
         }
         tc_fence_before();
-    } else if (warp == 2 || warp == 3 || warp == 7) {
-        // ===================== aux warps: three of them run the attention core =====================
-        const AttnCtx ac = attn_ctx(sQKV, warp == 7 ? 2 : warp - 2, lane);
-        uint32_t hq = 0;
+    } else if (warp >= 2 && wq >= 2) {
+        // ===================== aux warps: the attention core =====================
+        // O shares the A tile: nothing may be stored before the layer's last QKV MMA has read A (qkv_done).  Head 0
+        // finishes before that, so its output rows wait in registers and go out together with head 1's.
+        const AttnCtx1 ac = attn_ctx1(sQKV, (warp >> 2) * 2 + (wq - 2), lane);
+        const bool tr = warp == 2 && lane == 0;
+        uint32_t hq = 0, nl_done = 0;
+        float o[12], o0[12];
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-            for (int l = 0; l < p.nl; ++l)
+            for (int l = 0; l < p.nl; ++l, ++nl_done)
                 for (int h = 0; h < 4; ++h, ++hq) {
                     mbar_wait(qkv_full, hq & 1);
-                    if (warp == 2 && lane == 0) ENC_T(200 + 40 * l + 2 * h);
-                    attention_head(ac, sO, h, qkv_empty, o_ready, lane);
-                    if (warp == 2 && lane == 0) ENC_T(201 + 40 * l + 2 * h);
+                    if (tr) ENC_T(200 + 40 * l + 2 * h);
+                    attention_rows(ac, o, lane);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(qkv_empty);        // every lane of this warp has finished reading the head buffer
+                    if (h == 0) {
+#pragma unroll
+                        for (int i = 0; i < 12; ++i) o0[i] = o[i];
+                    } else {
+                        if (h == 1) {
+                            mbar_wait(qkv_done, nl_done & 1);
+                            tc_fence_after();
+                            store_o_rows(ac, sO, 0, o0);
+                        }
+                        store_o_rows(ac, sO, h, o);
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) { mbar_arrive(o_ready); if (h == 1) mbar_arrive(o_ready); }
+                    }
+                    if (tr) ENC_T(201 + 40 * l + 2 * h);
                 }
     }
     __syncthreads();
-#if ENC_CLUSTER
-    cluster_sync_all();                 // the peer may still be multicasting into this CTA's smem / signalling its barriers
-#endif
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);

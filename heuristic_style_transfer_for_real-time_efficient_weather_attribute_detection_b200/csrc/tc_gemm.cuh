@@ -34,6 +34,10 @@ struct GemmParams {
     const float* shift;       // [N] or null
     const float* resid;       // [M, ldc] fp32 or null (EPI_F32)
     size_t partial_stride;    // elements between split-K partial buffers
+    // SEG2 kernels only: a second K segment  D += A2[M, K2] · B2[N, K2]ᵀ  (ONE activation plane) accumulated into the same
+    // TMEM tile, split like the first one — token_proj's lo-weight term rides in the main GEMM instead of being a second
+    // launch with its own partial buffers
+    int K2, kblocks2_per_split;
 };
 
 constexpr int GEMM_BM = 128;
@@ -70,10 +74,11 @@ __host__ __device__ constexpr int gemm_smem_bytes() {
 
 // Persistent: CTA c processes work items c, c+gridDim.x, …; item = (split, n_tile, m_group), m fastest.
 // Two TMEM accumulator stages let the epilogue of item i overlap the MMAs of item i+1.
-template <int BN, int NA, int EPI, int ACT>
+template <int BN, int NA, int EPI, int ACT, bool SEG2 = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-            const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+            const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmA2,
+            const __grid_constant__ CUtensorMap tmB2, const GemmParams p) {
     constexpr int STAGES = gemm_stages<BN, NA>();
     constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;
     constexpr int B_BYTES = BN * GEMM_BK * 2;
@@ -102,13 +107,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
     const int groups_m = (tiles_m + MT - 1) / MT;
     const int tiles_n = p.N / BN;
     const int total_kb = p.K / GEMM_BK;
-    const int nsplit = (total_kb + p.kblocks_per_split - 1) / p.kblocks_per_split;
+    const int total_kb2 = SEG2 ? p.K2 / GEMM_BK : 0;
+    const int nsplit1 = (total_kb + p.kblocks_per_split - 1) / p.kblocks_per_split;
+    const int nsplit2 = SEG2 ? (total_kb2 + p.kblocks2_per_split - 1) / p.kblocks2_per_split : 0;
+    const int nsplit = nsplit1 > nsplit2 ? nsplit1 : nsplit2;
     const int total_items = groups_m * tiles_n * nsplit;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA_hi);
         if (NA == 2) prefetch_tmap(&tmA_lo);
         prefetch_tmap(&tmB);
+        if (SEG2) { prefetch_tmap(&tmA2); prefetch_tmap(&tmB2); }
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
         fence_barrier_init();
@@ -133,7 +142,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
             uint32_t it = 0;
             for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
                 const int mg = item % groups_m, nt = (item / groups_m) % tiles_n, sp = item / (groups_m * tiles_n);
-                const int kb0 = sp * p.kblocks_per_split, kb1 = min(total_kb, kb0 + p.kblocks_per_split);
+                const int kb0 = min(total_kb, sp * p.kblocks_per_split), kb1 = min(total_kb, kb0 + p.kblocks_per_split);
                 for (int j = 0; j < MT; ++j) {
                     const int mt = mg * MT + j;
                     if (mt >= tiles_m) break;
@@ -147,6 +156,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
                         if (NA == 2) tma_load_2d_hint(st + A_BYTES, &tmA_lo, &full_bar[s], kb * GEMM_BK, mt * GEMM_BM, kEvictFirst);
                         tma_load_2d_hint(st + NA * A_BYTES, &tmB, &full_bar[s], kb * GEMM_BK, nt * BN, kEvictLast);
                     }
+                    if (SEG2) {
+                        const int kc0 = min(total_kb2, sp * p.kblocks2_per_split), kc1 = min(total_kb2, kc0 + p.kblocks2_per_split);
+                        for (int kb = kc0; kb < kc1; ++kb, ++it) {
+                            const int s = it % STAGES;
+                            const uint32_t ph = (it / STAGES) & 1;
+                            mbar_wait(&empty_bar[s], ph ^ 1);
+                            uint8_t* st = smem + s * STAGE_BYTES;
+                            mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+                            tma_load_2d_hint(st, &tmA2, &full_bar[s], kb * GEMM_BK, mt * GEMM_BM, kEvictFirst);
+                            tma_load_2d_hint(st + NA * A_BYTES, &tmB2, &full_bar[s], kb * GEMM_BK, nt * BN, kEvictLast);
+                        }
+                    }
                 }
             }
         }
@@ -157,13 +178,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
             uint32_t it = 0, li = 0;
             for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
                 const int mg = item % groups_m, sp = item / (groups_m * tiles_n);
-                const int kb0 = sp * p.kblocks_per_split, kb1 = min(total_kb, kb0 + p.kblocks_per_split);
+                const int kb0 = min(total_kb, sp * p.kblocks_per_split), kb1 = min(total_kb, kb0 + p.kblocks_per_split);
                 const uint32_t as = li & 1, aph = (li >> 1) & 1;
                 mbar_wait(&tmem_empty_bar[as], aph ^ 1);     // epilogue has drained this accumulator stage
                 tc_fence_after();
                 for (int j = 0; j < MT; ++j) {
                     if (mg * MT + j >= tiles_m) break;
                     const uint32_t d_tmem = tmem_base + as * ACC_COLS + j * BN;
+                    uint32_t acc = 0;                           // 0 for the very first MMA of the tile
                     for (int kb = kb0; kb < kb1; ++kb, ++it) {
                         const int s = it % STAGES;
                         const uint32_t ph = (it / STAGES) & 1;
@@ -174,10 +196,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
 #pragma unroll
                         for (int k = 0; k < GEMM_BK / 16; ++k) {
                             const uint64_t bd = make_desc_k_sw128(b_ad + k * 32);
-                            umma_bf16(d_tmem, make_desc_k_sw128(a_hi + k * 32), bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                            umma_bf16(d_tmem, make_desc_k_sw128(a_hi + k * 32), bd, idesc, acc);
+                            acc = 1u;
                             if (NA == 2) umma_bf16(d_tmem, make_desc_k_sw128(a_hi + A_BYTES + k * 32), bd, idesc, 1u);
                         }
                         umma_commit(&empty_bar[s]);          // frees the smem stage when these MMAs have read it
+                    }
+                    if (SEG2) {
+                        const int kc0 = min(total_kb2, sp * p.kblocks2_per_split), kc1 = min(total_kb2, kc0 + p.kblocks2_per_split);
+                        for (int kb = kc0; kb < kc1; ++kb, ++it) {
+                            const int s = it % STAGES;
+                            const uint32_t ph = (it / STAGES) & 1;
+                            mbar_wait(&full_bar[s], ph);
+                            tc_fence_after();
+                            const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES);
+                            const uint32_t b_ad = a_hi + NA * A_BYTES;
+#pragma unroll
+                            for (int k = 0; k < GEMM_BK / 16; ++k) {
+                                umma_bf16(d_tmem, make_desc_k_sw128(a_hi + k * 32), make_desc_k_sw128(b_ad + k * 32), idesc, acc);
+                                acc = 1u;
+                            }
+                            umma_commit(&empty_bar[s]);
+                        }
                     }
                 }
                 umma_commit(&tmem_full_bar[as]);             // accumulator stage complete

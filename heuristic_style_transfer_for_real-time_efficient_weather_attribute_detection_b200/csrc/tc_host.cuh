@@ -3,6 +3,7 @@
 #pragma once
 
 #include <atomic>
+#include <cstring>
 
 #include "pmg_common.cuh"
 #include "tc_gemm.cuh"
@@ -25,6 +26,40 @@ inline EncodeTiledFn encode_fn() {
         return reinterpret_cast<EncodeTiledFn>(p);
     }();
     return fn;
+}
+
+// A tensor map is a pure function of (base pointer, dims, strides, box, element strides, swizzle): memoise it.  One forward
+// needs 8 maps and the driver's encode call costs several microseconds each — more than the launches themselves at B = 1.
+// The cache is thread-local (no locking, re-entrant per thread) and direct-mapped; a miss just re-encodes.
+struct TmapKey {
+    uint64_t base, dims[4], strides[3];
+    uint32_t box[4], estr[4], rank, swizzle;
+    bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct alignas(64) TmapSlot { CUtensorMap map; TmapKey key; bool valid; };
+constexpr int kTmapSlots = 256;
+
+inline int encode_tmap_cached(CUtensorMap* m, uint32_t rank, const void* base, const cuuint64_t* dims, const cuuint64_t* strides,
+                              const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapSwizzle swizzle, const char* what) {
+    thread_local TmapSlot* slots = nullptr;
+    if (!slots) slots = new TmapSlot[kTmapSlots]();      // lives as long as the thread (24 KB)
+    TmapKey k;
+    memset(&k, 0, sizeof(k));
+    k.base = reinterpret_cast<uint64_t>(base); k.rank = rank; k.swizzle = (uint32_t)swizzle;
+    for (uint32_t i = 0; i < rank; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; k.estr[i] = estr[i]; }
+    for (uint32_t i = 0; i + 1 < rank; ++i) k.strides[i] = strides[i];
+    uint64_t h = 0xcbf29ce484222325ull;
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(&k);
+    for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) { h ^= w[i]; h *= 0x100000001b3ull; h ^= h >> 29; }
+    TmapSlot& s = slots[h % kTmapSlots];
+    if (s.valid && s.key == k) { *m = s.map; return PMG_OK; }
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { pmg::set_cuda_error(cudaErrorNotSupported, "cuTensorMapEncodeTiled entry point"); return PMG_ERR_CUDA; }
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { pmg::set_cuda_error(cudaErrorInvalidValue, what); return PMG_ERR_CUDA; }
+    s.map = *m; s.key = k; s.valid = true;
+    return PMG_OK;
 }
 
 // launch with programmatic dependent launch enabled (the kernel must call tc::pdl_wait() before touching
@@ -85,17 +120,11 @@ inline int num_sms() {
 // 128-byte swizzle; out-of-bounds rows/cols read as zero.
 inline int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch_elems,
                           uint32_t box_rows) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) { pmg::set_cuda_error(cudaErrorNotSupported, "cuTensorMapEncodeTiled entry point"); return PMG_ERR_CUDA; }
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {pitch_elems * 2};
     cuuint32_t box[2] = {(cuuint32_t)GEMM_BK, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { pmg::set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled"); return PMG_ERR_CUDA; }
-    return PMG_OK;
+    return encode_tmap_cached(m, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B, "cuTensorMapEncodeTiled");
 }
 
 // 4-D view of a bf16 NCHW image batch (B,3,224,224) for the fused front end (tc_front.cuh):
@@ -107,33 +136,21 @@ inline int make_tmap_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint6
 //                           which bounded the whole kernel).  The UMMA descriptor still reads the slab with the
 //                           32-byte swizzle; tc_front.cuh explains how the resulting half swap is absorbed.
 inline int make_tmap_image_rows(CUtensorMap* m, const void* base, int B) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) { pmg::set_cuda_error(cudaErrorNotSupported, "cuTensorMapEncodeTiled entry point"); return PMG_ERR_CUDA; }
     cuuint64_t dims[4] = {224, 14, 16, (cuuint64_t)3 * B};
     cuuint64_t strides[3] = {7168, 448, 100352};
     cuuint32_t box[4] = {224, 8, 4, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { pmg::set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(image rows)"); return PMG_ERR_CUDA; }
-    return PMG_OK;
+    return encode_tmap_cached(m, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_NONE, "cuTensorMapEncodeTiled(image rows)");
 }
 
 // 4-D view of an NHWC bf16 activation plane (B, H, W, C) for the implicit-GEMM convolution (tc_igemm.cuh): one box =
 // 64 channels × Wo pixels (every `stride`-th) × bh rows (every `stride`-th) × nb images, 128-byte swizzle, zero OOB fill.
 inline int make_tmap_act4d(CUtensorMap* m, const void* base, int B, int H, int W, int C, int stride, int Wo, int bh, int nb) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) { pmg::set_cuda_error(cudaErrorNotSupported, "cuTensorMapEncodeTiled entry point"); return PMG_ERR_CUDA; }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)(stride * Wo), (cuuint32_t)(stride * bh), (cuuint32_t)nb};
     cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { pmg::set_cuda_error(cudaErrorInvalidValue, "cuTensorMapEncodeTiled(act 4d)"); return PMG_ERR_CUDA; }
-    return PMG_OK;
+    return encode_tmap_cached(m, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B, "cuTensorMapEncodeTiled(act 4d)");
 }
 
 // conv k4 p1 stride s of NHWC hi/lo planes (B,H,W,C) with weights [N][16·C] ((ky,kx,c) order) → out fp32 [B·Ho·Wo, N] + bias
@@ -171,29 +188,45 @@ inline int launch_conv_igemm(const void* act_hi, const void* act_lo, const void*
 
 // A: [M, K] bf16 planes (lo may be null ⇒ single plane), pitch lda; B: [N, K] bf16, pitch ldb.
 // k_cols = columns that really exist in memory (≤ K); TMA zero-fills [k_cols, K) — used for conv0's K = 48.
-template <int BN, int NA, int EPI, int ACT>
+// SEG2: a second K segment (A2 [M, K2] one plane, pitch lda; B2 [N, K2], pitch K2) accumulated into the same tiles.
+template <int BN, int NA, int EPI, int ACT, bool SEG2 = false>
 int launch_gemm_t(const void* A_hi, const void* A_lo, int lda, const void* B, int ldb, GemmParams p, int splits,
-                  int k_cols, cudaStream_t st) {
+                  int k_cols, cudaStream_t st, const void* A2 = nullptr, const void* B2 = nullptr, int K2 = 0) {
     if (p.K % GEMM_BK || p.N % BN || p.M < 1 || splits < 1 || k_cols > p.K || k_cols < 1 || p.N > GEMM_MAX_N)
         return PMG_ERR_BAD_SHAPE;
-    CUtensorMap ta_hi, ta_lo, tb;
+    if (SEG2 && (!A2 || !B2 || K2 < GEMM_BK || K2 % GEMM_BK)) return PMG_ERR_BAD_SHAPE;
+    CUtensorMap ta_hi, ta_lo, tb, ta2, tb2;
     int rc;
     if ((rc = make_tmap_bf16(&ta_hi, A_hi, p.M, k_cols, lda, GEMM_BM))) return rc;
     if ((rc = make_tmap_bf16(&ta_lo, NA == 2 ? A_lo : A_hi, p.M, k_cols, lda, GEMM_BM))) return rc;
     if ((rc = make_tmap_bf16(&tb, B, p.N, k_cols, ldb, BN))) return rc;
+    if (SEG2) {
+        if ((rc = make_tmap_bf16(&ta2, A2, p.M, K2, lda, GEMM_BM))) return rc;
+        if ((rc = make_tmap_bf16(&tb2, B2, p.N, K2, K2, BN))) return rc;
+    } else {
+        ta2 = ta_hi; tb2 = tb;
+    }
     const int total_kb = p.K / GEMM_BK;
     p.kblocks_per_split = (total_kb + splits - 1) / splits;
-    const int eff_splits = (total_kb + p.kblocks_per_split - 1) / p.kblocks_per_split;
+    int eff_splits = (total_kb + p.kblocks_per_split - 1) / p.kblocks_per_split;
+    p.K2 = 0; p.kblocks2_per_split = 1;
+    if (SEG2) {
+        const int total_kb2 = K2 / GEMM_BK;
+        p.K2 = K2;
+        p.kblocks2_per_split = (total_kb2 + splits - 1) / splits;
+        const int eff2 = (total_kb2 + p.kblocks2_per_split - 1) / p.kblocks2_per_split;
+        if (eff2 > eff_splits) eff_splits = eff2;
+    }
     constexpr int smem = gemm_smem_bytes<BN, NA>();
     static PerDeviceFlag attr_set;
     if (!attr_set.test()) {
-        PMG_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, NA, EPI, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "gemm smem attr");
+        PMG_CUDA_OK(cudaFuncSetAttribute(gemm_kernel<BN, NA, EPI, ACT, SEG2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "gemm smem attr");
         attr_set.set();
     }
     const int tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
     const int items = ((tiles_m + gemm_mt<BN>() - 1) / gemm_mt<BN>()) * eff_splits * (p.N / BN);
     const int grid = items < num_sms() ? items : num_sms();
-    PMG_CUDA_OK(launch_pdl(gemm_kernel<BN, NA, EPI, ACT>, dim3(grid), dim3(GEMM_THREADS), smem, st, ta_hi, ta_lo, tb, p), "tc gemm");
+    PMG_CUDA_OK(launch_pdl(gemm_kernel<BN, NA, EPI, ACT, SEG2>, dim3(grid), dim3(GEMM_THREADS), smem, st, ta_hi, ta_lo, tb, ta2, tb2, p), "tc gemm");
     return PMG_OK;
 }
 
@@ -226,11 +259,16 @@ int launch_gemm2_t(const void* A_hi, const void* A_lo, int lda, const void* B, i
     return PMG_OK;
 }
 
-// number of split-K partial buffers launch_gemm_t will actually write for (K, splits)
-inline int effective_splits(int K, int splits) {
+// number of split-K partial buffers launch_gemm_t will actually write for (K, splits) [and a second segment K2]
+inline int effective_splits(int K, int splits, int K2 = 0) {
     const int total_kb = K / GEMM_BK;
     const int per = (total_kb + splits - 1) / splits;
-    return (total_kb + per - 1) / per;
+    int eff = (total_kb + per - 1) / per;
+    if (K2 > 0) {
+        const int kb2 = K2 / GEMM_BK, per2 = (kb2 + splits - 1) / splits, eff2 = (kb2 + per2 - 1) / per2;
+        if (eff2 > eff) eff = eff2;
+    }
+    return eff;
 }
 
 }  // namespace tc

@@ -293,63 +293,129 @@ class HostPipeline:
     This is the call the end-to-end bench times; the reference's equivalent is the
     ``inputs.to(device)`` → ``model(inputs)`` → ``.cpu()`` loop of Functions/PMG_evaluation.py:124-150."""
 
-    def __init__(self, model, chunk: int = 128, device: Optional[torch.device] = None, u8_layout: str = "NHWC"):
+    def __init__(self, model, chunk: int = 128, device: Optional[torch.device] = None, u8_layout: str = "NHWC",
+                 tail_chunk: int = 32):
         """``x_host`` may be the normalised float batch (B,3,H,W) fp32 / bf16 — what the reference's loaders deliver — or
         the decoded uint8 images, (B,H,W,3) for ``u8_layout="NHWC"`` / (B,3,H,W) for "NCHW": then ToTensor + Normalize
-        (utils/datasets_utils.py:212-214) run on the GPU (prepost.preprocess_u8) and only 150 KB/image cross PCIe."""
+        (utils/datasets_utils.py:212-214) run on the GPU (prepost.preprocess_u8) and only 150 KB/image cross PCIe.
+
+        The wire is the bottleneck, so what a call adds to the bare copy time is the forward of the LAST chunk (nothing is
+        left to overlap it with): the last ``chunk`` images go out in halving pieces down to ``tail_chunk``."""
         self.model = model
         self.u8_layout = u8_layout
-        self._pre = [None, None]
         self.chunk = int(chunk)
+        self.tail_chunk = max(1, min(int(tail_chunk), self.chunk))
         self.device = device or next(model.parameters()).device
         self.copy_stream = torch.cuda.Stream(self.device)
         self.compute_stream = torch.cuda.Stream(self.device)
         self._dev = [None, None]
-        self._out = None
+        self._pre = [None, None]
+        self._consumed = [None, None]          # compute has finished reading device buffer i (persists across calls)
+        self._nchunk = 0                       # chunks enqueued so far (buffer parity runs across calls)
+        self._outs = [None, None]              # pinned result buffers, alternating per call
+        self._done = [None, None]
+        self._ncall = 0
+        self._pending = []                     # tickets submitted and not yet collected
+        self._pending_B = {}
+
+    def _schedule(self, B: int):
+        """[(lo, hi)] — uniform chunks, the last one split into halving pieces (…, 64, 32, 32)."""
+        edges, lo = [], 0
+        while B - lo > self.chunk:
+            edges.append((lo, lo + self.chunk))
+            lo += self.chunk
+        rest = B - lo
+        while rest > 2 * self.tail_chunk:
+            step = rest // 2
+            edges.append((lo, lo + step))
+            lo += step
+            rest -= step
+        if rest > self.tail_chunk:
+            edges.append((lo, lo + rest - self.tail_chunk))
+            lo += rest - self.tail_chunk
+            rest = self.tail_chunk
+        if rest:
+            edges.append((lo, lo + rest))
+        return edges
+
+    def _enqueue(self, x_host: torch.Tensor) -> int:
+        assert x_host.device.type == "cpu" and x_host.is_pinned(), "pass a pinned host tensor"
+        B = x_host.shape[0]
+        L = self.model._n_logits
+        slot = self._ncall & 1
+        assert slot not in [t & 1 for t in self._pending], "collect() the result submitted two calls ago first"
+        if self._outs[slot] is None or self._outs[slot].shape[0] < B:
+            self._outs[slot] = torch.empty((B, L), dtype=torch.float32).pin_memory()
+        out = self._outs[slot]
+        shape = (self.chunk,) + tuple(x_host.shape[1:])
+        for i in range(2):
+            if self._dev[i] is None or self._dev[i].shape != shape or self._dev[i].dtype != x_host.dtype:
+                if self._consumed[i] is not None:
+                    self._consumed[i].synchronize()
+                self._dev[i] = torch.empty(shape, dtype=x_host.dtype, device=self.device)
+        cur = torch.cuda.current_stream(self.device)
+        self.copy_stream.wait_stream(cur)
+        self.compute_stream.wait_stream(cur)
+        for lo, hi in self._schedule(B):
+            k = self._nchunk & 1
+            self._nchunk += 1
+            buf = self._dev[k]
+            copied = torch.cuda.Event()
+            with torch.cuda.stream(self.copy_stream):
+                if self._consumed[k] is not None:
+                    self.copy_stream.wait_event(self._consumed[k])
+                buf[: hi - lo].copy_(x_host[lo:hi], non_blocking=True)
+                copied.record(self.copy_stream)
+            with torch.cuda.stream(self.compute_stream):
+                self.compute_stream.wait_event(copied)
+                xin = buf[: hi - lo]
+                if xin.dtype == torch.uint8:
+                    from . import prepost
+                    n, hh, ww = (xin.shape[0], xin.shape[1], xin.shape[2]) if self.u8_layout == "NHWC" else (xin.shape[0], xin.shape[2], xin.shape[3])
+                    if self._pre[k] is None or self._pre[k].shape[1:] != (3, hh, ww) or self._pre[k].shape[0] < n:
+                        self._pre[k] = torch.empty((self.chunk, 3, hh, ww), dtype=torch.bfloat16, device=self.device)
+                    xin = prepost.preprocess_u8(xin, self.u8_layout, torch.bfloat16, out=self._pre[k][:n])
+                logits = self.model.forward_packed(xin)
+                self._consumed[k] = torch.cuda.Event()
+                self._consumed[k].record(self.compute_stream)
+                out[lo:hi].copy_(logits, non_blocking=True)
+        self._done[slot] = torch.cuda.Event()
+        self._done[slot].record(self.compute_stream)
+        ticket = self._ncall
+        self._ncall += 1
+        self._pending.append(ticket)
+        self._pending_B[ticket] = B
+        return ticket
 
     @torch.no_grad()
     def infer(self, x_host: torch.Tensor, sync: bool = True) -> torch.Tensor:
         """Returns the logits in pinned host memory.  ``sync=True`` (default) blocks until the last device→host copy has
         landed, i.e. the returned tensor is readable; ``sync=False`` only orders the current stream after the work."""
-        assert x_host.device.type == "cpu" and x_host.is_pinned(), "pass a pinned host tensor"
-        B = x_host.shape[0]
-        L = self.model._n_logits
-        if self._out is None or self._out.shape[0] < B:
-            self._out = torch.empty((B, L), dtype=torch.float32).pin_memory()
-        shape = (self.chunk,) + tuple(x_host.shape[1:])
-        for i in range(2):
-            if self._dev[i] is None or self._dev[i].shape != shape or self._dev[i].dtype != x_host.dtype:
-                self._dev[i] = torch.empty(shape, dtype=x_host.dtype, device=self.device)
-        n_chunks = (B + self.chunk - 1) // self.chunk
-        copied = [torch.cuda.Event() for _ in range(n_chunks)]
-        consumed = [torch.cuda.Event() for _ in range(n_chunks)]
-        cur = torch.cuda.current_stream(self.device)
-        self.copy_stream.wait_stream(cur)
-        self.compute_stream.wait_stream(cur)
-        for i in range(n_chunks):
-            lo, hi = i * self.chunk, min(B, (i + 1) * self.chunk)
-            buf = self._dev[i & 1]
-            with torch.cuda.stream(self.copy_stream):
-                if i >= 2:
-                    self.copy_stream.wait_event(consumed[i - 2])
-                buf[: hi - lo].copy_(x_host[lo:hi], non_blocking=True)
-                copied[i].record(self.copy_stream)
-            with torch.cuda.stream(self.compute_stream):
-                self.compute_stream.wait_event(copied[i])
-                xin = buf[: hi - lo]
-                if xin.dtype == torch.uint8:
-                    from . import prepost
-                    n, hh, ww = (xin.shape[0], xin.shape[1], xin.shape[2]) if self.u8_layout == "NHWC" else (xin.shape[0], xin.shape[2], xin.shape[3])
-                    if self._pre[i & 1] is None or self._pre[i & 1].shape[1:] != (3, hh, ww) or self._pre[i & 1].shape[0] < n:
-                        self._pre[i & 1] = torch.empty((self.chunk, 3, hh, ww), dtype=torch.bfloat16, device=self.device)
-                    xin = prepost.preprocess_u8(xin, self.u8_layout, torch.bfloat16, out=self._pre[i & 1][:n])
-                logits = self.model.forward_packed(xin)
-                consumed[i].record(self.compute_stream)
-                self._out[lo:hi].copy_(logits, non_blocking=True)
-        cur.wait_stream(self.compute_stream)
+        t = self._enqueue(x_host)
+        self._pending.remove(t)
+        B = self._pending_B.pop(t)
+        torch.cuda.current_stream(self.device).wait_stream(self.compute_stream)
         if sync:
-            self.compute_stream.synchronize()
-        return self._out[:B]
+            self._done[t & 1].synchronize()
+        return self._outs[t & 1][:B]
+
+    @torch.no_grad()
+    def submit(self, x_host: torch.Tensor) -> int:
+        """Streaming form: enqueue a batch and return a ticket without waiting.  At most two batches may be outstanding
+        (two pinned result buffers); the copy engine starts on batch i+1 while the forward of batch i's last chunk and its
+        device→host read are still running, so a loop ``t = submit(next); collect(prev)`` keeps the wire busy all the
+        time.  ``x_host`` must stay untouched until its ticket is collected."""
+        return self._enqueue(x_host)
+
+    def collect(self, ticket: Optional[int] = None) -> torch.Tensor:
+        """Blocks until the batch of ``ticket`` (default: the oldest outstanding one) is in pinned host memory; the
+        returned view is valid until two more batches have been submitted."""
+        if ticket is None:
+            ticket = self._pending[0]
+        self._pending.remove(ticket)
+        B = self._pending_B.pop(ticket)
+        self._done[ticket & 1].synchronize()
+        return self._outs[ticket & 1][:B]
 
 
 class GraphedPMG:

@@ -218,6 +218,11 @@ int pm_feature_shape(const pm_config* cfg, int H, int W, int* Hf, int* Wf, int* 
 int pm_forward(const pm_config* cfg, const void* packed, const void* x, int x_dtype, int B, int H, int W,
                float* logits, float* attn, float* feats, void* workspace, size_t workspace_bytes,
                unsigned flags, pmg_stream_t stream);
+/* Tuning hook (tools/bench_extra.py): images per internal pass of pm_forward (default 128) and passes in flight (1 or 2,
+ * default 2: the second pass runs on an internal stream forked from / joined to `stream` with events, so the HBM-bound
+ * InstanceNorm kernels of one pass overlap the tensor-bound convolutions of the other).  Changes what
+ * pm_workspace_bytes returns.  Process-global; not thread safe. */
+void pm_debug_set_chunking(int chunk, int lanes);
 
 /* Building block of the fast path, exported for unit tests and micro-benchmarks: one tcgen05 + TMA GEMM
  *   out[M,N] (fp32) = (a_hi[M,K] + a_lo[M,K]) · b[N,K]^T      bf16 row-major operands, a_lo may be null

@@ -49,15 +49,15 @@ def test_host_side_queries_committed_config():
     assert _lib.lib.pmg_workspace_bytes(p, 8, 8, 8) == 0          # too small for two k4s4 layers
     assert _lib.lib.pmg_workspace_bytes(p, 0, 224, 224) == 0
     assert _lib.lib.pmg_forward_launch_count(p, 8, 224, 224, _lib.PMG_FLAG_FORCE_GENERIC) == 3 + 3 + 14 + 1
-    # fast path: front | conv2+chan_proj+Gram (one kernel from 96 images up, mid + Gram kernels below) | token_proj ×2 | token stage
+    # fast path: front | conv2+chan_proj+Gram (one kernel from 96 images up, mid + Gram kernels below) | token_proj | token stage
     lc = lambda B, flags=0: _lib.lib.pmg_forward_launch_count(p, B, 224, 224, flags)
-    assert lc(1024) == 5 and lc(96) == 5 and lc(95) == 6 and lc(1) == 6
-    assert lc(1, _lib.PMG_FLAG_ALWAYS_FUSED_MIDGRAM) == 5
-    assert lc(1024, _lib.PMG_FLAG_NO_FUSED_MIDGRAM) == 6
-    assert lc(1024, _lib.PMG_FLAG_NO_FUSED_MID) == 7
-    assert lc(1024, _lib.PMG_FLAG_NO_FUSED_FRONT) == 7
-    assert lc(1024, _lib.PMG_FLAG_COUNT_F32_INPUT) == 6          # fp32 input: the hi/lo plane split in front of the fused kernel
-    assert lc(1024, _lib.PMG_FLAG_COUNT_F32_INPUT | _lib.PMG_FLAG_NO_FUSED_FRONT) == 7
+    assert lc(1024) == 4 and lc(96) == 4 and lc(95) == 5 and lc(1) == 5
+    assert lc(1, _lib.PMG_FLAG_ALWAYS_FUSED_MIDGRAM) == 4
+    assert lc(1024, _lib.PMG_FLAG_NO_FUSED_MIDGRAM) == 5
+    assert lc(1024, _lib.PMG_FLAG_NO_FUSED_MID) == 6
+    assert lc(1024, _lib.PMG_FLAG_NO_FUSED_FRONT) == 6
+    assert lc(1024, _lib.PMG_FLAG_COUNT_F32_INPUT) == 5          # fp32 input: the hi/lo plane split in front of the fused kernel
+    assert lc(1024, _lib.PMG_FLAG_COUNT_F32_INPUT | _lib.PMG_FLAG_NO_FUSED_FRONT) == 6
 
 
 def test_bad_arguments_are_status_codes_not_crashes():

@@ -133,11 +133,11 @@ def test_fused_midgram_matches_two_kernel_path(batch):
     with torch.no_grad():
         fused = m.forward_debug(x)
         plain = m.forward_packed(x).clone()              # no taps, no fp32 Gram: the production call
-        assert m.launches_per_forward(batch) == 5
+        assert m.launches_per_forward(batch) == 4
         m.fused_midgram = False
         two = m.forward_debug(x)
         m.fused_midgram = True
-    assert m.launches_per_forward(batch) == (5 if batch >= 96 else 6)
+    assert m.launches_per_forward(batch) == (4 if batch >= 96 else 5)
     assert torch.equal(fused[0], plain)
     assert rel_fro(fused[1].cpu().numpy(), two[1].cpu().numpy()) <= 1e-6
     assert rel_fro(fused[2]["chan"].cpu().numpy(), two[2]["chan"].cpu().numpy()) <= 1e-6

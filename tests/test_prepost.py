@@ -127,3 +127,31 @@ def test_uint8_host_pipeline_matches_float_path():
         got_c = pipe_c.infer(torch.from_numpy(np.ascontiguousarray(np.transpose(x, (0, 3, 1, 2)))).pin_memory()).clone().numpy()
     torch.cuda.synchronize()
     assert rel_fro(got, ref) <= 1e-6 and rel_fro(got_c, ref) <= 1e-6
+
+
+@pytest.mark.gpu
+def test_host_pipeline_streaming_matches_blocking():
+    """submit()/collect() with two batches outstanding delivers, per ticket, exactly what a blocking infer() of the same
+    batch returns (tail-chunk schedule, alternating device / pinned buffers across calls, ragged batch sizes)."""
+    from helpers import build_model, torch_state_dict
+    from oracle import synth
+    from pmg_b200.runner import HostPipeline
+    _, hp, tasks = load_contract()
+    m = build_model(hp, tasks)
+    m.load_state_dict(torch_state_dict(synth.pmg_state_dict(0, hp, tasks)), strict=True)
+    m.cuda().eval()
+    batches = [torch.from_numpy(_images(10 + i, n, 224, 224)).pin_memory() for i, n in enumerate((37, 64, 5, 70))]
+    pipe = HostPipeline(m, chunk=32, tail_chunk=8)
+    assert sum(b - a for a, b in pipe._schedule(70)) == 70 and pipe._schedule(70)[-1][1] - pipe._schedule(70)[-1][0] <= 8
+    want = [pipe.infer(b).clone() for b in batches]
+    got = []
+    prev = pipe.submit(batches[0])
+    for b in batches[1:]:
+        nxt = pipe.submit(b)
+        got.append(pipe.collect(prev).clone())
+        prev = nxt
+    got.append(pipe.collect(prev).clone())
+    for g, w in zip(got, want):
+        assert g.shape == w.shape and torch.equal(g, w)
+    with pytest.raises(AssertionError):
+        pipe.submit(batches[0]); pipe.submit(batches[1]); pipe.submit(batches[2])

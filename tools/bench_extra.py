@@ -65,22 +65,28 @@ def sweep(quiet=False, iters=40):
     return rows
 
 
-def pm(quiet=False):
+def pm(quiet=False, sweep=False):
+    """PM forward, B = 1024 in ONE call (pm_forward pipelines 128-image passes on two streams internally).
+    sweep=True also times other (images per pass, passes in flight) settings through the tuning hook."""
+    from pmg_b200 import _lib
     tasks = synth.PMG_TASKS
     rows = []
     m = pmg_b200.MultiTaskPatchGAN(tasks_dict=tasks, input_nc=3, ndf=64, norm="instance", patch_size=73, device=torch.device("cuda"), attn_use_se=False)
     m.cuda().eval()
-    B, chunk = 1024, 256
-    x = torch.randn(chunk, 3, 224, 224, device="cuda").to(torch.bfloat16)
+    B = 1024
+    x = torch.randn(B, 3, 224, 224, device="cuda").to(torch.bfloat16)
     def step():
         with torch.no_grad():
-            for _ in range(B // chunk):
-                m(x)
-    ms = ev_time(step, 3, warm=1)
-    v = B / ms * 1e3
-    emit(rows, {"config": "PM forward batch 1024 (BASELINE configs[3]; 4 chunks of 256, random-init weights)", "ms": round(ms, 3),
-                "images_per_s": round(v, 1), "flops_per_image": 5.40e9,
-                "tensor_frac_of_measured": round(v * 5.40e9 / 1e12 / PEAK["bf16_tflops"], 4)}, quiet)
+            m(x)
+    configs = [(128, 2)] + ([(256, 1), (256, 2), (64, 2), (128, 1)] if sweep else [])
+    for chunk, lanes in configs:
+        _lib.lib.pm_debug_set_chunking(chunk, lanes)
+        ms = ev_time(step, 3, warm=1)
+        v = B / ms * 1e3
+        emit(rows, {"config": f"PM forward batch 1024 (BASELINE configs[3]; one call, {chunk}-image passes, {lanes} in flight, random-init weights)",
+                    "ms": round(ms, 3), "images_per_s": round(v, 1), "flops_per_image": 5.40e9,
+                    "tensor_frac_of_measured": round(v * 5.40e9 / 1e12 / PEAK["bf16_tflops"], 4)}, quiet)
+    _lib.lib.pm_debug_set_chunking(128, 2)
     return rows
 
 
@@ -142,4 +148,4 @@ def latency(quiet=False, batches=(1, 8)):
 
 
 if __name__ == "__main__":
-    {"sweep": sweep, "pm": pm, "gram": gram, "latency": latency}[sys.argv[1]]()
+    {"sweep": sweep, "pm": pm, "pm_sweep": lambda: pm(sweep=True), "gram": gram, "latency": latency}[sys.argv[1]]()
