@@ -216,7 +216,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="images per GPU per step")
-    ap.add_argument("--e2e-chunk", type=int, default=128)
+    ap.add_argument("--e2e-chunk", type=int, default=512, help="largest H2D piece of HostPipeline (the last one is split 256, 128, ... 32)")
     ap.add_argument("--gather-steps", type=int, default=4, help="N>1: steps whose logits share one all_gather")
     ap.add_argument("--nccl-gather", action="store_true", help="N>1: use the NCCL all-gather instead of the peer-memory pull")
     ap.add_argument("--no-cpu-baseline", action="store_true")

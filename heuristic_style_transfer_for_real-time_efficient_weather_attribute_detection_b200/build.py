@@ -48,6 +48,8 @@ def _headers_mtime() -> float:
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
+    extra = os.environ.get("PMG_NVCC_EXTRA", "").split()      # A/B experiments on the GPU box, e.g. "-DENC_ATTN_R3=0"
+    force = force or bool(extra)
     hm = _headers_mtime()
     jobs = []
     objs = []
@@ -59,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(job):
         src, obj = job
-        cmd = [nvcc, *NVCC_FLAGS, "-I", INCLUDE, "-c", src, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-I", INCLUDE, "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode:
             sys.stderr.write(r.stdout + r.stderr)

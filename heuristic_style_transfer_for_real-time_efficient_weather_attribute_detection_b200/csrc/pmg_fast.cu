@@ -677,15 +677,8 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
         for (int t = 0; t < p.ntask; ++t)
             for (int c = p.cls_off[t]; c < p.cls_off[t + 1]; ++c) e.task_of[c] = (unsigned char)t;
         const int tiles = (B + tc::ENC_IPT - 1) / tc::ENC_IPT;
-#if ENC_CLUSTER
-        // CTA pairs share the weight stream (tc_encoder.cuh): an even grid, an odd tile count leaves one dummy tile
-        const int max_grid = tc::num_sms() & ~1;
-        const int grid = tiles + (tiles & 1) < max_grid ? tiles + (tiles & 1) : max_grid;
-        PMG_CUDA_OK(tc::launch_pdl_cluster2(tc::encoder_kernel, dim3(grid), dim3(tc::ENC_THREADS), tc::ENC_SMEM, st, e), "encoder_kernel");
-#else
         const int grid = tiles < tc::num_sms() ? tiles : tc::num_sms();
         PMG_CUDA_OK(tc::launch_pdl(tc::encoder_kernel, dim3(grid), dim3(tc::ENC_THREADS), tc::ENC_SMEM, st, e), "encoder_kernel");
-#endif
         PMG_MARK(tm, "encoder_heads");
         return PMG_OK;
     }

@@ -7,11 +7,11 @@
 // residual stream x of the tile lives in TMEM (columns 0..191, fp32) for the whole kernel: the out-proj and
 // FFN2 MMAs accumulate straight onto it, so the residual adds cost nothing.  Activations that feed an MMA are
 // written by the epilogue warps as two bf16 planes (hi + lo, DESIGN.md "precision") into K-major 128B-swizzled
-// smem operand tiles; all layer weights stream through a 4-stage ring of 24 KB blocks with cp.async.bulk from a
-// pre-swizzled copy (enc_pack_kernel), so one bulk copy lands a ready-to-use UMMA B tile.  The attention output tile
-// O shares its shared memory with the LayerNorm output tile A (same layout; O is written only once every QKV MMA
-// of the layer has read A) — that is what pays for the 4th ring stage: a 24 KB block takes ≈3 k cycles to arrive
-// from L2 while every SM pulls the same lines, so the bytes in flight set the rate at which the MMAs are fed.  Every small parameter
+// smem operand tiles; all layer weights stream through a 3-stage ring of 24 KB blocks with cp.async.bulk from a
+// pre-swizzled copy (enc_pack_kernel), so one bulk copy lands a ready-to-use UMMA B tile.  (A 4th stage — paid for by
+// letting O share A's shared memory — was built and measured in round 2: no change, the MMA thread still waits ≈18-20 k
+// cycles per tile for weights.  148 SMs pulling the same 1.2 MB at once is an aggregate L2 rate of ≈7 TB/s: the supply is
+// bandwidth-bound at the L2, not latency-bound at the ring.)  Every small parameter
 // (biases, LayerNorm affine, task map) is staged in smem once per CTA, before griddepcontrol.wait, so no global
 // load sits on the per-phase critical path.
 //
@@ -36,31 +36,31 @@
 namespace tc {
 
 constexpr int ENC_ATTN_WARPS = 8;
-constexpr int ENC_THREADS = 576;
+constexpr int ENC_THREADS = 576, ENC_W_PROD = 0, ENC_W_MMA = 1, ENC_W_CMP0 = 4;
 constexpr int ENC_IPT = 7;                   // images per tile
 constexpr int ENC_ROWS = 63;                 // token rows per tile
 constexpr int ENC_MAX_LAYERS = 2;            // parameters of every layer stay resident in smem
 constexpr int ENC_STAGE = 24576;             // weight ring stage
-constexpr int ENC_NSTAGE = 4;
+constexpr int ENC_NSTAGE = 3;
 constexpr int ENC_QKV_LD = 148;              // floats per row of the fp32 [q|k|v] head buffer (144 + 4: conflict-free 16-byte row accesses)
 constexpr int ENC_KB = 8192;                 // operand k-block: 64 rows × 128 B
 constexpr int ENC_PLANE = 3 * ENC_KB;        // [64 rows × 192 K] bf16
 constexpr int ENC_OFF_QKV = ENC_NSTAGE * ENC_STAGE;                 // fp32 head buffer; aliased by the FFN hidden tile and the heads result
-constexpr int ENC_QKV_BYTES = 49152;                                // ≥ 64·ENC_QKV_LD·4 (head buffer) and ≥ 63·192·4 (split-K staging of one partial)
+constexpr int ENC_QKV_BYTES = 64 * ENC_QKV_LD * 4;                  // 37,888 = 37 KB
 constexpr int ENC_OFF_A = ENC_OFF_QKV + ENC_QKV_BYTES;              // LN output / final tokens, hi then lo plane
-constexpr int ENC_OFF_O = ENC_OFF_A;                                // attention output: SAME tile (written after the layer's last QKV MMA)
+constexpr int ENC_OFF_O = ENC_OFF_A + 2 * ENC_PLANE;                // attention output, hi then lo plane
 constexpr int ENC_SC_LD = 65;                                       // [64][65] fp32 heads-GEMM result (inside the QKV region)
 // per-layer parameter block (floats): b_in 576 | b_o 192 | b_1 384 | b_2 192 | ln1w | ln1b | ln2w | ln2b (192 each)
 constexpr int ENC_P_BIN = 0, ENC_P_BO = 576, ENC_P_B1 = 768, ENC_P_B2 = 1152, ENC_P_LN1W = 1344, ENC_P_LN1B = 1536,
               ENC_P_LN2W = 1728, ENC_P_LN2B = 1920, ENC_P_LAYER = 2112;
 constexpr int ENC_P_TOKB = ENC_MAX_LAYERS * ENC_P_LAYER, ENC_P_CLSB = ENC_P_TOKB + 192, ENC_P_FLOATS = ENC_P_CLSB + 64;
-constexpr int ENC_OFF_PRM = ENC_OFF_A + 2 * ENC_PLANE;              // also the ≥ 8 KB over-read slack behind the A / O tile
+constexpr int ENC_OFF_PRM = ENC_OFF_O + 2 * ENC_PLANE;              // also the ≥ 8 KB over-read slack behind the O tile
 constexpr int ENC_OFF_TASK = ENC_OFF_PRM + ENC_P_FLOATS * 4;        // task_of[64] bytes
 constexpr int ENC_OFF_RED = ENC_OFF_TASK + 64;                      // LayerNorm partial sums: 2 × [4][64] fp32
 constexpr int ENC_OFF_BAR = ENC_OFF_RED + 2 * 4 * 64 * 4;
 constexpr int ENC_SMEM = ENC_OFF_BAR + 256 + 1024;
 static_assert(ENC_SMEM <= 232448, "token-stage kernel exceeds the 227 KB shared-memory limit");
-static_assert(ENC_QKV_BYTES >= 64 * ENC_QKV_LD * 4 && ENC_QKV_BYTES >= 63 * 192 * 4 && ENC_QKV_BYTES % 1024 == 0, "head buffer / staging");
+static_assert(ENC_OFF_QKV % 1024 == 0 && ENC_OFF_A % 1024 == 0 && ENC_OFF_O % 1024 == 0 && ENC_OFF_PRM % 16 == 0, "operand tiles need 1024-byte alignment");
 
 // weight stream geometry (bytes), per layer, in the order the MMA warp consumes it
 constexpr int ENC_QKV_BLK = 144 * 128;                               // one k-block of one head's [q|k|v] rows
@@ -194,7 +194,10 @@ __device__ __forceinline__ float fast_rcp(float x) {
 // 9-token attention core of one head out of the fp32 [q|k|v] head buffer (models_PMG.py:64: nn.MultiheadAttention,
 // 4 heads × 48, scale 1/sqrt(48) folded into q together with log2 e) on the eight aux warps: a thread owns ONE query row
 // × 12 of the head's 48 dims (4 lanes per row, 8 rows per warp); the 4 lanes of a row sum their partial q·k with two
-// xor-shuffles.  (Round 1 ran three rows per thread on three warps, two of them on one SM sub-partition.)
+// xor-shuffles: 2.85 k cycles per head.  Measured alternatives: three rows per thread on three warps (round 1; two of the
+// warps share a sub-partition) 3.1 k; three rows per thread with packed FFMA2 on four warps (a third of the LDS traffic, 16
+// warps and 128 registers for the kernel) 3.45 k — two warps per sub-partition cannot hide the dependent LDS → FMA → shuffle
+// → exp chains.
 // ------------------------------------------------------------------------------------------------
 struct AttnCtx1 {
     const float* qp; const float* kp; const float* vp;
@@ -274,7 +277,6 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
     float* sQKV = reinterpret_cast<float*>(smem + ENC_OFF_QKV);
     uint8_t* sH = smem + ENC_OFF_QKV;               // FFN hidden tile [plane hi/lo][kb 2] × 8 KB (FFN phase only)
     float* sSC = reinterpret_cast<float*>(smem + ENC_OFF_QKV);   // heads result (after the last layer only)
-    uint8_t* sStage2 = smem + ENC_OFF_QKV;          // split-K staging of the second partial (first phase of a tile only)
     uint8_t* sA = smem + ENC_OFF_A;
     uint8_t* sO = smem + ENC_OFF_O;
     float* sPrm = reinterpret_cast<float*>(smem + ENC_OFF_PRM);
@@ -296,8 +298,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
     uint64_t* h_ready = bb + 13;
     uint64_t* h_free = bb + 14;
     uint64_t* sc_full = bb + 15;
-    uint64_t* qkv_done = bb + 16;       // every QKV MMA of the layer has completed: the A tile may be overwritten by O
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bb + 17);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bb + 16);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int wq = warp & 3;
@@ -312,10 +313,10 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
             mbar_init(&dh_full[i], 1); mbar_init(&dh_empty[i], 8);
         }
         mbar_init(h_ready, 8); mbar_init(h_free, 1);
-        mbar_init(qkv_full, 6); mbar_init(qkv_empty, ENC_ATTN_WARPS); mbar_init(o_ready, 4 * ENC_ATTN_WARPS); mbar_init(x_full, 1); mbar_init(sc_full, 1); mbar_init(qkv_done, 1);
+        mbar_init(qkv_full, 6); mbar_init(qkv_empty, ENC_ATTN_WARPS); mbar_init(o_ready, 4 * ENC_ATTN_WARPS); mbar_init(x_full, 1); mbar_init(sc_full, 1);
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    if (warp == ENC_W_MMA) tmem_alloc(tmem_slot, 512);
     // parameters are constants of the model: stage them before waiting for the previous kernel
     for (int l = 0; l < p.nl; ++l) {
         const EncLayerPtrs& lp = p.layer[l];
@@ -339,7 +340,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
     const uint32_t tmem_base = *tmem_slot;
     pdl_trigger();
 
-    if (warp == 0) {
+    if (warp == ENC_W_PROD) {
         // ===================== weight producer =====================
         if (elect_one()) {      // one elected thread; elect.sync keeps the branch warp-uniform for ptxas
             uint32_t wi = 0;
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                 load((size_t)p.nl * ENC_LAYER_BYTES, ENC_STAGE);
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == ENC_W_MMA) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
             constexpr uint32_t id144 = make_idesc_bf16(128, 144, 0, 0);
@@ -421,7 +422,6 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                         umma_commit(&dq_full[b]);
                         ENC_T(2 + 40 * l + h);
                     }
-                    umma_commit(qkv_done);
                     mbar_wait(o_ready, no & 1); ++no;                          // x += O · Woᵀ
                     tc_fence_after();
                     ENC_T(6 + 40 * l);
@@ -466,9 +466,9 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
             }
             if (p.trace && blockIdx.x == 0) p.trace[250] = w_wait;
         }
-    } else if (warp >= 4 && wq < 2) {
+    } else if (warp >= ENC_W_CMP0 && wq < 2) {
         // ===================== compute warps: TMEM <-> registers, LayerNorm, epilogues =====================
-        const int q = wq, g = (warp - 4) >> 2, m = q * 32 + lane;
+        const int q = wq, g = (warp - ENC_W_CMP0) >> 2, m = q * 32 + lane;
         const int ct = g * 64 + m;                                  // 0..255
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         const uint32_t tX = tmem_base + lane_addr + 48 * g;         // this thread's slice of the residual stream
@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
         uint32_t hq = 0, nx = 0, hc = 0, nsc = 0;
         float v[48];
         pdl_wait();                                                 // partial sums come from the token_proj kernel
-        const bool tr = (warp == 4 && lane == 0);
+        const bool tr = (warp == ENC_W_CMP0 && lane == 0);
 #define ENC_TC(slot) do { if (tr) ENC_T(slot); } while (0)
         ENC_TC(100);
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
             const bool valid = m < ENC_ROWS && grow < T;
             // ---- x0 = Σ_s partial[s] + bias (token_proj epilogue, models_PMG.py:193) ----
             // the 256 compute threads pull the tile's [63 × 192] fp32 block of two split-K partials at a time with
-            // 16-byte cp.async into the (idle) A / O tile and head-buffer regions, chunk-swizzled per row; then every thread adds up
+            // 16-byte cp.async into the (idle) O and A regions, chunk-swizzled per row; then every thread adds up
             // its own 48-column slice.  One global round trip, no registers held across it.
             {
 #pragma unroll
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                         const uint32_t so = (uint32_t)(r * 48 + (c4 ^ (r & 7))) * 16;
                         const float* src = p.partial + (size_t)s0 * p.pstride + (ok ? (size_t)gr * 192 + 4 * c4 : 0);
                         cp_async16(sO + so, src, ok ? 16u : 0u);
-                        if (nb == 2) cp_async16(sStage2 + so, src + p.pstride, ok ? 16u : 0u);
+                        if (nb == 2) cp_async16(sA + so, src + p.pstride, ok ? 16u : 0u);
                     }
                     cp_async_wait_all();
                     named_bar_sync(1, 256);
@@ -512,7 +512,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                         const float4 a = *reinterpret_cast<const float4*>(sO + so);
                         v[4 * j] += a.x; v[4 * j + 1] += a.y; v[4 * j + 2] += a.z; v[4 * j + 3] += a.w;
                         if (nb == 2) {
-                            const float4 c = *reinterpret_cast<const float4*>(sStage2 + so);
+                            const float4 c = *reinterpret_cast<const float4*>(sA + so);
                             v[4 * j] += c.x; v[4 * j + 1] += c.y; v[4 * j + 2] += c.z; v[4 * j + 3] += c.w;
                         }
                     }
@@ -669,40 +669,28 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
         }
         tc_fence_before();
     } else if (warp >= 2 && wq >= 2) {
-        // ===================== aux warps: the attention core =====================
-        // O shares the A tile: nothing may be stored before the layer's last QKV MMA has read A (qkv_done).  Head 0
-        // finishes before that, so its output rows wait in registers and go out together with head 1's.
+        // ===================== all eight aux warps: the attention core =====================
         const AttnCtx1 ac = attn_ctx1(sQKV, (warp >> 2) * 2 + (wq - 2), lane);
         const bool tr = warp == 2 && lane == 0;
-        uint32_t hq = 0, nl_done = 0;
-        float o[12], o0[12];
+        uint32_t hq = 0;
+        float o[12];
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-            for (int l = 0; l < p.nl; ++l, ++nl_done)
+            for (int l = 0; l < p.nl; ++l)
                 for (int h = 0; h < 4; ++h, ++hq) {
                     mbar_wait(qkv_full, hq & 1);
                     if (tr) ENC_T(200 + 40 * l + 2 * h);
                     attention_rows(ac, o, lane);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(qkv_empty);        // every lane of this warp has finished reading the head buffer
-                    if (h == 0) {
-#pragma unroll
-                        for (int i = 0; i < 12; ++i) o0[i] = o[i];
-                    } else {
-                        if (h == 1) {
-                            mbar_wait(qkv_done, nl_done & 1);
-                            tc_fence_after();
-                            store_o_rows(ac, sO, 0, o0);
-                        }
-                        store_o_rows(ac, sO, h, o);
-                        fence_proxy_async();
-                        __syncwarp();
-                        if (lane == 0) { mbar_arrive(o_ready); if (h == 1) mbar_arrive(o_ready); }
-                    }
+                    store_o_rows(ac, sO, h, o);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(o_ready);
                     if (tr) ENC_T(201 + 40 * l + 2 * h);
                 }
     }
     __syncthreads();
-    if (warp == 1) {
+    if (warp == ENC_W_MMA) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }

@@ -293,7 +293,7 @@ class HostPipeline:
     This is the call the end-to-end bench times; the reference's equivalent is the
     ``inputs.to(device)`` → ``model(inputs)`` → ``.cpu()`` loop of Functions/PMG_evaluation.py:124-150."""
 
-    def __init__(self, model, chunk: int = 128, device: Optional[torch.device] = None, u8_layout: str = "NHWC",
+    def __init__(self, model, chunk: int = 512, device: Optional[torch.device] = None, u8_layout: str = "NHWC",
                  tail_chunk: int = 32):
         """``x_host`` may be the normalised float batch (B,3,H,W) fp32 / bf16 — what the reference's loaders deliver — or
         the decoded uint8 images, (B,H,W,3) for ``u8_layout="NHWC"`` / (B,3,H,W) for "NCHW": then ToTensor + Normalize
