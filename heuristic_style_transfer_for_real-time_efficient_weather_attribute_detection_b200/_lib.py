@@ -13,6 +13,8 @@ PMG_F32, PMG_BF16 = 0, 1
 PMG_FLAG_FORCE_GENERIC, PMG_FLAG_FORCE_FAST, PMG_FLAG_NO_FUSED_FRONT, PMG_FLAG_NO_FUSED_ENCODER, PMG_FLAG_NO_FUSED_MID = 1, 2, 4, 8, 16
 PMG_FLAG_NO_FUSED_MIDGRAM, PMG_FLAG_ALWAYS_FUSED_MIDGRAM, PMG_FLAG_COUNT_F32_INPUT = 32, 64, 128
 PM_FLAG_NO_IGEMM = 1
+PM_FLAG_IGEMM_N128 = 2
+PM_FLAG_NO_FUSED_STATS = 4
 
 
 class PmgConfig(C.Structure):

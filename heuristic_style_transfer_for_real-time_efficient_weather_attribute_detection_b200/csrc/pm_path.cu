@@ -220,6 +220,31 @@ __global__ void __launch_bounds__(256) pm_im2col_kernel(const bf16* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------ InstanceNorm
+// normalise + LeakyReLU + hi/lo split of one (sample, 32-channel) slice: a thread owns 4 channels of every 32nd pixel
+__device__ __forceinline__ void pm_normalise_pass(const float* __restrict__ src, const float4 sc, const float4 sh, bf16* __restrict__ o_hi,
+                                                  bf16* __restrict__ o_lo, float* __restrict__ o_f32, size_t obase, int pr, int HW, int C) {
+    auto emit = [&](int pp, const float4& v) {
+        float y0 = fmaf(v.x, sc.x, sh.x), y1 = fmaf(v.y, sc.y, sh.y), y2 = fmaf(v.z, sc.z, sh.z), y3 = fmaf(v.w, sc.w, sh.w);
+        y0 = fmaxf(y0, 0.2f * y0); y1 = fmaxf(y1, 0.2f * y1); y2 = fmaxf(y2, 0.2f * y2); y3 = fmaxf(y3, 0.2f * y3);
+        uint32_t h0, l0, h1, l1;
+        tc::split_bf16x2(y0, y1, h0, l0);
+        tc::split_bf16x2(y2, y3, h1, l1);
+        const size_t o = obase + (size_t)pp * C;
+        *reinterpret_cast<uint2*>(o_hi + o) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(o_lo + o) = make_uint2(l0, l1);
+        if (o_f32) *reinterpret_cast<float4*>(o_f32 + o) = make_float4(y0, y1, y2, y3);
+    };
+    int p = pr;
+    for (; p + 7 * 32 < HW; p += 8 * 32) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const float4*>(src + (size_t)(p + 32 * u) * C);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) emit(p + 32 * u, v[u]);
+    }
+    for (; p < HW; p += 32) emit(p, *reinterpret_cast<const float4*>(src + (size_t)p * C));
+}
+
 // conv (B, HW, C) fp32 → LeakyReLU(IN(conv)) as hi/lo planes (and fp32 on request).  Block = (sample, 32 channels).
 // A thread owns 4 channels (float4) of every 32nd pixel: 8 lanes cover the block's 128-byte channel slice of one pixel,
 // a warp load covers 4 pixels, and 8 independent loads per thread are in flight — the first version (one 4-byte load per
@@ -279,28 +304,61 @@ __global__ void __launch_bounds__(256) pm_instnorm_kernel(const float* __restric
         s_scale[threadIdx.x] = sc; s_shift[threadIdx.x] = sh;
     }
     __syncthreads();
-    const float4 sc = s_scale[threadIdx.x & 7], sh = s_shift[threadIdx.x & 7];
-    const size_t obase = (size_t)b * HW * C + c0 + cl;
-    auto emit = [&](int pp, const float4& v) {
-        float y0 = fmaf(v.x, sc.x, sh.x), y1 = fmaf(v.y, sc.y, sh.y), y2 = fmaf(v.z, sc.z, sh.z), y3 = fmaf(v.w, sc.w, sh.w);
-        y0 = fmaxf(y0, 0.2f * y0); y1 = fmaxf(y1, 0.2f * y1); y2 = fmaxf(y2, 0.2f * y2); y3 = fmaxf(y3, 0.2f * y3);
-        uint32_t h0, l0, h1, l1;
-        tc::split_bf16x2(y0, y1, h0, l0);
-        tc::split_bf16x2(y2, y3, h1, l1);
-        const size_t o = obase + (size_t)pp * C;
-        *reinterpret_cast<uint2*>(o_hi + o) = make_uint2(h0, h1);
-        *reinterpret_cast<uint2*>(o_lo + o) = make_uint2(l0, l1);
-        if (o_f32) *reinterpret_cast<float4*>(o_f32 + o) = make_float4(y0, y1, y2, y3);
-    };
-    p = pr;
-    for (; p + 7 * 32 < HW; p += 8 * 32) {
-        float4 v[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = *reinterpret_cast<const float4*>(src + (size_t)(p + 32 * u) * C);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) emit(p + 32 * u, v[u]);
+    pm_normalise_pass(src, s_scale[threadIdx.x & 7], s_shift[threadIdx.x & 7], o_hi, o_lo, o_f32, (size_t)b * HW * C + c0 + cl, pr, HW, C);
+}
+
+// Same layer with the statistics taken from the convolution's own epilogue (tc_gemm.cuh / tc_igemm.cuh `stats`): every
+// epilogue warp left (mean, Σ(x − mean)²) of its ≤ 32 rows per channel, the tile lying inside one sample.  The block merges
+// the sample's partials in a fixed order (Chan et al. pairwise update: deterministic, no cancellation) and then makes the
+// ONE pass over the fp32 output that normalises it — the separate statistics pass (a full extra read of the output, from
+// HBM for the early layers) is gone.  tiles = M tiles per sample, rows_full / rows_last = rows of a full / the last tile.
+__global__ void __launch_bounds__(256) pm_instnorm_fused_kernel(const float* __restrict__ conv, const float2* __restrict__ stats,
+                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                bf16* __restrict__ o_hi, bf16* __restrict__ o_lo,
+                                                                float* __restrict__ o_f32, int HW, int C, int tiles, int rows_full,
+                                                                int rows_last) {
+    __shared__ float m_n[8][32], m_mean[8][32], m_m2[8][32];
+    __shared__ float4 s_scale[8], s_shift[8];
+    const int b = blockIdx.y, c0 = blockIdx.x * 32;
+    {
+        const int c = threadIdx.x & 31, pw = threadIdx.x >> 5;            // channel, partial phase (one warp per phase)
+        const int n_part = tiles * 4;
+        const float2* src = stats + ((size_t)b * n_part) * C + c0 + c;
+        float n = 0.f, mean = 0.f, m2 = 0.f;
+        for (int i = pw; i < n_part; i += 8) {
+            const int ty = i >> 2, q = i & 3;
+            const int rows = ty < tiles - 1 ? rows_full : rows_last;
+            const int cnt = min(32, max(0, rows - 32 * q));               // warp-uniform
+            if (cnt == 0) continue;
+            const float2 t = src[(size_t)i * C];
+            const float nb = (float)cnt, nn = n + nb, d = t.x - mean;
+            mean += d * (nb / nn);
+            m2 += t.y + d * d * (n * nb / nn);
+            n = nn;
+        }
+        m_n[pw][c] = n; m_mean[pw][c] = mean; m_m2[pw][c] = m2;
     }
-    for (; p < HW; p += 32) emit(p, *reinterpret_cast<const float4*>(src + (size_t)p * C));
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int c = threadIdx.x;
+        float n = 0.f, mean = 0.f, m2 = 0.f;
+        for (int w = 0; w < 8; ++w) {
+            const float nb = m_n[w][c];
+            if (nb == 0.f) continue;
+            const float nn = n + nb, d = m_mean[w][c] - mean;
+            mean += d * (nb / nn);
+            m2 += m_m2[w][c] + d * d * (n * nb / nn);
+            n = nn;
+        }
+        const float var = fmaxf(m2 / (float)HW, 0.f);                     // biased variance (InstanceNorm2d)
+        const float sc = gamma[c0 + c] / sqrtf(var + kInEps);
+        reinterpret_cast<float*>(s_scale)[c] = sc;
+        reinterpret_cast<float*>(s_shift)[c] = beta[c0 + c] - mean * sc;
+    }
+    __syncthreads();
+    const int cl = (threadIdx.x & 7) * 4, pr = threadIdx.x >> 3;
+    pm_normalise_pass(conv + (size_t)b * HW * C + c0 + cl, s_scale[threadIdx.x & 7], s_shift[threadIdx.x & 7], o_hi, o_lo, o_f32,
+                      (size_t)b * HW * C + c0 + cl, pr, HW, C);
 }
 
 // ------------------------------------------------------------------------------------------------ heads finish
@@ -349,22 +407,27 @@ __global__ void __launch_bounds__(128) pm_heads_finish_kernel(const PmFinishArgs
 }
 
 // ------------------------------------------------------------------------------------------------ workspace
-struct PmWs { size_t a_hi, a_lo, conv, act_hi[2], act_lo[2], sc, feats, total; };
+struct PmWs { size_t a_hi, a_lo, conv, act_hi[2], act_lo[2], sc, stats, feats, total; };
 
 static PmWs pm_ws(const PmPlan& p, const PmShape& s, int Bc) {
     PmWs w{};
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t r = o; o = align256(o + bytes); return r; };
-    size_t amax = 0, cmax = 0;
+    size_t amax = 0, cmax = 0, smax = 0;
     for (int l = 0; l < p.n_layers; ++l) {
         const size_t rows = (size_t)Bc * s.h[l + 1] * s.w[l + 1];
         amax = max(amax, rows * p.layer[l].Kp);
         cmax = max(cmax, rows * p.layer[l].cout);
+        // fused InstanceNorm statistics: ≤ 4 (mean, M2) pairs per channel per M tile; an implicit-GEMM tile holds ≥ one
+        // output row of an image, a plain GEMM tile 128 rows
+        const size_t tiles = l == 0 ? (rows + 127) / 128 : (size_t)Bc * s.h[l + 1];
+        smax = max(smax, tiles * 4 * p.layer[l].cout * sizeof(float2));
     }
     w.a_hi = take(amax * 2); w.a_lo = take(amax * 2);
     w.conv = take(cmax * 4);
     for (int i = 0; i < 2; ++i) { w.act_hi[i] = take(cmax * 2); w.act_lo[i] = take(cmax * 2); }
     w.sc = take((size_t)Bc * s.h[p.n_layers] * s.w[p.n_layers] * 64 * 4);
+    w.stats = take(smax);
     w.total = o;
     return w;
 }
@@ -380,11 +443,12 @@ static int pm_gemm(const void* a_hi, const void* a_lo, int Kp, const void* wgt, 
 // N may exceed GEMM_MAX_N (scale/shift staging): run column panels of ≤ 512
 template <int NA>
 static int pm_conv_gemm(const void* a_hi, const void* a_lo, int Kp, const bf16* wgt, int M, int N, float* out, const float* bias,
-                        cudaStream_t st) {
+                        cudaStream_t st, float2* stats = nullptr) {
     for (int n0 = 0; n0 < N; n0 += 512) {
         const int nn = min(512, N - n0);
         tc::GemmParams g{};
         g.M = M; g.N = nn; g.K = Kp; g.epi = tc::EPI_F32; g.act = tc::GACT_NONE; g.ldc = N; g.out_f32 = out + n0; g.shift = bias + n0;
+        g.stats = N <= 512 ? stats : nullptr;          // statistics rows are N wide: single column panel only
         int rc;
         if (nn % 128 == 0) rc = tc::launch_gemm_t<128, NA, tc::EPI_F32, tc::GACT_NONE>(a_hi, a_lo, Kp, wgt + (size_t)n0 * Kp, Kp, g, 1, Kp, st);
         else if (nn % 64 == 0) rc = tc::launch_gemm_t<64, NA, tc::EPI_F32, tc::GACT_NONE>(a_hi, a_lo, Kp, wgt + (size_t)n0 * Kp, Kp, g, 1, Kp, st);
@@ -534,6 +598,9 @@ int pm_forward(const pm_config* cfg, const void* packed, const void* x, int x_dt
             const int Ho = s.h[l + 1], Wo = s.w[l + 1];
             const int rows = Bc * Ho * Wo;
             float* conv = reinterpret_cast<float*>(ws + w.conv);
+            // InstanceNorm statistics from the convolution's own epilogue wherever every M tile lies inside one sample
+            float2* stats = (flags & PM_FLAG_NO_FUSED_STATS) ? nullptr : reinterpret_cast<float2*>(ws + w.stats);
+            int st_tiles = 0, st_rows_full = 128, st_rows_last = 128;
             // layers with ≥ 64 input channels: implicit GEMM straight from the previous layer's NHWC hi/lo planes
             // (tc_igemm.cuh) — no im2col planes are written or re-read.  Layer 0 (3 input channels, NCHW image) keeps
             // im2col + GEMM.
@@ -542,8 +609,10 @@ int pm_forward(const pm_config* cfg, const void* packed, const void* x, int x_dt
             if (igemm) {
                 if ((rc = tc::launch_conv_igemm(Hb(w.act_hi[(l - 1) & 1]), Hb(w.act_lo[(l - 1) & 1]), pk + L.w[l],
                                                 reinterpret_cast<const float*>(pk + L.bias[l]), Bc, s.h[l], s.w[l], y.cin, Ho, Wo,
-                                                y.stride, y.cout, conv, st)))
+                                                y.stride, y.cout, conv, st, (flags & PM_FLAG_IGEMM_N128) != 0, stats, &st_tiles,
+                                                &st_rows_full)))
                     return rc;
+                st_rows_last = Ho * Wo - (st_tiles - 1) * st_rows_full;
             } else {
             const size_t row_smem = (size_t)y.cin * 4 * (s.w[l] + 2) * sizeof(float);
             if (l == 0 && row_smem <= 48 * 1024) {
@@ -563,21 +632,29 @@ int pm_forward(const pm_config* cfg, const void* packed, const void* x, int x_dt
                                                             y.cin, s.h[l], s.w[l], Ho, Wo, y.stride);
             }
             PMG_LAUNCH_OK("pm im2col");
+            // plain GEMM tiles are 128 consecutive rows of [B·Ho·Wo]: inside one sample iff 128 divides Ho·Wo
+            float2* gstats = (stats && (Ho * Wo) % 128 == 0 && y.cout <= 512) ? stats : nullptr;
+            if (gstats) st_tiles = Ho * Wo / 128;
             // a bf16 image is exact in one plane: layer 0 then runs without the (all-zero) lo plane
             if (l == 0 && x_dtype == PMG_BF16)
                 rc = pm_conv_gemm<1>(Hb(w.a_hi), nullptr, y.Kp, reinterpret_cast<const bf16*>(pk + L.w[l]), rows, y.cout, conv,
-                                     reinterpret_cast<const float*>(pk + L.bias[l]), st);
+                                     reinterpret_cast<const float*>(pk + L.bias[l]), st, gstats);
             else
                 rc = pm_conv_gemm<2>(Hb(w.a_hi), Hb(w.a_lo), y.Kp, reinterpret_cast<const bf16*>(pk + L.w[l]), rows, y.cout, conv,
-                                     reinterpret_cast<const float*>(pk + L.bias[l]), st);
+                                     reinterpret_cast<const float*>(pk + L.bias[l]), st, gstats);
             if (rc) return rc;
             }
             const bool last = l == p.n_layers - 1;
-            pm_instnorm_kernel<<<dim3(y.cout / 32, Bc), 256, 0, st>>>(conv, reinterpret_cast<const float*>(pk + L.gamma[l]),
-                                                                      reinterpret_cast<const float*>(pk + L.beta[l]), Hb(w.act_hi[l & 1]),
-                                                                      Hb(w.act_lo[l & 1]),
-                                                                      (last && feats) ? feats + (size_t)b0 * HWf * p.C : nullptr,
-                                                                      Ho * Wo, y.cout);
+            float* f32_out = (last && feats) ? feats + (size_t)b0 * HWf * p.C : nullptr;
+            if (st_tiles > 0)
+                pm_instnorm_fused_kernel<<<dim3(y.cout / 32, Bc), 256, 0, st>>>(conv, stats, reinterpret_cast<const float*>(pk + L.gamma[l]),
+                                                                                reinterpret_cast<const float*>(pk + L.beta[l]),
+                                                                                Hb(w.act_hi[l & 1]), Hb(w.act_lo[l & 1]), f32_out, Ho * Wo,
+                                                                                y.cout, st_tiles, st_rows_full, st_rows_last);
+            else
+                pm_instnorm_kernel<<<dim3(y.cout / 32, Bc), 256, 0, st>>>(conv, reinterpret_cast<const float*>(pk + L.gamma[l]),
+                                                                          reinterpret_cast<const float*>(pk + L.beta[l]), Hb(w.act_hi[l & 1]),
+                                                                          Hb(w.act_lo[l & 1]), f32_out, Ho * Wo, y.cout);
             PMG_LAUNCH_OK("pm instnorm");
         }
         const int lf = (p.n_layers - 1) & 1;

@@ -38,6 +38,7 @@ struct GemmParams {
     // TMEM tile, split like the first one — token_proj's lo-weight term rides in the main GEMM instead of being a second
     // launch with its own partial buffers
     int K2, kblocks2_per_split;
+    float2* stats;            // optional (EPI_F32): per (M tile, epilogue warp q) column statistics [tiles_m·4][N] (mean, M2) of the stored values
 };
 
 constexpr int GEMM_BM = 128;
@@ -287,6 +288,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ 
                     __syncwarp();
                     stage_write_row(wbuf, lane, w);
                     __syncwarp();
+                    if (EPI == EPI_F32 && p.stats)
+                        p.stats[((size_t)(mg * MT + j) * 4 + q) * p.N + nb + lane] =
+                            stage_col_stats(wbuf, lane, min(32, max(0, p.M - ((mg * MT + j) * GEMM_BM + q * 32))));
                     const int row0 = (mg * MT + j) * GEMM_BM + q * 32 + sr;    // + 4·i per store instruction
                     const int rows_left = p.M - row0;                          // row 4i valid ⇔ 4i < rows_left
                     if (EPI == EPI_SPLIT) {

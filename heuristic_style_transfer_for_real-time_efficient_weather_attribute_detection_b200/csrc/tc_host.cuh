@@ -153,9 +153,32 @@ inline int make_tmap_act4d(CUtensorMap* m, const void* base, int B, int H, int W
     return encode_tmap_cached(m, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_128B, "cuTensorMapEncodeTiled(act 4d)");
 }
 
+template <int BN>
+int launch_conv_igemm_t(const void* act_hi, const void* act_lo, const void* wgt, int B, int H, int W, const IgemmParams& p, cudaStream_t st) {
+    CUtensorMap ta_hi, ta_lo, tb;
+    int rc;
+    if ((rc = make_tmap_act4d(&ta_hi, act_hi, B, H, W, p.C, p.stride, p.Wo, p.bh, p.nb))) return rc;
+    if ((rc = make_tmap_act4d(&ta_lo, act_lo, B, H, W, p.C, p.stride, p.Wo, p.bh, p.nb))) return rc;
+    if ((rc = make_tmap_bf16(&tb, wgt, p.N, (uint64_t)16 * p.C, (uint64_t)16 * p.C, BN))) return rc;
+    constexpr int smem = ig_smem_bytes<BN>();
+    static_assert(smem <= 232448, "implicit-GEMM kernel exceeds the 227 KB shared-memory limit");
+    static PerDeviceFlag attr_set;
+    if (!attr_set.test()) {
+        PMG_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "igemm smem attr");
+        attr_set.set();
+    }
+    const long long items = (long long)((p.B + p.nb - 1) / p.nb) * p.tiles_y * (p.N / BN);
+    const int grid = (int)(items < num_sms() ? items : num_sms());
+    conv_igemm_kernel<BN><<<grid, ig_threads<BN>(), smem, st>>>(ta_hi, ta_lo, tb, p);
+    PMG_LAUNCH_OK("conv_igemm");
+    return PMG_OK;
+}
+
 // conv k4 p1 stride s of NHWC hi/lo planes (B,H,W,C) with weights [N][16·C] ((ky,kx,c) order) → out fp32 [B·Ho·Wo, N] + bias
+// narrow = keep the 128-wide N tile even where 256 divides N (A/B measurements)
 inline int launch_conv_igemm(const void* act_hi, const void* act_lo, const void* wgt, const float* bias, int B, int H, int W, int C,
-                             int Ho, int Wo, int stride, int N, float* out, cudaStream_t st) {
+                             int Ho, int Wo, int stride, int N, float* out, cudaStream_t st, bool narrow = false,
+                             float2* stats = nullptr, int* stats_tiles_y = nullptr, int* stats_rows_full = nullptr) {
     if (C % 64 || N % 128 || N > IG_MAX_N || Wo < 1 || Wo > 128 || stride * Wo > 256) return PMG_ERR_UNSUPPORTED;
     // M tile = nb images × bh output rows × Wo ≤ 128 rows: several rows of one image, or one row of several images,
     // whichever leaves fewer of the 128 MMA rows empty over the whole layer
@@ -165,25 +188,16 @@ inline int launch_conv_igemm(const void* act_hi, const void* act_lo, const void*
     const double eff_imgs = (double)B * Wo / (((B + per - 1) / per) * 128.0);
     if (eff_imgs > eff_rows + 1e-9) { bh = 1; nb = per < B ? per : B; }
     if (stride * bh > 256 || nb > 256) return PMG_ERR_UNSUPPORTED;
-    CUtensorMap ta_hi, ta_lo, tb;
-    int rc;
-    if ((rc = make_tmap_act4d(&ta_hi, act_hi, B, H, W, C, stride, Wo, bh, nb))) return rc;
-    if ((rc = make_tmap_act4d(&ta_lo, act_lo, B, H, W, C, stride, Wo, bh, nb))) return rc;
-    if ((rc = make_tmap_bf16(&tb, wgt, N, (uint64_t)16 * C, (uint64_t)16 * C, 128))) return rc;
     IgemmParams p{};
     p.B = B; p.Ho = Ho; p.Wo = Wo; p.bh = bh; p.nb = nb; p.tiles_y = (Ho + bh - 1) / bh; p.C = C; p.N = N; p.stride = stride;
     p.out = out; p.bias = bias;
-    constexpr int smem = ig_smem_bytes<128>();
-    static PerDeviceFlag attr_set;
-    if (!attr_set.test()) {
-        PMG_CUDA_OK(cudaFuncSetAttribute(conv_igemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "igemm smem attr");
-        attr_set.set();
-    }
-    const long long items = (long long)((B + nb - 1) / nb) * p.tiles_y * (N / 128);
-    const int grid = (int)(items < num_sms() ? items : num_sms());
-    conv_igemm_kernel<128><<<grid, IG_THREADS, smem, st>>>(ta_hi, ta_lo, tb, p);
-    PMG_LAUNCH_OK("conv_igemm");
-    return PMG_OK;
+    // fused InstanceNorm statistics need every M tile inside one image; the caller learns the tile geometry (or that it
+    // has to take its statistics from the output itself: *stats_tiles_y = 0)
+    p.stats = nb == 1 ? stats : nullptr;
+    if (stats_tiles_y) *stats_tiles_y = p.stats ? p.tiles_y : 0;
+    if (stats_rows_full) *stats_rows_full = bh * Wo;
+    return (N % 256 == 0 && !narrow) ? launch_conv_igemm_t<256>(act_hi, act_lo, wgt, B, H, W, p, st)
+                                     : launch_conv_igemm_t<128>(act_hi, act_lo, wgt, B, H, W, p, st);
 }
 
 // A: [M, K] bf16 planes (lo may be null ⇒ single plane), pitch lda; B: [N, K] bf16, pitch ldb.

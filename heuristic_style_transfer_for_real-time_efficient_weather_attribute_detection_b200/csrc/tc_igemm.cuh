@@ -23,11 +23,20 @@ struct IgemmParams {
     int C, N, stride;                   // input channels (multiple of 64), output channels (multiple of BN), conv stride
     float* out;                         // [B·Ho·Wo, N] fp32
     const float* bias;                  // [N]
+    float2* stats;                      // optional (nb == 1 only): per (M tile, epilogue warp q) column statistics [tiles_m·4][N] (mean, M2)
 };
 
-constexpr int IG_THREADS = 320;          // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9 = two epilogue groups
 constexpr int IG_STAGES = 3;
 constexpr int IG_MAX_N = 1024;
+// N tile 128: two epilogue groups (warps 2-5 / 6-9), one per accumulator stage.  N tile 256 (layers with ≥ 256 output
+// channels): a k-block stage is A hi + A lo + B = 16 + 16 + 32 KB for 16 MMAs of 128 cycles — 32 B/clk of shared-memory fill
+// instead of the 94 B/clk a 128-wide tile needs to keep the tensor pipe busy (measured: 58-72 % busy, the TMA fill being the
+// limit), and the A boxes are re-fetched for half as many N tiles.  Three 64 KB stages leave room for ONE epilogue group,
+// which drains the two accumulator stages alternately.
+template <int BN>
+__host__ __device__ constexpr int ig_groups() { return BN > 128 ? 1 : 2; }
+template <int BN>
+__host__ __device__ constexpr int ig_threads() { return 64 + 128 * ig_groups<BN>(); }   // warp 0 TMA, warp 1 MMA, then the epilogue groups
 
 __device__ __forceinline__ void tma_load_4d_hint(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1,
                                                  int32_t c2, int32_t c3, uint64_t policy) {
@@ -42,17 +51,20 @@ template <int BN>
 __host__ __device__ constexpr int ig_stage_bytes() { return 2 * 128 * 128 + BN * 128; }
 template <int BN>
 __host__ __device__ constexpr int ig_smem_bytes() {
-    return IG_STAGES * ig_stage_bytes<BN>() + 1024 + 256 + IG_MAX_N * 4 + 8 * 4096;
+    return IG_STAGES * ig_stage_bytes<BN>() + 1024 + 256 + IG_MAX_N * 4 + ig_groups<BN>() * 4 * 4096;
 }
 
 template <int BN>
-__global__ void __launch_bounds__(IG_THREADS, 1)
+__global__ void __launch_bounds__(ig_threads<BN>(), 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                   const __grid_constant__ CUtensorMap tmB, const IgemmParams p) {
     constexpr int A_BYTES = 128 * 128;
     constexpr int B_BYTES = BN * 128;
     constexpr int STAGE_BYTES = ig_stage_bytes<BN>();
-    static_assert(BN == 128 || BN == 64, "accumulator stages are 128 columns apart");
+    static_assert(BN == 256 || BN == 128 || BN == 64, "accumulator stages are 128 (256) columns apart");
+    constexpr int IG_THREADS = ig_threads<BN>();
+    constexpr int NG = ig_groups<BN>();
+    constexpr uint32_t ACC_STRIDE = BN > 128 ? 256 : 128;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -62,7 +74,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
     float* s_bias = reinterpret_cast<float*>(smem + IG_STAGES * STAGE_BYTES + 256);
-    uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_bias + IG_MAX_N);          // 8 × 4 KB
+    uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_bias + IG_MAX_N);          // 4 KB per epilogue warp
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const int tiles_m = ((p.B + p.nb - 1) / p.nb) * p.tiles_y;
@@ -79,7 +91,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 256);
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * ACC_STRIDE);
     for (int i = threadIdx.x; i < p.N; i += IG_THREADS) s_bias[i] = p.bias ? p.bias[i] : 0.f;
     // rows of an A stage beyond the box are read by the MMA (M = 128) without ever being written: clear once
     for (int i = threadIdx.x; i < IG_STAGES * STAGE_BYTES / 16; i += IG_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -118,7 +130,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 const uint32_t as = li & 1, aph = (li >> 1) & 1;
                 mbar_wait(&tmem_empty_bar[as], aph ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * 128;
+                const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
                 for (int kb = 0; kb < total_kb; ++kb, ++it) {
                     const int s = it % IG_STAGES;
                     const uint32_t ph = (it / IG_STAGES) & 1;
@@ -138,7 +150,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
             }
         }
     } else {
-        // ===== epilogue: group g = (warp-2)/4 drains accumulator stage g (items li ≡ g mod 2) =====
+        // ===== epilogue: group g = (warp-2)/4 drains accumulator stage g (items li ≡ g mod 2); a single group drains both =====
         const int q = warp & 3;
         const uint32_t grp = (uint32_t)(warp - 2) >> 2;
         uint8_t* wbuf = s_stage + (warp - 2) * 4096;
@@ -153,15 +165,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
         }
         uint32_t li = 0;
         for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++li) {
-            if ((li & 1) != grp) continue;
+            if (NG == 2 && (li & 1) != grp) continue;
+            const uint32_t as = NG == 2 ? grp : (li & 1);
             const int mt = item % tiles_m, nt = item / tiles_m;
             const int g = mt / p.tiles_y, b = g * p.nb, oy0 = (mt - g * p.tiles_y) * p.bh;
             const int valid_img = min(p.nb, p.B - b);                        // images of this tile that exist
             const int valid_rem = min(p.bh, p.Ho - oy0) * p.Wo;              // rows per image that exist
             const size_t out_row0 = ((size_t)b * p.Ho + oy0) * p.Wo;
-            mbar_wait(&tmem_full_bar[grp], (li >> 1) & 1);
+            mbar_wait(&tmem_full_bar[as], (li >> 1) & 1);
             tc_fence_after();
-            const uint32_t t_addr = tmem_base + grp * 128 + ((uint32_t)(q * 32) << 16);
+            const uint32_t t_addr = tmem_base + as * ACC_STRIDE + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t r[32];
@@ -170,7 +183,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 if (c0 + 32 >= BN) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty_bar[grp]);
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
                 }
                 const int nb = nt * BN + c0;
                 uint32_t w[32];
@@ -183,6 +196,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
                 __syncwarp();
                 stage_write_row(wbuf, lane, w);
                 __syncwarp();
+                if (p.stats)      // rows 32q.. of the tile that exist (nb == 1: the tile lies inside one image)
+                    p.stats[((size_t)mt * 4 + q) * p.N + nb + lane] = stage_col_stats(wbuf, lane, min(32, max(0, valid_rem - q * 32)));
                 float* dst = p.out + out_row0 * (size_t)p.N + nb + sc * 4;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -198,7 +213,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_const
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc(tmem_base, 2 * ACC_STRIDE);
     }
 }
 

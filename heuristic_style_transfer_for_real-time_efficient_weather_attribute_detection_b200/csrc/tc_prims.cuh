@@ -245,6 +245,30 @@ __device__ __forceinline__ void stage_write_row(uint8_t* wbuf, int lane, const u
     for (int c = 0; c < 8; ++c)
         *reinterpret_cast<uint4*>(wbuf + lane * 128 + ((c ^ (lane & 7)) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
 }
+// Per-column statistics of the staged 32-row × 32-column fp32 tile (lane = column; conflict-free thanks to the chunk swizzle):
+// mean and Σ(x − mean)² of the first nvalid rows, two passes over values held in registers.  InstanceNorm of the PM trunk
+// merges these per-warp partials (Chan et al.) instead of re-reading the whole convolution output for its statistics.
+__device__ __forceinline__ float2 stage_col_stats(const uint8_t* wbuf, int lane, int nvalid) {
+    float v[32];
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr)
+        v[rr] = *reinterpret_cast<const float*>(wbuf + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4) + (lane & 3) * 4);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < 32; rr += 4) {
+        s0 += rr < nvalid ? v[rr] : 0.f; s1 += rr + 1 < nvalid ? v[rr + 1] : 0.f;
+        s2 += rr + 2 < nvalid ? v[rr + 2] : 0.f; s3 += rr + 3 < nvalid ? v[rr + 3] : 0.f;
+    }
+    const float mean = nvalid > 0 ? ((s0 + s1) + (s2 + s3)) / (float)nvalid : 0.f;
+    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < 32; rr += 4) {
+        const float d0 = rr < nvalid ? v[rr] - mean : 0.f, d1 = rr + 1 < nvalid ? v[rr + 1] - mean : 0.f;
+        const float d2 = rr + 2 < nvalid ? v[rr + 2] - mean : 0.f, d3 = rr + 3 < nvalid ? v[rr + 3] - mean : 0.f;
+        q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+    }
+    return make_float2(mean, (q0 + q1) + (q2 + q3));
+}
 __device__ __forceinline__ uint4 stage_read(const uint8_t* wbuf, int lane, int i, int& r, int& c) {
     r = 4 * i + (lane >> 3);
     c = lane & 7;

@@ -180,7 +180,9 @@ class MultiTaskPatchGAN(nn.Module):
                                      attn.data_ptr() if attn is not None else None,
                                      feats.data_ptr() if feats is not None else None,
                                      self._ws.data_ptr(), self._ws.numel(),
-                                     0 if getattr(self, "implicit_gemm", True) else _lib.PM_FLAG_NO_IGEMM, stream)
+                                     (0 if getattr(self, "implicit_gemm", True) else _lib.PM_FLAG_NO_IGEMM)
+                                     | (_lib.PM_FLAG_IGEMM_N128 if getattr(self, "igemm_n128", False) else 0)
+                                     | (0 if getattr(self, "fused_stats", True) else _lib.PM_FLAG_NO_FUSED_STATS), stream)
             _lib.check(rc, "pm_forward")
         return logits, attn, feats
 

@@ -128,16 +128,25 @@ def test_pm_against_oracle_ragged_batch():
 def test_pm_implicit_gemm_matches_im2col_path(batch, h, w):
     """Stride-2 trunk layers as implicit GEMM (TMA boxes with element strides straight from the NHWC planes, tc_igemm.cuh)
     vs the im2col + GEMM path: the same products in the same K order.  160×208 gives tiles whose last M tile of an image
-    is short; 258 images cross the internal 256-image chunk."""
+    is short; 258 images cross the internal 128-image passes (two in flight on two streams)."""
     hp, tasks = synth.PM_HPARAMS, synth.PMG_TASKS
     m = build_pm(hp, tasks)
     m.load_state_dict(torch_state_dict(synth.pm_state_dict(4, hp, tasks)))
     m.to("cuda").eval()
     x = torch.from_numpy(synth.images(4, batch, h, w)).cuda().to(torch.bfloat16)
     with torch.no_grad():
-        a = m(x, return_full=True)
+        a = m(x, return_full=True)                     # 256-wide N tiles where 256 divides the output channels
+        m.igemm_n128 = True
+        c = m(x, return_full=True)                     # 128-wide N tiles everywhere
+        m.igemm_n128 = False
+        m.fused_stats = False
+        d = m(x, return_full=True)                     # InstanceNorm statistics from a separate pass over the conv output
+        m.fused_stats = True
         m.implicit_gemm = False
         b = m(x, return_full=True)
     for t in tasks:
         assert rel_fro(a[t]["logits"].cpu().numpy(), b[t]["logits"].cpu().numpy()) <= 1e-5, t
         assert rel_fro(a[t]["attn"].cpu().numpy(), b[t]["attn"].cpu().numpy()) <= 1e-5, t
+        assert torch.equal(a[t]["logits"], c[t]["logits"]) and torch.equal(a[t]["attn"], c[t]["attn"]), t   # same products, same K order
+        assert rel_fro(a[t]["logits"].cpu().numpy(), d[t]["logits"].cpu().numpy()) <= 1e-4, t   # two statistics algorithms: rounding-level differences
+        assert rel_fro(a[t]["attn"].cpu().numpy(), d[t]["attn"].cpu().numpy()) <= 1e-4, t
