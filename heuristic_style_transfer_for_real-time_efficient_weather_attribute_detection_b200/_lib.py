@@ -15,6 +15,7 @@ PMG_FLAG_NO_FUSED_MIDGRAM, PMG_FLAG_ALWAYS_FUSED_MIDGRAM, PMG_FLAG_COUNT_F32_INP
 PM_FLAG_NO_IGEMM = 1
 PM_FLAG_IGEMM_N128 = 2
 PM_FLAG_NO_FUSED_STATS = 4
+PM_FLAG_NO_FUSED_CONV0 = 8
 
 
 class PmgConfig(C.Structure):

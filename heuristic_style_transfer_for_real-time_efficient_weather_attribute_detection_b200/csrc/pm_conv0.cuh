@@ -1,0 +1,275 @@
+// pm_conv0.cuh — first trunk layer of the PM model, Conv2d(Cin ≤ 4, N, k4, s2, p1) + InstanceNorm + LeakyReLU, straight from
+// the NCHW image: no im2col planes, no fp32 convolution output.
+// Reference: models_PM.py:121-128 (first block of the trunk), nn.InstanceNorm2d(affine) semantics as pm_instnorm_kernel.
+//
+// InstanceNorm needs the statistics of the whole H×W map before a single value can be normalised, and the layer is all
+// memory traffic (K = 16·Cin = 48: 77 MFLOP against 3.2 MB of fp32 output per image).  So the convolution is computed
+// TWICE, which is cheaper than writing it once:
+//   pass 1   image rows → A tile in shared memory → MMA → epilogue keeps only per-(tile, warp) column statistics
+//   finalize merge the partials per (sample, channel) → scale / shift
+//   pass 2   the same convolution again → epilogue normalises, LeakyReLU, hi/lo split → NHWC bf16 planes for layer 1
+// Traffic per image: 2 × 0.3 MB of image reads + 3.2 MB of plane writes, instead of im2col planes (1.6 MB written + read),
+// the fp32 output (3.2 MB written, read once or twice) and the planes.
+//
+// Tile = one output row (b, yo): Wo ≤ 128 pixels = the MMA rows; a CTA takes a contiguous run of tiles (consecutive output rows
+// share two of their four image rows in L2, and the sample — hence pass 2's scale / shift — changes once per ~100 tiles).
+// 128 loader threads stage the 4·Cin image rows the tile
+// needs with 16-byte cp.async (zero fill for the padding rows, zero pads left and right of every row; the rows of tile t+1
+// fly while tile t is built) and build the K-major 128B-swizzled operand tile: chunk j of pixel xo = 8 consecutive k =
+// (c, ky ∈ {2(j&1), 2(j&1)+1}, kx 0..3) = for two image rows the 4 pixels 2·xo-1 .. 2·xo+2, picked out of three 32-bit
+// words with two byte permutes (bf16 image) or split into hi/lo planes (fp32 image).  One MMA warp; two epilogue groups of
+// four warps (thread = pixel), one per TMEM accumulator stage, so two tiles' epilogues are in flight (pass 2 is bound by its
+// 28 KB of plane writes per tile, pass 1 by the statistics arithmetic); operand tile double-buffered.
+#pragma once
+
+#include "tc_prims.cuh"
+
+namespace tc {
+
+struct Conv0Params {
+    const void* x;                  // (B, Cin, H, W) bf16 | fp32
+    const __nv_bfloat16* wgt;       // [N][64] bf16, k = c·16 + ky·4 + kx, zero padded
+    float2* stats;                  // pass 1 out: [B·Ho·4][N] (Σ acc, Σ acc²) per (tile, epilogue warp), acc = conv without bias
+    const float2* scsh;             // pass 2 in: [B][N] (scale, shift) of InstanceNorm, applied to acc
+    __nv_bfloat16* o_hi;            // pass 2 out: [B·Ho·Wo][N]
+    __nv_bfloat16* o_lo;
+    int B, Cin, H, W, Ho, Wo, N;
+};
+
+constexpr int C0_LOADERS = 128;
+constexpr int C0_W_MMA = C0_LOADERS / 32;                 // warps 0-3 loaders, 4 MMA, 5-8 / 9-12 the two epilogue groups
+constexpr int C0_THREADS = C0_LOADERS + 32 + 256;
+constexpr int C0_A_BYTES = 128 * 128;                     // one operand plane of a tile
+constexpr int C0_ROWBUF_MAX = 12 * 1024;                  // per buffer: 4·Cin rows × (W·esize + 32)
+constexpr int C0_NBUF = 4;                                // row buffers: the rows of tiles t+1 .. t+3 are in flight while tile t is built
+                                                          // (one tile ahead made the tile period = the memory latency: 3.2 k cycles)
+
+template <bool F32IN>
+__host__ __device__ constexpr int c0_planes() { return F32IN ? 2 : 1; }
+template <bool F32IN>
+__host__ __device__ constexpr int c0_smem_bytes() {
+    return 2 * c0_planes<F32IN>() * C0_A_BYTES + 128 * 128 /*B ≤ 128 rows*/ + C0_NBUF * C0_ROWBUF_MAX + 8 * 4096 /*epilogue staging*/ +
+           2 * 128 * 8 /*scale, shift per group*/ + 256 /*barriers*/ + 1024 /*align*/;
+}
+
+__device__ __forceinline__ void c0_cp_async16(void* smem_dst, const void* gsrc, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void c0_named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+template <bool F32IN, int PASS>
+__global__ void __launch_bounds__(C0_THREADS, 1) pm_conv0_kernel(const Conv0Params p) {
+    constexpr int NP = c0_planes<F32IN>();
+    constexpr int ES = F32IN ? 4 : 2;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sA = smem;                                         // [buf 2][plane NP] × 16 KB
+    uint8_t* sB = sA + 2 * NP * C0_A_BYTES;                     // [N ≤ 128][128 B]
+    uint8_t* sRow = sB + 128 * 128;                             // [C0_NBUF] × C0_ROWBUF_MAX
+    uint8_t* sStage = sRow + C0_NBUF * C0_ROWBUF_MAX;           // 8 × 4 KB
+    float2* sScShAll = reinterpret_cast<float2*>(sStage + 8 * 4096);   // [group 2][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sScShAll + 256);
+    uint64_t* a_full = bars;        // [2]  8 loader warps
+    uint64_t* a_empty = bars + 2;   // [2]  MMA commit
+    uint64_t* d_full = bars + 4;    // [2]  MMA commit
+    uint64_t* d_empty = bars + 6;   // [2]  4 epilogue warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+    const int n_tiles = p.B * p.Ho;
+    const int per_cta = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int t0 = blockIdx.x * per_cta, t1 = min(n_tiles, t0 + per_cta);      // this CTA's run of tiles
+    const int pitch = p.W * ES + 32;                            // row pitch in the staging buffer (16 zero bytes each side)
+    const int nrows = 4 * p.Cin;
+    const uint32_t tmem_cols = p.N <= 16 ? 32u : p.N <= 32 ? 64u : p.N <= 64 ? 128u : 256u;      // 2 accumulator stages
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], C0_LOADERS / 32); mbar_init(&a_empty[i], 1); mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == C0_W_MMA) tmem_alloc(tmem_slot, tmem_cols);
+    // operand tiles and row buffers start as zeros: rows ≥ Wo, k ≥ 16·Cin and the row pads are never written afterwards
+    for (int i = threadIdx.x; i < (2 * NP * C0_A_BYTES + 128 * 128 + C0_NBUF * C0_ROWBUF_MAX) / 16; i += C0_THREADS)
+        reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    // weights: [N][64] bf16 rows of 128 bytes → swizzled K-major B tile
+    for (int i = threadIdx.x; i < p.N * 8; i += C0_THREADS) {
+        const int n = i >> 3, j = i & 7;
+        *reinterpret_cast<uint4*>(sB + n * 128 + ((j ^ (n & 7)) << 4)) = *reinterpret_cast<const uint4*>(p.wgt + (size_t)n * 64 + j * 8);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < C0_W_MMA) {
+        // ===================== loaders =====================
+        const int tid = threadIdx.x;
+        const int ppr = p.W * ES / 16;                          // 16-byte pieces per image row
+        // warp w fetches image rows w, w+4, …; its lanes the 16-byte pieces of a row (no integer division on this path: one
+        // loader warp per SM sub-partition has nobody to hide its latencies behind)
+        auto fetch_rows = [&](int tile, int rb) {               // always commits a group (possibly empty): wait_group counts stay aligned
+            if (tile < t1) {
+                const int b = tile / p.Ho, yo = tile - b * p.Ho;
+                uint8_t* dst0 = sRow + rb * C0_ROWBUF_MAX + 16;
+                for (int r = warp; r < nrows; r += C0_LOADERS / 32) {
+                    const int c = r >> 2, ky = r & 3;
+                    const int y = 2 * yo - 1 + ky;
+                    const bool ok = y >= 0 && y < p.H;
+                    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.x) + ((((size_t)b * p.Cin + c) * p.H + (ok ? y : 0)) * p.W) * ES;
+                    for (int pc = lane; pc < ppr; pc += 32) c0_cp_async16(dst0 + r * pitch + pc * 16, src + pc * 16, ok ? 16u : 0u);
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        for (int d = 0; d < C0_NBUF - 1; ++d) fetch_rows(t0 + d, d);
+        uint32_t it = 0;
+        for (int tile = t0; tile < t1; ++tile, ++it) {
+            const int buf = it & 1, rb = it % C0_NBUF;
+            asm volatile("cp.async.wait_group %0;" ::"n"(C0_NBUF - 2) : "memory");
+            c0_named_bar(1, C0_LOADERS);                        // rows of this tile landed everywhere; everyone is done with tile it-1
+            fetch_rows(tile + C0_NBUF - 1, (it + C0_NBUF - 1) % C0_NBUF);       // into the buffer tile it-1 was built from
+            mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1);      // the MMAs of tile it-2 have read this operand buffer
+            const uint8_t* rows = sRow + rb * C0_ROWBUF_MAX;
+            uint8_t* a_hi = sA + buf * NP * C0_A_BYTES;
+            const int nchunk = 2 * p.Cin;
+            // thread = output pixel: its ≤ 8 chunks are independent (loads of all of them in flight), consecutive lanes read
+            // consecutive words of a staged row and write different 16-byte chunks of consecutive operand rows
+            for (int xo = tid; xo < p.Wo; xo += C0_LOADERS) {
+                uint8_t* drow = a_hi + xo * 128;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (j >= nchunk) break;
+                    const int r0 = (j >> 1) * 4 + 2 * (j & 1);
+                    uint8_t* dst = drow + ((j ^ (xo & 7)) << 4);
+                    if (!F32IN) {
+                        // element x sits at byte 16 + 2x: x = 2xo-1 is the upper half of word xo+3
+                        const uint32_t* w0 = reinterpret_cast<const uint32_t*>(rows + r0 * pitch) + xo + 3;
+                        const uint32_t* w1 = reinterpret_cast<const uint32_t*>(rows + (r0 + 1) * pitch) + xo + 3;
+                        const uint32_t a0 = w0[0], a1 = w0[1], a2 = w0[2], b0 = w1[0], b1 = w1[1], b2 = w1[2];
+                        *reinterpret_cast<uint4*>(dst) = make_uint4(__byte_perm(a0, a1, 0x5432), __byte_perm(a1, a2, 0x5432),
+                                                                    __byte_perm(b0, b1, 0x5432), __byte_perm(b1, b2, 0x5432));
+                    } else {
+                        // element x sits at byte 16 + 4x: x = 2xo-1 → float index 2xo + 3
+                        const float* f0 = reinterpret_cast<const float*>(rows + r0 * pitch) + 2 * xo + 3;
+                        const float* f1 = reinterpret_cast<const float*>(rows + (r0 + 1) * pitch) + 2 * xo + 3;
+                        uint32_t hi[4], lo[4];
+                        split_bf16x2(f0[0], f0[1], hi[0], lo[0]); split_bf16x2(f0[2], f0[3], hi[1], lo[1]);
+                        split_bf16x2(f1[0], f1[1], hi[2], lo[2]); split_bf16x2(f1[2], f1[3], hi[3], lo[3]);
+                        *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(dst + C0_A_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[buf]);
+        }
+    } else if (warp == C0_W_MMA) {
+        // ===================== MMA issuer =====================
+        if (elect_one()) {
+            const uint32_t idesc = make_idesc_bf16(128, p.N, 0, 0);
+            const uint32_t aB = smem_u32(sB);
+            uint32_t it = 0;
+            for (int tile = t0; tile < t1; ++tile, ++it) {
+                const int buf = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                mbar_wait(&a_full[buf], ph);
+                mbar_wait(&d_empty[buf], ph ^ 1);
+                tc_fence_after();
+                const uint32_t aA = smem_u32(sA + buf * NP * C0_A_BYTES);
+                const uint32_t d = tmem_base + buf * (tmem_cols / 2);
+                for (int k = 0; k < p.Cin; ++k) {                // K = 16 per input channel
+                    const uint64_t bd = make_desc_k_sw128(aB + k * 32);
+                    umma_bf16(d, make_desc_k_sw128(aA + k * 32), bd, idesc, k > 0 ? 1u : 0u);
+                    if (F32IN) umma_bf16(d, make_desc_k_sw128(aA + C0_A_BYTES + k * 32), bd, idesc, 1u);
+                }
+                umma_commit(&a_empty[buf]);
+                umma_commit(&d_full[buf]);
+            }
+        }
+    } else {
+        // ===================== epilogue: thread = output pixel; group g owns accumulator stage g (tiles it ≡ g mod 2) =====
+        const int q = warp & 3;                                   // TMEM lane quarter
+        const int grp = (warp - C0_W_MMA - 1) >> 2;
+        uint8_t* wbuf = sStage + (warp - C0_W_MMA - 1) * 4096;
+        float2* sScSh = sScShAll + grp * 128;
+        const int sr = lane >> 3, sc = lane & 7;
+        const int et = (threadIdx.x - (C0_LOADERS + 32)) & 127;   // thread of the group
+        int cur_b = -1;
+        uint32_t it = 0;
+        for (int tile = t0; tile < t1; ++tile, ++it) {
+            if ((int)(it & 1) != grp) continue;
+            const int buf = grp;
+            const int b = tile / p.Ho;
+            if (PASS == 2 && b != cur_b) {                        // group-uniform
+                c0_named_bar(2 + grp, 128);                       // the group's readers of the previous sample's values are done
+                for (int i = et; i < p.N; i += 128) sScSh[i] = p.scsh[(size_t)b * p.N + i];
+                c0_named_bar(2 + grp, 128);
+                cur_b = b;
+            }
+            mbar_wait(&d_full[buf], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + buf * (tmem_cols / 2) + ((uint32_t)(q * 32) << 16);
+            const int nvalid = min(32, max(0, p.Wo - q * 32));   // rows of this warp that are pixels
+#pragma unroll 1
+            for (int c0 = 0; c0 < p.N; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(t_addr + (uint32_t)c0, r);
+                tmem_ld_wait();
+                if (c0 + 32 >= p.N) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&d_empty[buf]);
+                }
+                if (PASS == 1) {
+                    // Σ acc and Σ acc² per channel over the warp's 32 rows (rows that are not pixels hold exact zeros).  The
+                    // bias is left out on purpose: InstanceNorm subtracts the per-sample mean, so it cancels — the raw
+                    // accumulator is the value shifted by the bias, which is what keeps the single-pass sums well conditioned.
+                    __syncwarp();
+                    stage_write_row(wbuf, lane, r);
+                    __syncwarp();
+                    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+                    for (int rr = 0; rr < 32; rr += 2) {
+                        const float v0 = *reinterpret_cast<const float*>(wbuf + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4) + (lane & 3) * 4);
+                        const float v1 = *reinterpret_cast<const float*>(wbuf + (rr + 1) * 128 + (((lane >> 2) ^ ((rr + 1) & 7)) << 4) + (lane & 3) * 4);
+                        s0 += v0; s1 += v1;
+                        q0 = fmaf(v0, v0, q0); q1 = fmaf(v1, v1, q1);
+                    }
+                    p.stats[((size_t)tile * 4 + q) * p.N + c0 + lane] = make_float2(s0 + s1, q0 + q1);
+                } else {
+                    uint32_t w[32];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float4 ss = *reinterpret_cast<const float4*>(sScSh + c0 + 2 * i);      // (scale, shift) of two channels
+                        float y0 = fmaf(__uint_as_float(r[2 * i]), ss.x, ss.y);
+                        float y1 = fmaf(__uint_as_float(r[2 * i + 1]), ss.z, ss.w);
+                        y0 = fmaxf(y0, 0.2f * y0); y1 = fmaxf(y1, 0.2f * y1);
+                        split_bf16x2(y0, y1, w[i], w[16 + i]);    // row slice = [hi 64 B | lo 64 B]
+                    }
+                    __syncwarp();
+                    stage_write_row(wbuf, lane, w);
+                    __syncwarp();
+                    const int row0 = q * 32 + sr;                  // + 4·i per store instruction
+                    __nv_bfloat16* dst = (sc < 4 ? p.o_hi : p.o_lo) + ((size_t)tile * p.Wo + row0) * p.N + c0 + (sc & 3) * 8;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int rr = 4 * i + sr;
+                        const uint4 d = *reinterpret_cast<const uint4*>(wbuf + rr * 128 + ((sc ^ (rr & 7)) << 4));
+                        if (row0 + 4 * i < p.Wo) *reinterpret_cast<uint4*>(dst + (size_t)(4 * i) * p.N) = d;
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == C0_W_MMA) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+}  // namespace tc

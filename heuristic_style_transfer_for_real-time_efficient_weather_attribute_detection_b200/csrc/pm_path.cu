@@ -10,6 +10,7 @@
 // Σ_p A_p (W·f_p) == W·(Σ_p A_p f_p) and no (B, K, H, W) map is materialised.
 #include "pmg_common.cuh"
 #include "tc_host.cuh"
+#include "pm_conv0.cuh"
 
 #include <mutex>
 
@@ -307,6 +308,73 @@ __global__ void __launch_bounds__(256) pm_instnorm_kernel(const float* __restric
     pm_normalise_pass(src, s_scale[threadIdx.x & 7], s_shift[threadIdx.x & 7], o_hi, o_lo, o_f32, (size_t)b * HW * C + c0 + cl, pr, HW, C);
 }
 
+// Block of 256 threads = (sample b, channels c0..c0+31): merge the sample's per-(tile, epilogue warp) partials (mean, M2) in a
+// fixed order — warp w takes partials w, w+8, …, then thread c < 32 folds the 8 results (Chan et al.: deterministic, no
+// cancellation) — and turn them into InstanceNorm's scale / shift (y = v·scale + shift for the values v the statistics were
+// taken of).  Returns true in the 32 threads that hold a result.
+template <bool RAW_SUMS = false>
+__device__ __forceinline__ bool pm_merge_tile_stats(const float2* __restrict__ stats, const float* __restrict__ gamma,
+                                                    const float* __restrict__ beta, int b, int c0, int C, int HW, int tiles,
+                                                    int rows_full, int rows_last, float& sc, float& sh) {
+    __shared__ float m_n[8][32], m_mean[8][32], m_m2[8][32];
+    {
+        const int c = threadIdx.x & 31, pw = threadIdx.x >> 5;            // channel, partial phase (one warp per phase)
+        const int n_part = tiles * 4;
+        const float2* src = stats + ((size_t)b * n_part) * C + c0 + c;
+        float n = 0.f, mean = 0.f, m2 = 0.f;
+        for (int i0 = pw; i0 < n_part; i0 += 8 * 8) {                     // 8 loads in flight, then the (dependent) merges
+            float2 t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + 8 * u;
+                t[u] = i < n_part ? src[(size_t)i * C] : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = i0 + 8 * u;
+                const int ty = i >> 2, q = i & 3;
+                const int rows = ty < tiles - 1 ? rows_full : rows_last;
+                const int cnt = i < n_part ? min(32, max(0, rows - 32 * q)) : 0;      // warp-uniform
+                if (cnt == 0) continue;
+                const float nb = (float)cnt, nn = n + nb;
+                // RAW_SUMS: the partial is (Σ v, Σ v²) of values already shifted near zero (pm_conv0.cuh) → (mean, M2)
+                const float pm = RAW_SUMS ? t[u].x / nb : t[u].x;
+                const float pm2 = RAW_SUMS ? fmaxf(t[u].y - t[u].x * pm, 0.f) : t[u].y;
+                const float d = pm - mean;
+                mean += d * (nb / nn);
+                m2 += pm2 + d * d * (n * nb / nn);
+                n = nn;
+            }
+        }
+        m_n[pw][c] = n; m_mean[pw][c] = mean; m_m2[pw][c] = m2;
+    }
+    __syncthreads();
+    if (threadIdx.x >= 32) return false;
+    const int c = threadIdx.x;
+    float n = 0.f, mean = 0.f, m2 = 0.f;
+    for (int w = 0; w < 8; ++w) {
+        const float nb = m_n[w][c];
+        if (nb == 0.f) continue;
+        const float nn = n + nb, d = m_mean[w][c] - mean;
+        mean += d * (nb / nn);
+        m2 += m_m2[w][c] + d * d * (n * nb / nn);
+        n = nn;
+    }
+    const float var = fmaxf(m2 / (float)HW, 0.f);                         // biased variance (InstanceNorm2d)
+    sc = gamma[c0 + c] / sqrtf(var + kInEps);
+    sh = beta[c0 + c] - mean * sc;
+    return true;
+}
+
+// layer 0 (pm_conv0.cuh): partials of pass 1 → (scale, shift) [B][C] for pass 2; grid (C/32, B)
+__global__ void __launch_bounds__(256) pm_conv0_finalize_kernel(const float2* __restrict__ stats, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, float2* __restrict__ scsh, int HW,
+                                                                int C, int tiles, int rows) {
+    float sc, sh;
+    if (pm_merge_tile_stats<true>(stats, gamma, beta, blockIdx.y, blockIdx.x * 32, C, HW, tiles, rows, rows, sc, sh))
+        scsh[(size_t)blockIdx.y * C + blockIdx.x * 32 + threadIdx.x] = make_float2(sc, sh);
+}
+
 // Same layer with the statistics taken from the convolution's own epilogue (tc_gemm.cuh / tc_igemm.cuh `stats`): every
 // epilogue warp left (mean, Σ(x − mean)²) of its ≤ 32 rows per channel, the tile lying inside one sample.  The block merges
 // the sample's partials in a fixed order (Chan et al. pairwise update: deterministic, no cancellation) and then makes the
@@ -317,43 +385,12 @@ __global__ void __launch_bounds__(256) pm_instnorm_fused_kernel(const float* __r
                                                                 bf16* __restrict__ o_hi, bf16* __restrict__ o_lo,
                                                                 float* __restrict__ o_f32, int HW, int C, int tiles, int rows_full,
                                                                 int rows_last) {
-    __shared__ float m_n[8][32], m_mean[8][32], m_m2[8][32];
     __shared__ float4 s_scale[8], s_shift[8];
     const int b = blockIdx.y, c0 = blockIdx.x * 32;
-    {
-        const int c = threadIdx.x & 31, pw = threadIdx.x >> 5;            // channel, partial phase (one warp per phase)
-        const int n_part = tiles * 4;
-        const float2* src = stats + ((size_t)b * n_part) * C + c0 + c;
-        float n = 0.f, mean = 0.f, m2 = 0.f;
-        for (int i = pw; i < n_part; i += 8) {
-            const int ty = i >> 2, q = i & 3;
-            const int rows = ty < tiles - 1 ? rows_full : rows_last;
-            const int cnt = min(32, max(0, rows - 32 * q));               // warp-uniform
-            if (cnt == 0) continue;
-            const float2 t = src[(size_t)i * C];
-            const float nb = (float)cnt, nn = n + nb, d = t.x - mean;
-            mean += d * (nb / nn);
-            m2 += t.y + d * d * (n * nb / nn);
-            n = nn;
-        }
-        m_n[pw][c] = n; m_mean[pw][c] = mean; m_m2[pw][c] = m2;
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        const int c = threadIdx.x;
-        float n = 0.f, mean = 0.f, m2 = 0.f;
-        for (int w = 0; w < 8; ++w) {
-            const float nb = m_n[w][c];
-            if (nb == 0.f) continue;
-            const float nn = n + nb, d = m_mean[w][c] - mean;
-            mean += d * (nb / nn);
-            m2 += m_m2[w][c] + d * d * (n * nb / nn);
-            n = nn;
-        }
-        const float var = fmaxf(m2 / (float)HW, 0.f);                     // biased variance (InstanceNorm2d)
-        const float sc = gamma[c0 + c] / sqrtf(var + kInEps);
-        reinterpret_cast<float*>(s_scale)[c] = sc;
-        reinterpret_cast<float*>(s_shift)[c] = beta[c0 + c] - mean * sc;
+    float sc, sh;
+    if (pm_merge_tile_stats(stats, gamma, beta, b, c0, C, HW, tiles, rows_full, rows_last, sc, sh)) {
+        reinterpret_cast<float*>(s_scale)[threadIdx.x] = sc;
+        reinterpret_cast<float*>(s_shift)[threadIdx.x] = sh;
     }
     __syncthreads();
     const int cl = (threadIdx.x & 7) * 4, pr = threadIdx.x >> 3;
@@ -407,7 +444,7 @@ __global__ void __launch_bounds__(128) pm_heads_finish_kernel(const PmFinishArgs
 }
 
 // ------------------------------------------------------------------------------------------------ workspace
-struct PmWs { size_t a_hi, a_lo, conv, act_hi[2], act_lo[2], sc, stats, feats, total; };
+struct PmWs { size_t a_hi, a_lo, conv, act_hi[2], act_lo[2], sc, stats, scsh, feats, total; };
 
 static PmWs pm_ws(const PmPlan& p, const PmShape& s, int Bc) {
     PmWs w{};
@@ -420,7 +457,7 @@ static PmWs pm_ws(const PmPlan& p, const PmShape& s, int Bc) {
         cmax = max(cmax, rows * p.layer[l].cout);
         // fused InstanceNorm statistics: ≤ 4 (mean, M2) pairs per channel per M tile; an implicit-GEMM tile holds ≥ one
         // output row of an image, a plain GEMM tile 128 rows
-        const size_t tiles = l == 0 ? (rows + 127) / 128 : (size_t)Bc * s.h[l + 1];
+        const size_t tiles = max((rows + 127) / 128, (size_t)Bc * s.h[l + 1]);
         smax = max(smax, tiles * 4 * p.layer[l].cout * sizeof(float2));
     }
     w.a_hi = take(amax * 2); w.a_lo = take(amax * 2);
@@ -428,6 +465,7 @@ static PmWs pm_ws(const PmPlan& p, const PmShape& s, int Bc) {
     for (int i = 0; i < 2; ++i) { w.act_hi[i] = take(cmax * 2); w.act_lo[i] = take(cmax * 2); }
     w.sc = take((size_t)Bc * s.h[p.n_layers] * s.w[p.n_layers] * 64 * 4);
     w.stats = take(smax);
+    w.scsh = take((size_t)Bc * p.layer[0].cout * sizeof(float2));
     w.total = o;
     return w;
 }
@@ -467,6 +505,34 @@ static cudaStream_t pm_side_stream() {
     std::lock_guard<std::mutex> lk(mu);
     if (!side[dev] && cudaStreamCreateWithFlags(&side[dev], cudaStreamNonBlocking) != cudaSuccess) side[dev] = nullptr;
     return side[dev];
+}
+
+// layer 0 fused (pm_conv0.cuh): two convolution passes around a statistics merge; writes the NHWC hi/lo planes of layer 1's input
+static bool pm_conv0_supported(const PmPlan& p, const PmShape& s, int x_dtype) {
+    const PmLayer& y = p.layer[0];
+    const int es = x_dtype == PMG_F32 ? 4 : 2;
+    return p.n_layers > 1 && y.stride == 2 && y.cin <= 4 && y.cout % 32 == 0 && y.cout <= 128 && s.w[1] <= 128 && s.w[0] == 2 * s.w[1] &&
+           s.h[0] == 2 * s.h[1] && (s.w[0] * es) % 16 == 0 && 4 * y.cin * (s.w[0] * es + 32) + 16 <= tc::C0_ROWBUF_MAX;
+}
+
+template <bool F32IN>
+static int pm_conv0_run(const tc::Conv0Params& cp, const float* gamma, const float* beta, float2* scsh, cudaStream_t st) {
+    constexpr int smem = tc::c0_smem_bytes<F32IN>();
+    static tc::PerDeviceFlag attr_set;
+    if (!attr_set.test()) {
+        PMG_CUDA_OK(cudaFuncSetAttribute(tc::pm_conv0_kernel<F32IN, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "conv0 smem attr");
+        PMG_CUDA_OK(cudaFuncSetAttribute(tc::pm_conv0_kernel<F32IN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "conv0 smem attr");
+        attr_set.set();
+    }
+    const int tiles = cp.B * cp.Ho;
+    const int grid = tiles < tc::num_sms() ? tiles : tc::num_sms();
+    tc::pm_conv0_kernel<F32IN, 1><<<grid, tc::C0_THREADS, smem, st>>>(cp);
+    PMG_LAUNCH_OK("pm conv0 pass 1");
+    pm_conv0_finalize_kernel<<<dim3(cp.N / 32, cp.B), 256, 0, st>>>(cp.stats, gamma, beta, scsh, cp.Ho * cp.Wo, cp.N, cp.Ho, cp.Wo);
+    PMG_LAUNCH_OK("pm conv0 finalize");
+    tc::pm_conv0_kernel<F32IN, 2><<<grid, tc::C0_THREADS, smem, st>>>(cp);
+    PMG_LAUNCH_OK("pm conv0 pass 2");
+    return PMG_OK;
 }
 
 static int grid1d(size_t n) { size_t g = (n + 255) / 256; return (int)(g > 148 * 32 ? 148 * 32 : (g < 1 ? 1 : g)); }
@@ -597,6 +663,19 @@ int pm_forward(const pm_config* cfg, const void* packed, const void* x, int x_dt
             const PmLayer& y = p.layer[l];
             const int Ho = s.h[l + 1], Wo = s.w[l + 1];
             const int rows = Bc * Ho * Wo;
+            if (l == 0 && !(flags & PM_FLAG_NO_FUSED_CONV0) && pm_conv0_supported(p, s, x_dtype)) {
+                tc::Conv0Params cp{};
+                cp.x = xb; cp.wgt = reinterpret_cast<const bf16*>(pk + L.w[0]);      // the conv bias cancels in InstanceNorm
+                cp.stats = reinterpret_cast<float2*>(ws + w.stats); cp.scsh = reinterpret_cast<const float2*>(ws + w.scsh);
+                cp.o_hi = Hb(w.act_hi[0]); cp.o_lo = Hb(w.act_lo[0]);
+                cp.B = Bc; cp.Cin = y.cin; cp.H = H; cp.W = W; cp.Ho = Ho; cp.Wo = Wo; cp.N = y.cout;
+                const float* ga = reinterpret_cast<const float*>(pk + L.gamma[0]);
+                const float* be = reinterpret_cast<const float*>(pk + L.beta[0]);
+                rc = x_dtype == PMG_F32 ? pm_conv0_run<true>(cp, ga, be, reinterpret_cast<float2*>(ws + w.scsh), st)
+                                        : pm_conv0_run<false>(cp, ga, be, reinterpret_cast<float2*>(ws + w.scsh), st);
+                if (rc) return rc;
+                continue;
+            }
             float* conv = reinterpret_cast<float*>(ws + w.conv);
             // InstanceNorm statistics from the convolution's own epilogue wherever every M tile lies inside one sample
             float2* stats = (flags & PM_FLAG_NO_FUSED_STATS) ? nullptr : reinterpret_cast<float2*>(ws + w.stats);

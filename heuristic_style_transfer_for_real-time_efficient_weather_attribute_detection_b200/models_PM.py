@@ -182,7 +182,8 @@ class MultiTaskPatchGAN(nn.Module):
                                      self._ws.data_ptr(), self._ws.numel(),
                                      (0 if getattr(self, "implicit_gemm", True) else _lib.PM_FLAG_NO_IGEMM)
                                      | (_lib.PM_FLAG_IGEMM_N128 if getattr(self, "igemm_n128", False) else 0)
-                                     | (0 if getattr(self, "fused_stats", True) else _lib.PM_FLAG_NO_FUSED_STATS), stream)
+                                     | (0 if getattr(self, "fused_stats", True) else _lib.PM_FLAG_NO_FUSED_STATS)
+                                     | (0 if getattr(self, "fused_conv0", True) else _lib.PM_FLAG_NO_FUSED_CONV0), stream)
             _lib.check(rc, "pm_forward")
         return logits, attn, feats
 

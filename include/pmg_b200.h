@@ -212,6 +212,7 @@ size_t pm_workspace_bytes(const pm_config* cfg, int B, int H, int W);
 int pm_feature_shape(const pm_config* cfg, int H, int W, int* Hf, int* Wf, int* C);
 #define PM_FLAG_NO_IGEMM 1u /* pm_forward: run every trunk layer as im2col + GEMM (default: implicit GEMM for the layers with >= 64 input channels) */
 #define PM_FLAG_NO_FUSED_STATS 4u /* pm_forward: InstanceNorm statistics by a separate pass over the convolution output (default: from the convolution epilogue where every M tile lies inside one sample) */
+#define PM_FLAG_NO_FUSED_CONV0 8u /* pm_forward: first layer as im2col + GEMM + InstanceNorm kernels (default: pm_conv0.cuh — the convolution computed twice around a statistics merge, straight from the NCHW image) */
 #define PM_FLAG_IGEMM_N128 2u /* pm_forward: keep the 128-wide N tile in the implicit GEMMs (default: 256 where 256 divides the output channels) */
 
 /* The forward pass — replaces MultiTaskPatchGAN.forward (models_PM.py:159-194).

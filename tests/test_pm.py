@@ -142,11 +142,21 @@ def test_pm_implicit_gemm_matches_im2col_path(batch, h, w):
         m.fused_stats = False
         d = m(x, return_full=True)                     # InstanceNorm statistics from a separate pass over the conv output
         m.fused_stats = True
+        m.fused_conv0 = False
+        e = m(x, return_full=True)                     # layer 0 as im2col + GEMM + InstanceNorm kernels
+        ef = m(x.float(), return_full=True)
+        m.fused_conv0 = True
+        af = m(x.float(), return_full=True)            # fp32 image: hi/lo operand planes built in the layer-0 loader
         m.implicit_gemm = False
         b = m(x, return_full=True)
     for t in tasks:
-        assert rel_fro(a[t]["logits"].cpu().numpy(), b[t]["logits"].cpu().numpy()) <= 1e-5, t
-        assert rel_fro(a[t]["attn"].cpu().numpy(), b[t]["attn"].cpu().numpy()) <= 1e-5, t
+        # same products in the same K order; the InstanceNorm statistics come from the conv epilogue (Chan-merged two-pass
+        # partials) on one side and from the single-pass shifted kernel on the other: rounding-level differences
+        assert rel_fro(a[t]["logits"].cpu().numpy(), b[t]["logits"].cpu().numpy()) <= 1e-4, t
+        assert rel_fro(a[t]["attn"].cpu().numpy(), b[t]["attn"].cpu().numpy()) <= 1e-4, t
         assert torch.equal(a[t]["logits"], c[t]["logits"]) and torch.equal(a[t]["attn"], c[t]["attn"]), t   # same products, same K order
         assert rel_fro(a[t]["logits"].cpu().numpy(), d[t]["logits"].cpu().numpy()) <= 1e-4, t   # two statistics algorithms: rounding-level differences
         assert rel_fro(a[t]["attn"].cpu().numpy(), d[t]["attn"].cpu().numpy()) <= 1e-4, t
+        for u, v in ((a, e), (af, ef), (a, af)):       # the bf16 image is exact in fp32: all four must agree
+            assert rel_fro(u[t]["logits"].cpu().numpy(), v[t]["logits"].cpu().numpy()) <= 1e-4, t
+            assert rel_fro(u[t]["attn"].cpu().numpy(), v[t]["attn"].cpu().numpy()) <= 1e-4, t

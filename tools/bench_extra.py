@@ -87,6 +87,14 @@ def pm(quiet=False, sweep=False):
                     "ms": round(ms, 3), "images_per_s": round(v, 1), "flops_per_image": 5.40e9,
                     "tensor_frac_of_measured": round(v * 5.40e9 / 1e12 / PEAK["bf16_tflops"], 4)}, quiet)
     _lib.lib.pm_debug_set_chunking(128, 2)
+    if sweep:        # what each round-2 change is worth, one at a time switched off
+        for attr, off, what in (("fused_conv0", False, "layer 0 as im2col + GEMM + InstanceNorm kernels"),
+                                ("fused_stats", False, "InstanceNorm statistics by a separate pass"),
+                                ("igemm_n128", True, "128-wide N tiles in every implicit GEMM")):
+            setattr(m, attr, off)
+            ms = ev_time(step, 3, warm=1)
+            setattr(m, attr, not off)
+            emit(rows, {"config": "PM forward batch 1024, default chunking, WITHOUT: " + what, "ms": round(ms, 3), "images_per_s": round(B / ms * 1e3, 1)}, quiet)
     return rows
 
 
