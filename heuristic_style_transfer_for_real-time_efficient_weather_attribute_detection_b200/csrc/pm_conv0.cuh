@@ -13,9 +13,11 @@
 //
 // Tile = one output row (b, yo): Wo ≤ 128 pixels = the MMA rows; a CTA takes a contiguous run of tiles (consecutive output rows
 // share two of their four image rows in L2, and the sample — hence pass 2's scale / shift — changes once per ~100 tiles).
-// 128 loader threads stage the 4·Cin image rows the tile
-// needs with 16-byte cp.async (zero fill for the padding rows, zero pads left and right of every row; the rows of tile t+1
-// fly while tile t is built) and build the K-major 128B-swizzled operand tile: chunk j of pixel xo = 8 consecutive k =
+// The 4·Cin image rows a tile needs arrive as ONE TMA box of a 3-D map (x, y, b·Cin + c) — box (W + 16 bytes' worth of pad each
+// side) × 4 rows × Cin planes from (x = -pad, y = 2·yo - 1): TMA's out-of-bounds zero fill IS the convolution's padding, left,
+// right, top and bottom; four boxes are in flight, issued by the MMA thread as it sees a tile built.  (The first version
+// staged the rows with 16-byte cp.async from the loader threads: 1.2 k of the tile's 2.1 k cycles went into issuing them.)
+// 128 loader threads (thread = output pixel) build the K-major 128B-swizzled operand tile: chunk j of pixel xo = 8 consecutive k =
 // (c, ky ∈ {2(j&1), 2(j&1)+1}, kx 0..3) = for two image rows the 4 pixels 2·xo-1 .. 2·xo+2, picked out of three 32-bit
 // words with two byte permutes (bf16 image) or split into hi/lo planes (fp32 image).  One MMA warp; two epilogue groups of
 // four warps (thread = pixel), one per TMEM accumulator stage, so two tiles' epilogues are in flight (pass 2 is bound by its
@@ -34,11 +36,14 @@ struct Conv0Params {
     __nv_bfloat16* o_hi;            // pass 2 out: [B·Ho·Wo][N]
     __nv_bfloat16* o_lo;
     int B, Cin, H, W, Ho, Wo, N;
+    long long* trace;               // optional (pmg_debug_set_trace): clock64 stamps of CTA 0's roles at its 10th tile, slots 400 + 20·(PASS-1) ..
 };
+#define C0_T(slot) do { if (p.trace && blockIdx.x == 0 && it == 10) p.trace[400 + 20 * (PASS - 1) + (slot)] = clock64(); } while (0)
 
 constexpr int C0_LOADERS = 128;
-constexpr int C0_W_MMA = C0_LOADERS / 32;                 // warps 0-3 loaders, 4 MMA, 5-8 / 9-12 the two epilogue groups
-constexpr int C0_THREADS = C0_LOADERS + 32 + 256;
+constexpr int C0_W_MMA = C0_LOADERS / 32;                 // warps 0-3 loaders, 4 MMA, 5-8 / 9-12 the two epilogue groups, 13 TMA producer
+constexpr int C0_W_TMA = C0_W_MMA + 9;
+constexpr int C0_THREADS = C0_LOADERS + 32 + 256 + 32;
 constexpr int C0_A_BYTES = 128 * 128;                     // one operand plane of a tile
 constexpr int C0_ROWBUF_MAX = 12 * 1024;                  // per buffer: 4·Cin rows × (W·esize + 32)
 constexpr int C0_NBUF = 4;                                // row buffers: the rows of tiles t+1 .. t+3 are in flight while tile t is built
@@ -52,13 +57,16 @@ __host__ __device__ constexpr int c0_smem_bytes() {
            2 * 128 * 8 /*scale, shift per group*/ + 256 /*barriers*/ + 1024 /*align*/;
 }
 
-__device__ __forceinline__ void c0_cp_async16(void* smem_dst, const void* gsrc, uint32_t src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(src_bytes) : "memory");
+__device__ __forceinline__ void c0_tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1, int32_t c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "l"(kEvictLast)
+        : "memory");
 }
 __device__ __forceinline__ void c0_named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 template <bool F32IN, int PASS>
-__global__ void __launch_bounds__(C0_THREADS, 1) pm_conv0_kernel(const Conv0Params p) {
+__global__ void __launch_bounds__(C0_THREADS, 1) pm_conv0_kernel(const __grid_constant__ CUtensorMap tmX, const Conv0Params p) {
     constexpr int NP = c0_planes<F32IN>();
     constexpr int ES = F32IN ? 4 : 2;
     extern __shared__ uint8_t smem_raw[];
@@ -73,7 +81,8 @@ __global__ void __launch_bounds__(C0_THREADS, 1) pm_conv0_kernel(const Conv0Para
     uint64_t* a_empty = bars + 2;   // [2]  MMA commit
     uint64_t* d_full = bars + 4;    // [2]  MMA commit
     uint64_t* d_empty = bars + 6;   // [2]  4 epilogue warps
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* rows_full = bars + 8; // [C0_NBUF]  TMA box of a tile's image rows
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + C0_NBUF);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
     const int n_tiles = p.B * p.Ho;
@@ -85,6 +94,8 @@ __global__ void __launch_bounds__(C0_THREADS, 1) pm_conv0_kernel(const Conv0Para
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], C0_LOADERS / 32); mbar_init(&a_empty[i], 1); mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 4); }
+        for (int i = 0; i < C0_NBUF; ++i) mbar_init(&rows_full[i], 1);
+        prefetch_tmap(&tmX);
         fence_barrier_init();
     }
     if (warp == C0_W_MMA) tmem_alloc(tmem_slot, tmem_cols);
@@ -106,87 +117,127 @@ __global__ void __launch_bounds__(C0_THREADS, 1) pm_conv0_kernel(const Conv0Para
     if (warp < C0_W_MMA) {
         // ===================== loaders =====================
         const int tid = threadIdx.x;
-        const int ppr = p.W * ES / 16;                          // 16-byte pieces per image row
-        // warp w fetches image rows w, w+4, …; its lanes the 16-byte pieces of a row (no integer division on this path: one
-        // loader warp per SM sub-partition has nobody to hide its latencies behind)
-        auto fetch_rows = [&](int tile, int rb) {               // always commits a group (possibly empty): wait_group counts stay aligned
-            if (tile < t1) {
-                const int b = tile / p.Ho, yo = tile - b * p.Ho;
-                uint8_t* dst0 = sRow + rb * C0_ROWBUF_MAX + 16;
-                for (int r = warp; r < nrows; r += C0_LOADERS / 32) {
-                    const int c = r >> 2, ky = r & 3;
-                    const int y = 2 * yo - 1 + ky;
-                    const bool ok = y >= 0 && y < p.H;
-                    const uint8_t* src = reinterpret_cast<const uint8_t*>(p.x) + ((((size_t)b * p.Cin + c) * p.H + (ok ? y : 0)) * p.W) * ES;
-                    for (int pc = lane; pc < ppr; pc += 32) c0_cp_async16(dst0 + r * pitch + pc * 16, src + pc * 16, ok ? 16u : 0u);
-                }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-        for (int d = 0; d < C0_NBUF - 1; ++d) fetch_rows(t0 + d, d);
         uint32_t it = 0;
         for (int tile = t0; tile < t1; ++tile, ++it) {
             const int buf = it & 1, rb = it % C0_NBUF;
-            asm volatile("cp.async.wait_group %0;" ::"n"(C0_NBUF - 2) : "memory");
-            c0_named_bar(1, C0_LOADERS);                        // rows of this tile landed everywhere; everyone is done with tile it-1
-            fetch_rows(tile + C0_NBUF - 1, (it + C0_NBUF - 1) % C0_NBUF);       // into the buffer tile it-1 was built from
+            if (tid == 0) C0_T(0);
+            mbar_wait(&rows_full[rb], (it / C0_NBUF) & 1);      // this tile's rows have landed (the MMA thread issues the boxes)
+            if (tid == 0) C0_T(1);
             mbar_wait(&a_empty[buf], ((it >> 1) & 1) ^ 1);      // the MMAs of tile it-2 have read this operand buffer
+            if (tid == 0) C0_T(4);
             const uint8_t* rows = sRow + rb * C0_ROWBUF_MAX;
             uint8_t* a_hi = sA + buf * NP * C0_A_BYTES;
             const int nchunk = 2 * p.Cin;
             // thread = output pixel: its ≤ 8 chunks are independent (loads of all of them in flight), consecutive lanes read
             // consecutive words of a staged row and write different 16-byte chunks of consecutive operand rows
+            // (all loads first, then the stores: the compiler must assume the operand tile aliases the staged rows)
             for (int xo = tid; xo < p.Wo; xo += C0_LOADERS) {
                 uint8_t* drow = a_hi + xo * 128;
+                if (!F32IN) {
+                    // element x sits at byte 16 + 2x: x = 2xo-1 is the upper half of word xo+3
+                    uint32_t wa[8][3], wb[8][3];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (j >= nchunk) break;
-                    const int r0 = (j >> 1) * 4 + 2 * (j & 1);
-                    uint8_t* dst = drow + ((j ^ (xo & 7)) << 4);
-                    if (!F32IN) {
-                        // element x sits at byte 16 + 2x: x = 2xo-1 is the upper half of word xo+3
+                    for (int j = 0; j < 8; ++j) {
+                        if (j >= nchunk) break;
+                        const int r0 = (j >> 1) * 4 + 2 * (j & 1);
                         const uint32_t* w0 = reinterpret_cast<const uint32_t*>(rows + r0 * pitch) + xo + 3;
                         const uint32_t* w1 = reinterpret_cast<const uint32_t*>(rows + (r0 + 1) * pitch) + xo + 3;
-                        const uint32_t a0 = w0[0], a1 = w0[1], a2 = w0[2], b0 = w1[0], b1 = w1[1], b2 = w1[2];
-                        *reinterpret_cast<uint4*>(dst) = make_uint4(__byte_perm(a0, a1, 0x5432), __byte_perm(a1, a2, 0x5432),
-                                                                    __byte_perm(b0, b1, 0x5432), __byte_perm(b1, b2, 0x5432));
-                    } else {
-                        // element x sits at byte 16 + 4x: x = 2xo-1 → float index 2xo + 3
+                        wa[j][0] = w0[0]; wa[j][1] = w0[1]; wa[j][2] = w0[2];
+                        wb[j][0] = w1[0]; wb[j][1] = w1[1]; wb[j][2] = w1[2];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j >= nchunk) break;
+                        *reinterpret_cast<uint4*>(drow + ((j ^ (xo & 7)) << 4)) =
+                            make_uint4(__byte_perm(wa[j][0], wa[j][1], 0x5432), __byte_perm(wa[j][1], wa[j][2], 0x5432),
+                                       __byte_perm(wb[j][0], wb[j][1], 0x5432), __byte_perm(wb[j][1], wb[j][2], 0x5432));
+                    }
+                } else {
+                    // element x sits at byte 16 + 4x: x = 2xo-1 → float index 2xo + 3
+                    float fa[8][4], fb[8][4];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j >= nchunk) break;
+                        const int r0 = (j >> 1) * 4 + 2 * (j & 1);
                         const float* f0 = reinterpret_cast<const float*>(rows + r0 * pitch) + 2 * xo + 3;
                         const float* f1 = reinterpret_cast<const float*>(rows + (r0 + 1) * pitch) + 2 * xo + 3;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { fa[j][e] = f0[e]; fb[j][e] = f1[e]; }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j >= nchunk) break;
+                        uint8_t* dst = drow + ((j ^ (xo & 7)) << 4);
                         uint32_t hi[4], lo[4];
-                        split_bf16x2(f0[0], f0[1], hi[0], lo[0]); split_bf16x2(f0[2], f0[3], hi[1], lo[1]);
-                        split_bf16x2(f1[0], f1[1], hi[2], lo[2]); split_bf16x2(f1[2], f1[3], hi[3], lo[3]);
+                        split_bf16x2(fa[j][0], fa[j][1], hi[0], lo[0]); split_bf16x2(fa[j][2], fa[j][3], hi[1], lo[1]);
+                        split_bf16x2(fb[j][0], fb[j][1], hi[2], lo[2]); split_bf16x2(fb[j][2], fb[j][3], hi[3], lo[3]);
                         *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                         *reinterpret_cast<uint4*>(dst + C0_A_BYTES) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
                 }
             }
+            if (tid == 0) C0_T(5);
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_full[buf]);
+            if (tid == 0) C0_T(6);
         }
     } else if (warp == C0_W_MMA) {
         // ===================== MMA issuer =====================
         if (elect_one()) {
             const uint32_t idesc = make_idesc_bf16(128, p.N, 0, 0);
             const uint32_t aB = smem_u32(sB);
+            uint64_t bdesc[4], adesc[2][4];                         // [plane][k step] of operand buffer 0: nothing but issue work inside the loop
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                bdesc[k] = make_desc_k_sw128(aB + k * 32);
+#pragma unroll
+                for (int pl = 0; pl < 2; ++pl) adesc[pl][k] = make_desc_k_sw128(smem_u32(sA + (pl < NP ? pl : 0) * C0_A_BYTES) + k * 32);
+            }
+            constexpr uint64_t kBufStep = (uint64_t)(NP * C0_A_BYTES) >> 4;      // descriptor start-address field counts 16-byte units
             uint32_t it = 0;
             for (int tile = t0; tile < t1; ++tile, ++it) {
                 const int buf = it & 1;
                 const uint32_t ph = (it >> 1) & 1;
+                C0_T(8);
                 mbar_wait(&a_full[buf], ph);
+                C0_T(9);
                 mbar_wait(&d_empty[buf], ph ^ 1);
+                C0_T(10);
                 tc_fence_after();
-                const uint32_t aA = smem_u32(sA + buf * NP * C0_A_BYTES);
                 const uint32_t d = tmem_base + buf * (tmem_cols / 2);
-                for (int k = 0; k < p.Cin; ++k) {                // K = 16 per input channel
-                    const uint64_t bd = make_desc_k_sw128(aB + k * 32);
-                    umma_bf16(d, make_desc_k_sw128(aA + k * 32), bd, idesc, k > 0 ? 1u : 0u);
-                    if (F32IN) umma_bf16(d, make_desc_k_sw128(aA + C0_A_BYTES + k * 32), bd, idesc, 1u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {                    // K = 16 per input channel
+                    if (k >= p.Cin) break;
+                    umma_bf16(d, adesc[0][k] + buf * kBufStep, bdesc[k], idesc, k > 0 ? 1u : 0u);
+                    if (F32IN) umma_bf16(d, adesc[1][k] + buf * kBufStep, bdesc[k], idesc, 1u);
                 }
                 umma_commit(&a_empty[buf]);
                 umma_commit(&d_full[buf]);
+                C0_T(11);
+            }
+        }
+    } else if (warp == C0_W_TMA) {
+        // ===================== TMA producer of the image rows =====================
+        // once a_full(t) has been seen, every loader warp has finished reading row buffer t % C0_NBUF, which can take the box
+        // of tile t + C0_NBUF.  (On the MMA thread this cost it 450 cycles per tile and made IT the pace-setter.)
+        if (elect_one()) {
+            const uint32_t box_bytes = (uint32_t)(nrows * pitch);
+            const int xpad = 16 / ES;                               // elements of zero pad left of x = 0
+            int fb = t0 / p.Ho, fy = t0 - fb * p.Ho;                // (sample, output row) of the next tile to fetch: no division in the loop
+            int ft = t0;
+            auto fetch_next = [&](int rb) {
+                if (ft >= t1) return;
+                mbar_expect_tx(&rows_full[rb], box_bytes);
+                c0_tma_load_3d(sRow + rb * C0_ROWBUF_MAX, &tmX, &rows_full[rb], -xpad, 2 * fy - 1, fb * p.Cin);
+                ++ft;
+                if (++fy == p.Ho) { fy = 0; ++fb; }
+            };
+            for (int d = 0; d < C0_NBUF; ++d) fetch_next(d);
+            uint32_t it = 0;
+            for (int tile = t0; tile < t1; ++tile, ++it) {
+                mbar_wait(&a_full[it & 1], (it >> 1) & 1);
+                fetch_next(it % C0_NBUF);
             }
         }
     } else {
@@ -209,10 +260,11 @@ __global__ void __launch_bounds__(C0_THREADS, 1) pm_conv0_kernel(const Conv0Para
                 c0_named_bar(2 + grp, 128);
                 cur_b = b;
             }
+            if (et == 0) C0_T(12);
             mbar_wait(&d_full[buf], (it >> 1) & 1);
+            if (et == 0) C0_T(13);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + buf * (tmem_cols / 2) + ((uint32_t)(q * 32) << 16);
-            const int nvalid = min(32, max(0, p.Wo - q * 32));   // rows of this warp that are pixels
 #pragma unroll 1
             for (int c0 = 0; c0 < p.N; c0 += 32) {
                 uint32_t r[32];
@@ -262,6 +314,7 @@ __global__ void __launch_bounds__(C0_THREADS, 1) pm_conv0_kernel(const Conv0Para
                     }
                 }
             }
+            if (et == 0) C0_T(14);
         }
         tc_fence_before();
     }

@@ -17,6 +17,7 @@
 namespace pmg {
 
 using bf16 = __nv_bfloat16;
+extern long long* g_enc_trace;            // pmg_fast.cu (pmg_debug_set_trace)
 constexpr int PM_MAX_LAYERS = 8;
 // Images per internal pass (bounds the workspace) and the number of passes in flight.  A pass is a chain of tensor-bound
 // kernels (implicit-GEMM convolutions: persistent, one CTA per SM) and HBM-bound ones (InstanceNorm, layer-0 im2col: small
@@ -512,7 +513,7 @@ static bool pm_conv0_supported(const PmPlan& p, const PmShape& s, int x_dtype) {
     const PmLayer& y = p.layer[0];
     const int es = x_dtype == PMG_F32 ? 4 : 2;
     return p.n_layers > 1 && y.stride == 2 && y.cin <= 4 && y.cout % 32 == 0 && y.cout <= 128 && s.w[1] <= 128 && s.w[0] == 2 * s.w[1] &&
-           s.h[0] == 2 * s.h[1] && (s.w[0] * es) % 16 == 0 && 4 * y.cin * (s.w[0] * es + 32) + 16 <= tc::C0_ROWBUF_MAX;
+           s.h[0] == 2 * s.h[1] && (s.w[0] * es) % 16 == 0 && 4 * y.cin * (s.w[0] * es + 32) <= tc::C0_ROWBUF_MAX && s.w[0] + 32 / es <= 256;
 }
 
 template <bool F32IN>
@@ -524,13 +525,25 @@ static int pm_conv0_run(const tc::Conv0Params& cp, const float* gamma, const flo
         PMG_CUDA_OK(cudaFuncSetAttribute(tc::pm_conv0_kernel<F32IN, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "conv0 smem attr");
         attr_set.set();
     }
+    // image as (x, y, b·Cin + c); a box = (W + 32 bytes of pad) × 4 rows × Cin planes, out-of-bounds = zero = the conv padding
+    constexpr int ES = F32IN ? 4 : 2;
+    CUtensorMap tmx;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)cp.W, (cuuint64_t)cp.H, (cuuint64_t)cp.B * cp.Cin};
+        cuuint64_t strides[2] = {(cuuint64_t)cp.W * ES, (cuuint64_t)cp.H * cp.W * ES};
+        cuuint32_t box[3] = {(cuuint32_t)(cp.W + 32 / ES), 4, (cuuint32_t)cp.Cin};
+        cuuint32_t estr[3] = {1, 1, 1};
+        int rc = tc::encode_tmap_cached(&tmx, 3, cp.x, dims, strides, box, estr, CU_TENSOR_MAP_SWIZZLE_NONE, "cuTensorMapEncodeTiled(pm conv0 image)",
+                                        F32IN ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+        if (rc) return rc;
+    }
     const int tiles = cp.B * cp.Ho;
     const int grid = tiles < tc::num_sms() ? tiles : tc::num_sms();
-    tc::pm_conv0_kernel<F32IN, 1><<<grid, tc::C0_THREADS, smem, st>>>(cp);
+    tc::pm_conv0_kernel<F32IN, 1><<<grid, tc::C0_THREADS, smem, st>>>(tmx, cp);
     PMG_LAUNCH_OK("pm conv0 pass 1");
     pm_conv0_finalize_kernel<<<dim3(cp.N / 32, cp.B), 256, 0, st>>>(cp.stats, gamma, beta, scsh, cp.Ho * cp.Wo, cp.N, cp.Ho, cp.Wo);
     PMG_LAUNCH_OK("pm conv0 finalize");
-    tc::pm_conv0_kernel<F32IN, 2><<<grid, tc::C0_THREADS, smem, st>>>(cp);
+    tc::pm_conv0_kernel<F32IN, 2><<<grid, tc::C0_THREADS, smem, st>>>(tmx, cp);
     PMG_LAUNCH_OK("pm conv0 pass 2");
     return PMG_OK;
 }
@@ -668,7 +681,7 @@ int pm_forward(const pm_config* cfg, const void* packed, const void* x, int x_dt
                 cp.x = xb; cp.wgt = reinterpret_cast<const bf16*>(pk + L.w[0]);      // the conv bias cancels in InstanceNorm
                 cp.stats = reinterpret_cast<float2*>(ws + w.stats); cp.scsh = reinterpret_cast<const float2*>(ws + w.scsh);
                 cp.o_hi = Hb(w.act_hi[0]); cp.o_lo = Hb(w.act_lo[0]);
-                cp.B = Bc; cp.Cin = y.cin; cp.H = H; cp.W = W; cp.Ho = Ho; cp.Wo = Wo; cp.N = y.cout;
+                cp.trace = g_enc_trace; cp.B = Bc; cp.Cin = y.cin; cp.H = H; cp.W = W; cp.Ho = Ho; cp.Wo = Wo; cp.N = y.cout;
                 const float* ga = reinterpret_cast<const float*>(pk + L.gamma[0]);
                 const float* be = reinterpret_cast<const float*>(pk + L.beta[0]);
                 rc = x_dtype == PMG_F32 ? pm_conv0_run<true>(cp, ga, be, reinterpret_cast<float2*>(ws + w.scsh), st)

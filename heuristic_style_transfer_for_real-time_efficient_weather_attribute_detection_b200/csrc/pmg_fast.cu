@@ -25,7 +25,7 @@
 
 namespace pmg {
 
-static long long* g_enc_trace = nullptr;   // debug only (pmg_debug_set_trace)
+long long* g_enc_trace = nullptr;          // debug only (pmg_debug_set_trace); pm_path.cu reads it too
 
 int launch_pool_heads(const Plan& p, const PackedLayout& L, const char* packed, const float* tok, int B, int N,
                       float* logits, cudaStream_t st);

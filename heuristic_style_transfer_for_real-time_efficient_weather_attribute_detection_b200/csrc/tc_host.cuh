@@ -40,12 +40,13 @@ struct alignas(64) TmapSlot { CUtensorMap map; TmapKey key; bool valid; };
 constexpr int kTmapSlots = 256;
 
 inline int encode_tmap_cached(CUtensorMap* m, uint32_t rank, const void* base, const cuuint64_t* dims, const cuuint64_t* strides,
-                              const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapSwizzle swizzle, const char* what) {
+                              const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapSwizzle swizzle, const char* what,
+                              CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
     thread_local TmapSlot* slots = nullptr;
     if (!slots) slots = new TmapSlot[kTmapSlots]();      // lives as long as the thread (24 KB)
     TmapKey k;
     memset(&k, 0, sizeof(k));
-    k.base = reinterpret_cast<uint64_t>(base); k.rank = rank; k.swizzle = (uint32_t)swizzle;
+    k.base = reinterpret_cast<uint64_t>(base); k.rank = rank; k.swizzle = (uint32_t)swizzle | ((uint32_t)dtype << 8);
     for (uint32_t i = 0; i < rank; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; k.estr[i] = estr[i]; }
     for (uint32_t i = 0; i + 1 < rank; ++i) k.strides[i] = strides[i];
     uint64_t h = 0xcbf29ce484222325ull;
@@ -55,7 +56,7 @@ inline int encode_tmap_cached(CUtensorMap* m, uint32_t rank, const void* base, c
     if (s.valid && s.key == k) { *m = s.map; return PMG_OK; }
     EncodeTiledFn fn = encode_fn();
     if (!fn) { pmg::set_cuda_error(cudaErrorNotSupported, "cuTensorMapEncodeTiled entry point"); return PMG_ERR_CUDA; }
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = fn(m, dtype, rank, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { pmg::set_cuda_error(cudaErrorInvalidValue, what); return PMG_ERR_CUDA; }
     s.map = *m; s.key = k; s.valid = true;
