@@ -160,3 +160,32 @@ def test_pm_implicit_gemm_matches_im2col_path(batch, h, w):
         for u, v in ((a, e), (af, ef), (a, af)):       # the bf16 image is exact in fp32: all four must agree
             assert rel_fro(u[t]["logits"].cpu().numpy(), v[t]["logits"].cpu().numpy()) <= 1e-4, t
             assert rel_fro(u[t]["attn"].cpu().numpy(), v[t]["attn"].cpu().numpy()) <= 1e-4, t
+
+
+@pytest.mark.gpu
+def test_pm_forward_is_graph_capturable_with_two_passes_in_flight():
+    """pm_forward runs its 128-image passes two at a time, the second on a library-owned side stream forked from / joined to
+    the caller's stream with events: the whole call must still be ordered on the caller's stream — in particular it must be
+    capturable into a CUDA graph and replay to the same bits."""
+    hp, tasks = synth.PM_HPARAMS, synth.PMG_TASKS
+    m = build_pm(hp, tasks)
+    m.load_state_dict(torch_state_dict(synth.pm_state_dict(4, hp, tasks)))
+    m.to("cuda").eval()
+    x = torch.from_numpy(synth.images(6, 130, 224, 224)).cuda().to(torch.bfloat16)       # 128 + 2 images: both lanes
+    with torch.no_grad():
+        want = m(x)
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            m(x)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            got = m(x)
+        for _ in range(2):
+            g.replay()
+        torch.cuda.synchronize()
+    for t in tasks:
+        assert torch.equal(got[t], want[t]), t
