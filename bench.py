@@ -339,10 +339,27 @@ def main():
         flag = torch.tensor([1 if ok else 0], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         assert int(flag.item()) == 1, "gathered logits differ from the per-rank logits"
+        # what the end-of-window drain of the LAST bucket costs (nothing is left to overlap it with): events around flush()
+        dr = []
+        for _ in range(5):
+            with torch.no_grad():
+                for sidx in range(args.gather_steps):
+                    model.forward_packed(x, out=bucket.slot())
+                    if sidx < args.gather_steps - 1:
+                        bucket.commit()
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            d0.record()
+            bucket.commit()
+            bucket.flush()
+            d1.record()
+            fence()
+            dr.append(d0.elapsed_time(d1))
+        drain_ms = over_ranks(statistics.median(dr))[0]
         stat = lambda v: {"min": round(min(v) / args.steps, 4), "median": round(statistics.median(v) / args.steps, 4),
                           "max": round(max(v) / args.steps, 4)}
         multi = {"rank_ms_per_step": stat(rank_ms),
                  "no_collective": {"value": round(GB * args.steps / (ms_nc / 1e3), 1), "rank_ms_per_step": stat(rank_ms_nc)},
+                 "last_bucket_drain_ms": round(drain_ms, 4),
                  "gather_check": "every rank: gathered (world,B,52) bucket == own logits at its slot, peers' slots match "
                                  "their fp64 checksums"}
 

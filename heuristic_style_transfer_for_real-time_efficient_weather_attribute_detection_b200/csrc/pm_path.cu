@@ -664,6 +664,9 @@ int pm_forward(const pm_config* cfg, const void* packed, const void* x, int x_dt
     }
     const int Hf = s.h[p.n_layers], Wf = s.w[p.n_layers], HWf = Hf * Wf;
     const size_t img_elems = (size_t)cfg->input_nc * H * W;
+    // the passes: a lambda, so that the side stream is joined to the caller's on EVERY exit path (an error return that left
+    // the fork un-joined would leave the caller's stream — or a graph capture — depending on a dangling branch)
+    auto run_passes = [&]() -> int {
     int ci = 0;
     for (int b0 = 0; b0 < B; b0 += chunk, ++ci) {
         const int Bc = min(chunk, B - b0);
@@ -762,13 +765,20 @@ int pm_forward(const pm_config* cfg, const void* packed, const void* x, int x_dt
         pm_heads_finish_kernel<<<(Bc * p.ntask + 3) / 4, 128, 0, st>>>(a);
         PMG_LAUNCH_OK("pm heads finish");
     }
+    return PMG_OK;
+    };
+    const int rc_passes = run_passes();
     if (lanes == 2) {
-        PMG_CUDA_OK(cudaEventRecord(ev_join, lane_st[1]), "pm join record");
-        PMG_CUDA_OK(cudaStreamWaitEvent(st0, ev_join, 0), "pm join wait");
+        const cudaError_t e1 = cudaEventRecord(ev_join, lane_st[1]);
+        const cudaError_t e2 = cudaStreamWaitEvent(st0, ev_join, 0);
         cudaEventDestroy(ev_fork);          // released by the runtime once the recorded work has completed
         cudaEventDestroy(ev_join);
+        if (rc_passes == PMG_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
+            set_cuda_error(e1 != cudaSuccess ? e1 : e2, "pm join");
+            return PMG_ERR_CUDA;
+        }
     }
-    return PMG_OK;
+    return rc_passes;
 }
 
 }  // extern "C"

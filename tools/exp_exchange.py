@@ -79,6 +79,17 @@ class NoCopies(PeerBucketedGather):
             self.world = w
 
 
+def symm_write_only():
+    """logits written into the symmetric (peer-mapped) send area, nothing else: is it the memory the encoder stores to?"""
+    g = PeerBucketedGather(B, 52, 4, dev)
+    st = {"n": 0}
+    def step():
+        with torch.no_grad():
+            m.forward_packed(x, out=g.send[0][st["n"] % 4])
+        st["n"] += 1
+    return step, lambda: None
+
+
 def bucketed(cls):
     def make():
         g = cls(B, 52, 4, dev)
@@ -90,10 +101,14 @@ def bucketed(cls):
     return make
 
 
-for name, steps, mk in [("control", 20, control), ("event record + side-stream wait per bucket", 20, events_only),
-                        ("peer gather, no barriers", 20, bucketed(NoBarrier)), ("peer gather, no copies", 20, bucketed(NoCopies)),
-                        ("peer gather", 20, bucketed(PeerBucketedGather)), ("peer gather", 80, bucketed(PeerBucketedGather)),
-                        ("nccl all_gather", 20, bucketed(BucketedGather)), ("nccl all_gather", 80, bucketed(BucketedGather)),
-                        ("control", 80, control)]:
+legs = [("control", 20, control), ("event record + side-stream wait per bucket", 20, events_only),
+        ("symmetric-memory logits, no exchange", 20, symm_write_only),
+        ("peer gather, no barriers", 20, bucketed(NoBarrier)), ("peer gather, no copies", 20, bucketed(NoCopies)),
+        ("peer gather", 20, bucketed(PeerBucketedGather)), ("peer gather", 80, bucketed(PeerBucketedGather)),
+        ("nccl all_gather", 20, bucketed(BucketedGather)), ("nccl all_gather", 80, bucketed(BucketedGather)),
+        ("control", 80, control)]
+if "--quick" in sys.argv:          # the 20-step legs only, three rounds (leg-to-leg noise on a multi-GPU box is +-3 %)
+    legs = [l for l in legs if l[1] == 20 and "nccl" not in l[0]] * 3
+for name, steps, mk in legs:
     run(name, steps, mk)
 dist.destroy_process_group()
