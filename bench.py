@@ -218,7 +218,10 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="images per GPU per step")
     ap.add_argument("--e2e-chunk", type=int, default=512, help="largest H2D piece of HostPipeline (the last one is split 256, 128, ... 32)")
     ap.add_argument("--gather-steps", type=int, default=4, help="N>1: steps whose logits share one all_gather")
-    ap.add_argument("--nccl-gather", action="store_true", help="N>1: use the NCCL all-gather instead of the peer-memory pull")
+    ap.add_argument("--nccl-gather", action="store_true", help="N>1: use the NCCL all-gather instead of peer memory")
+    ap.add_argument("--exchange", default="pull", choices=["push", "pull"],
+                    help="N>1, peer memory: copy-engine pulls (pull, default: measured faster) or logits stored to every rank by the "
+                         "token-stage kernel itself (push, pmg_forward_bcast)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--force-generic", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-memory end-to-end leg (ncu runs)")
@@ -261,7 +264,7 @@ def main():
     # the logits of --gather-steps consecutive steps go out in ONE all_gather (runner.BucketedGather): each forward writes
     # straight into its slot of the bucket, the gather of a full bucket runs under the forwards that fill the next one, and
     # drain() gathers what is left and waits for everything, inside the timed region
-    bucket, exchange = (make_bucketed_gather(B, 52, args.gather_steps, dev, prefer_peer=not args.nccl_gather)
+    bucket, exchange = (make_bucketed_gather(B, 52, args.gather_steps, dev, prefer_peer=not args.nccl_gather, kind=args.exchange)
                         if world > 1 else (None, "none"))
 
     lg_single = torch.empty((B, 52), dtype=torch.float32, device=dev)
@@ -270,7 +273,7 @@ def main():
         with torch.no_grad():
             if bucket is None:
                 return model.forward_packed(x, out=lg_single)
-            lg = model.forward_packed(x, out=bucket.slot())
+            lg = model.forward_packed(x, out=bucket.slot(), also=bucket.peers())
             bucket.commit()
         return lg
 
@@ -283,6 +286,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_enqueue_ms = []
+
     def timed(step_fn, drain_fn):
         """W warm-up + args.steps timed steps of step_fn on this rank; returns this rank's device ms (events on the
         launching stream, barrier + synchronize on both sides)."""
@@ -292,8 +297,10 @@ def main():
         fence()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
+        h0 = time.perf_counter()
         for _ in range(args.steps):
             step_fn()
+        host_enqueue_ms.append((time.perf_counter() - h0) * 1e3 / args.steps)     # host time to ENQUEUE a step (not in the JSON value)
         drain_fn()
         b.record()
         fence()
@@ -308,7 +315,17 @@ def main():
         per = [float(v) for v in t.tolist()]
         return max(per), per
 
+    def step_nocoll():
+        with torch.no_grad():
+            model.forward_packed(x, out=lg_single)
+
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    # N > 1: the control leg (same forwards, no exchange) runs FIRST.  On a multi-GPU box whatever is measured in the first
+    # second of a process comes out a few per cent slow (tools/exp_exchange.py --quick: control 0.294 -> 0.283 -> 0.279 ms over
+    # three rounds); the diagnostic leg takes that, the recorded leg is measured after it.  (Order only: every leg is still W
+    # warm-up + exactly K timed steps between barriers.)
+    if world > 1:
+        ms_nc, rank_ms_nc = over_ranks(timed(step_nocoll, lambda: None))
     ms, rank_ms = over_ranks(timed(step, drain))
     value = GB * args.steps / (ms / 1e3)
 
@@ -317,22 +334,17 @@ def main():
     # gathered bucket must hold, at every rank's slot, exactly the logits that rank computed.
     multi = None
     if world > 1:
-        def step_nocoll():
-            with torch.no_grad():
-                model.forward_packed(x, out=lg_single)
-
-        ms_nc, rank_ms_nc = over_ranks(timed(step_nocoll, lambda: None))
-        chk, _ = make_bucketed_gather(B, 52, args.gather_steps, dev, keep=True, prefer_peer=not args.nccl_gather)
+        chk, _ = make_bucketed_gather(B, 52, args.gather_steps, dev, keep=True, prefer_peer=not args.nccl_gather, kind=args.exchange)
         with torch.no_grad():
-            for _ in range(args.gather_steps):
-                model.forward_packed(x, out=chk.slot())
+            for _ in range(3 * args.gather_steps + 1):      # several buckets and a partly filled last one: every index is reused
+                model.forward_packed(x, out=chk.slot(), also=chk.peers())
                 chk.commit()
             chk.flush()
             mine = model.forward_packed(x)
         got = chk.pop()
         sums = torch.zeros(world, dtype=torch.float64, device=dev)
         dist.all_gather_into_tensor(sums, mine.double().sum().reshape(1))
-        ok = len(got) == args.gather_steps
+        ok = len(got) == 3 * args.gather_steps + 1
         for t in got:                                   # t: (world, B, 52) — slot r = rank r's logits of that micro-batch
             ok = ok and bool(torch.equal(t[rank], mine))
             ok = ok and bool(torch.equal(t.double().sum(dim=(1, 2)), sums))
@@ -344,7 +356,7 @@ def main():
         for _ in range(5):
             with torch.no_grad():
                 for sidx in range(args.gather_steps):
-                    model.forward_packed(x, out=bucket.slot())
+                    model.forward_packed(x, out=bucket.slot(), also=bucket.peers())
                     if sidx < args.gather_steps - 1:
                         bucket.commit()
             d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -358,6 +370,8 @@ def main():
         stat = lambda v: {"min": round(min(v) / args.steps, 4), "median": round(statistics.median(v) / args.steps, 4),
                           "max": round(max(v) / args.steps, 4)}
         multi = {"rank_ms_per_step": stat(rank_ms),
+                 "host_enqueue_ms_per_step": {"exchange_leg": round(host_enqueue_ms[1], 4), "no_collective_leg": round(host_enqueue_ms[0], 4),
+                                              "what": "rank 0's host time to enqueue one step; the device time per step is above"},
                  "no_collective": {"value": round(GB * args.steps / (ms_nc / 1e3), 1), "rank_ms_per_step": stat(rank_ms_nc)},
                  "last_bucket_drain_ms": round(drain_ms, 4),
                  "gather_check": "every rank: gathered (world,B,52) bucket == own logits at its slot, peers' slots match "

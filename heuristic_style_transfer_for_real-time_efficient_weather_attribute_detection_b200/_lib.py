@@ -47,7 +47,7 @@ class PmgError(RuntimeError):
 EXPORTS = [
     "pmg_abi_version", "pmg_status_string", "pmg_last_cuda_error", "pmg_param_count", "pmg_packed_bytes",
     "pmg_pack_weights", "pmg_workspace_bytes", "pmg_logits_per_image", "pmg_forward_launch_count",
-    "pmg_forward", "pmg_forward_profile", "pmg_gram_batched", "pmg_tc_gemm", "pmg_debug_set_trace",
+    "pmg_forward", "pmg_forward_bcast", "pmg_forward_profile", "pmg_gram_batched", "pmg_tc_gemm", "pmg_debug_set_trace",
     "pmg_preprocess_u8", "pmg_postprocess", "pmg_style_gram_shape", "pmg_style_grams", "pmg_resize_scratch_bytes", "pmg_resize_crop_u8", "pmg_debug_tmem_a", "pmg_tc_gemm2", "pmg_debug_load_probe", "pm_debug_set_chunking",
     "pm_param_count", "pm_packed_bytes", "pm_pack_weights", "pm_workspace_bytes", "pm_feature_shape", "pm_forward",
 ]
@@ -79,6 +79,9 @@ def _load() -> C.CDLL:
     lib.pmg_forward.argtypes = [cfgp, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                 C.c_void_p, C.POINTER(PmgTaps), C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p]
     lib.pmg_forward.restype = C.c_int
+    lib.pmg_forward_bcast.argtypes = [cfgp, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                      C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p]
+    lib.pmg_forward_bcast.restype = C.c_int
     lib.pmg_forward_profile.argtypes = [cfgp, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.POINTER(PmgStageTime),
                                         C.c_int, C.POINTER(C.c_int)]

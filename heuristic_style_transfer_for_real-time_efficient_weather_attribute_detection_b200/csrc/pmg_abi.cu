@@ -119,7 +119,7 @@ int pmg_forward_launch_count(const pmg_config* cfg, int B, int H, int W, unsigne
 
 static int forward_impl(const pmg_config* cfg, const void* packed, const void* x, int x_dtype, int B, int H, int W,
                         float* logits, float* gram, const pmg_taps* taps, void* workspace, size_t workspace_bytes,
-                        unsigned flags, pmg_stream_t stream, StageTimer* tm) {
+                        unsigned flags, pmg_stream_t stream, StageTimer* tm, const LogitPeers* peers = nullptr) {
     const Plan p = make_plan(cfg);
     if (!p.ok || !packed || !x || !logits || !workspace) return PMG_ERR_BAD_ARG;
     if (x_dtype != PMG_F32 && x_dtype != PMG_BF16) return PMG_ERR_BAD_ARG;
@@ -139,9 +139,10 @@ static int forward_impl(const pmg_config* cfg, const void* packed, const void* x
     if (workspace_bytes < need) return PMG_ERR_WORKSPACE;
     if (fast)
         return fast_forward(p, s, L, reinterpret_cast<const char*>(packed), x, x_dtype, B, logits, gram, taps,
-                            reinterpret_cast<char*>(workspace), st, tm, flags);
-    return generic_forward(p, s, L, reinterpret_cast<const char*>(packed), x, x_dtype, B, logits, gram, taps,
-                           reinterpret_cast<char*>(workspace), st, tm);
+                            reinterpret_cast<char*>(workspace), st, tm, flags, peers);
+    rc = generic_forward(p, s, L, reinterpret_cast<const char*>(packed), x, x_dtype, B, logits, gram, taps,
+                         reinterpret_cast<char*>(workspace), st, tm);
+    return rc ? rc : copy_logits_to_peers(logits, (size_t)B * p.ncls_total * sizeof(float), peers, st);
 }
 
 int pmg_forward(const pmg_config* cfg, const void* packed, const void* x, int x_dtype, int B, int H, int W,
@@ -149,6 +150,20 @@ int pmg_forward(const pmg_config* cfg, const void* packed, const void* x, int x_
                 unsigned flags, pmg_stream_t stream) {
     return forward_impl(cfg, packed, x, x_dtype, B, H, W, logits, gram, taps, workspace, workspace_bytes, flags,
                         stream, nullptr);
+}
+
+int pmg_forward_bcast(const pmg_config* cfg, const void* packed, const void* x, int x_dtype, int B, int H, int W,
+                      float* logits, float* const* peer_logits, int n_peers, void* workspace, size_t workspace_bytes,
+                      unsigned flags, pmg_stream_t stream) {
+    if (n_peers < 0 || n_peers > PMG_MAX_PEERS || (n_peers > 0 && !peer_logits)) return PMG_ERR_BAD_ARG;
+    LogitPeers peers;
+    peers.n = n_peers;
+    for (int d = 0; d < n_peers; ++d) {
+        if (!peer_logits[d] || misaligned(peer_logits[d], 4)) return PMG_ERR_BAD_ARG;
+        peers.dst[d] = peer_logits[d];
+    }
+    return forward_impl(cfg, packed, x, x_dtype, B, H, W, logits, nullptr, nullptr, workspace, workspace_bytes, flags, stream,
+                        nullptr, &peers);
 }
 
 int pmg_forward_profile(const pmg_config* cfg, const void* packed, const void* x, int x_dtype, int B, int H, int W,

@@ -179,12 +179,22 @@ int style_grams_forward(const Plan& p, const Shape& s, const PackedLayout& L, co
                         int B, float* grams, char* ws, cudaStream_t st);
 int pack_generic(const Plan& p, const PackedLayout& L, const float* const* prm, char* packed, cudaStream_t st);
 
+// Extra destinations of the packed logits (pmg_forward_bcast): device pointers, possibly peer-mapped memory of other GPUs.
+// The fused token-stage kernel stores every logit to all of them from its epilogue (the multi-GPU exchange costs no extra
+// launch, copy or SM); every other path copies after the fact.
+constexpr int PMG_MAX_PEERS = 15;
+struct LogitPeers {
+    float* dst[PMG_MAX_PEERS];
+    int n = 0;
+};
+int copy_logits_to_peers(const float* logits, size_t bytes, const LogitPeers* peers, cudaStream_t st);
+
 // fast path entry points (pmg_fast.cu)
 bool fast_supported(const Plan& p, const Shape& s);
 size_t fast_workspace_bytes(const Plan& p, const Shape& s, int B);
 int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const char* packed, const void* x,
                  int x_dtype, int B, float* logits, float* gram, const pmg_taps* taps, char* ws,
-                 cudaStream_t st, StageTimer* tm, unsigned flags);
+                 cudaStream_t st, StageTimer* tm, unsigned flags, const LogitPeers* peers = nullptr);
 int fast_launch_count(const Plan& p, const Shape& s, int B, unsigned flags);
 int pack_fast(const Plan& p, const PackedLayout& L, const float* const* prm, char* packed, cudaStream_t st);
 

@@ -502,9 +502,15 @@ static int gemm(const void* a_hi, const void* a_lo, int lda, const void* b, int 
     return tc::launch_gemm_t<BN, NA, EPI, ACT>(a_hi, a_lo, lda, b, kc, g, splits, kc, st);
 }
 
+int copy_logits_to_peers(const float* logits, size_t bytes, const LogitPeers* peers, cudaStream_t st) {
+    for (int d = 0; peers && d < peers->n; ++d)
+        PMG_CUDA_OK(cudaMemcpyAsync(peers->dst[d], logits, bytes, cudaMemcpyDefault, st), "logits -> peer");
+    return PMG_OK;
+}
+
 int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const char* packed, const void* x, int x_dtype,
                  int B, float* logits, float* gram, const pmg_taps* taps, char* ws, cudaStream_t st, StageTimer* tm,
-                 unsigned flags) {
+                 unsigned flags, const LogitPeers* peers) {
     const FastWs w = fast_ws(B);
     const FastW f = fast_w(p);
     const char* fb = packed + L.fast;
@@ -670,6 +676,8 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
         e.cls_bias = Pf(L.cls_b); e.logits = logits;
         e.tok_in = taps ? taps->tokens_in : nullptr; e.tok_out = taps ? taps->tokens_out : nullptr;
         e.nl = p.nl; e.B = B; e.ntask = p.ntask; e.ncls_total = p.ncls_total; e.trace = g_enc_trace;
+        e.n_peers = peers ? peers->n : 0;
+        for (int d = 0; d < e.n_peers; ++d) e.peer_logits[d] = peers->dst[d];
         for (int l = 0; l < p.nl; ++l) {
             const TfLayerOff& t = L.tf[l];
             e.layer[l] = {Pf(t.b_in), Pf(t.b_o), Pf(t.b_1), Pf(t.b_2), Pf(t.ln1w), Pf(t.ln1b), Pf(t.ln2w), Pf(t.ln2b)};
@@ -732,7 +740,7 @@ int fast_forward(const Plan& p, const Shape& s, const PackedLayout& L, const cha
         PMG_CUDA_OK(tc::launch_pdl(pool_finish_kernel, dim3((B * p.ncls_total + 255) / 256), dim3(256), 0, st, a), "pool_finish");
     }
     PMG_MARK(tm, "pool_heads");
-    return PMG_OK;
+    return copy_logits_to_peers(logits, (size_t)B * p.ncls_total * sizeof(float), peers, st);      // unfused token stage: copies after the fact
 }
 
 // ------------------------------------------------------------------------------------------------

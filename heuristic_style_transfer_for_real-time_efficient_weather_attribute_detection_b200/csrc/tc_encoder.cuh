@@ -80,6 +80,8 @@ struct EncParams {
     const float* tok_bias;           // [192]
     const float* cls_bias;           // [ncls_total]
     float* logits;                   // [B][ncls_total]
+    float* peer_logits[15];          // optional copies of the logits (peer-mapped memory of other GPUs): stored from the same epilogue
+    int n_peers;
     float* tok_in;                   // optional taps [T][192]
     float* tok_out;
     EncLayerPtrs layer[ENC_MAX_LAYERS];
@@ -662,7 +664,10 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                     den += e;
                     acc = fmaf(e, s[n * ENC_SC_LD + p.ntask + c], acc);
                 }
-                p.logits[(size_t)img * p.ncls_total + c] = acc / den + sPrm[ENC_P_CLSB + c];
+                const float lg = acc / den + sPrm[ENC_P_CLSB + c];
+                const size_t li = (size_t)img * p.ncls_total + c;
+                p.logits[li] = lg;
+                for (int d = 0; d < p.n_peers; ++d) p.peer_logits[d][li] = lg;      // posted stores over NVLink: the exchange rides in this kernel
             }
             named_bar_sync(1, 256);
             ENC_TC(191);

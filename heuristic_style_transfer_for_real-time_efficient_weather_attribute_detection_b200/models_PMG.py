@@ -240,7 +240,7 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
 
     # ------------------------------------------------------------------ forward
     def _run(self, x: torch.Tensor, want_gram: bool = False, taps: bool = False, out: Optional[torch.Tensor] = None,
-             ws: Optional[torch.Tensor] = None):
+             ws: Optional[torch.Tensor] = None, also=None):
         """``ws``: caller-owned workspace (uint8, >= pmg_workspace_bytes) used instead of the module's own — a captured
         CUDA graph must keep replaying into memory nobody reallocates (runner.GraphedPMG)."""
         if self.training:
@@ -310,6 +310,23 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
                          "tokens_out": torch.empty((B, np_, d), dtype=torch.float32, device=x.device)}
                 tp = _lib.PmgTaps(extra["chan"].data_ptr(), extra["tokens_in"].data_ptr(), extra["tokens_out"].data_ptr())
             flags = self._flags()
+            if also is not None and (hasattr(also, "ptrs") or len(also)):
+                # further destinations of the logits (peer-mapped buffers of other GPUs): stored by the token-stage kernel itself
+                if want_gram or taps:
+                    raise ValueError("`also` cannot be combined with gram / taps outputs")
+                if hasattr(also, "ptrs"):                  # runner.PeerSlots: validated once, pointer array ready
+                    if also.shape != (B, self._n_logits):
+                        raise ValueError(f"`also` slots are {also.shape}, the logits ({B}, {self._n_logits})")
+                    ptrs, n_also = also.ptrs, also.n
+                else:
+                    for t in also:
+                        if t.shape != (B, self._n_logits) or t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+                            raise ValueError(f"every `also` tensor must be a contiguous CUDA ({B}, {self._n_logits}) float32 tensor")
+                    ptrs, n_also = (ctypes.c_void_p * len(also))(*[t.data_ptr() for t in also]), len(also)
+                rc = _lib.lib.pmg_forward_bcast(cfgp, packed.data_ptr(), x.data_ptr(), dt, B, H, W, logits.data_ptr(), ptrs, n_also,
+                                                ws.data_ptr(), ws.numel(), flags, stream)
+                _lib.check(rc, "pmg_forward_bcast")
+                return logits, gram, extra
             rc = _lib.lib.pmg_forward(cfgp, packed.data_ptr(), x.data_ptr(), dt, B, H, W, logits.data_ptr(),
                                       gram.data_ptr() if gram is not None else None,
                                       ctypes.byref(tp) if tp is not None else None,
@@ -328,11 +345,13 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
         logits, _, _ = self._run(x)
         return self._split(logits)
 
-    def forward_packed(self, x, out: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward_packed(self, x, out: Optional[torch.Tensor] = None, ws: Optional[torch.Tensor] = None, also=None) -> torch.Tensor:
         """(B, Σncls) fp32 — the dict of ``forward`` as one tensor, columns in Tasks.json order.  ``out``: write the
         logits into this (B, Σncls) fp32 tensor (e.g. a slot of a gather bucket, runner.BucketedGather); ``ws``: a
-        caller-owned workspace of ``workspace_bytes(...)`` bytes (graph capture)."""
-        return self._run(x, out=out, ws=ws)[0]
+        caller-owned workspace of ``workspace_bytes(...)`` bytes (graph capture); ``also``: up to 15 more (B, Σncls) fp32
+        tensors — typically peer-mapped slots on the other GPUs (runner.PushBucketedGather) — that receive the same logits,
+        written by the token-stage kernel's own epilogue (``pmg_forward_bcast``)."""
+        return self._run(x, out=out, ws=ws, also=also)[0]
 
     def workspace_bytes(self, B: int, H: int = 224, W: int = 224) -> int:
         return int(_lib.lib.pmg_workspace_bytes(ctypes.byref(self._cfg), B, H, W))

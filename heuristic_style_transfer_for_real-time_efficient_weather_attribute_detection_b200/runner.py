@@ -101,6 +101,11 @@ class BucketedGather:
             self._retire(self.cur)          # the previous gather of this bucket must have read the send buffer
         return self.send[self.cur][self.n]
 
+    def peers(self):
+        """Further destinations the forward itself should store the slot's logits to (``forward_packed(x, out=slot(),
+        also=peers())``; call after ``slot()``).  None here: the exchange is a separate step of this class."""
+        return None
+
     def commit(self) -> None:
         """The forward that fills the current slot has been enqueued on the current stream."""
         self.n += 1
@@ -227,21 +232,140 @@ class PeerBucketedGather(BucketedGather):
             if self.keep:
                 self._done.extend(self.recv[j][:, s] for s in range(self.filled[j]))
 
-def make_bucketed_gather(b_local: int, n_logits: int, steps: int, device, group=None, keep: bool = False, prefer_peer: bool = True):
-    """(gather, kind): the SM-free peer-memory exchange when the ranks can map each other's memory, else the NCCL / gloo
-    all-gather.  Every rank must take the same branch: the outcome of the attempt is agreed on with one all-reduce."""
+class PeerSlots:
+    """Pre-validated extra destinations for ``forward_packed(..., also=…)``: a ctypes array of device pointers to contiguous
+    (B, Σncls) fp32 buffers (``tensors`` keeps them alive)."""
+    __slots__ = ("ptrs", "n", "shape", "tensors")
+
+    def __init__(self, ptrs, n, shape, tensors):
+        self.ptrs, self.n, self.shape, self.tensors = ptrs, n, shape, tensors
+
+
+class PushBucketedGather(BucketedGather):
+    """MEASURED SLOWER than PeerBucketedGather's copy-engine pull (2 B200: 0.2899 vs 0.2815 ms per 1024-image step, 8 B200: 0.3029
+    vs 0.3000) and therefore not the default: a kernel is not complete before its remote writes have been flushed, so the NVLink
+    round trip of the epilogue's stores sits between every forward and the next one, where the pull keeps all of the exchange
+    off the compute stream.  Kept as the reference point for that comparison (``make_bucketed_gather(kind="push")``).
+
+    The exchange fused into the forward: there is no collective, no copy and no extra kernel on the data path.  The
+    receive buckets live in symmetric (peer-mapped) memory and the token-stage kernel of every forward stores its logits
+    into its slot on EVERY rank from its own epilogue (``forward_packed(x, out=slot(), also=peers())`` →
+    ``pmg_forward_bcast``: 208 B per image and peer as posted NVLink writes).  What is left per bucket is synchronisation,
+    two one-CTA signal-pad barriers on side streams: "every rank's forwards of this bucket are complete" (the results are
+    readable) and, one bucket later, "every rank has taken its results out" (the index may be written again — remote ranks
+    write into this rank's memory, so reuse needs everybody's consent).  Three bucket indices: the second barrier of an
+    index has a whole bucket of time before anybody waits for it.  ``pop()`` hands out copies (a remote rank may be writing
+    the next use of a buffer while this rank still holds its results).  Same interface as BucketedGather; CUDA + NVLink peer
+    access only (construction raises otherwise)."""
+
+    NBUF = 3
+
+    def __init__(self, b_local: int, n_logits: int, steps: int, device, group=None, keep: bool = False):
+        import torch.distributed._symmetric_memory as symm
+        if not dist.is_initialized() or dist.get_world_size(group) < 2:
+            raise RuntimeError("PushBucketedGather needs an initialised process group with at least 2 ranks")
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world - 1 > 15:
+            raise RuntimeError("pmg_forward_bcast takes at most 15 peer destinations")
+        self.steps, self.b, self.L, self.keep = int(steps), int(b_local), int(n_logits), keep
+        shape = (self.NBUF, self.world, self.steps, self.b, self.L)
+        self._sym = symm.empty(shape, dtype=torch.float32, device=device)
+        self._hdl = symm.rendezvous(self._sym, self.group)
+        self._peer = [self._hdl.get_buffer(p, shape, torch.float32) for p in range(self.world)]
+        self.recv = [self._sym[i] for i in range(self.NBUF)]        # (world, steps, b, L): slot [r] is written by rank r
+        self.xs, self.fs = torch.cuda.Stream(device), torch.cuda.Stream(device)
+        self.work = [None] * self.NBUF        # event: bucket in index i is complete on every rank
+        self.free = [None] * self.NBUF        # event: every rank has taken the results of index i out
+        self.filled = [0] * self.NBUF
+        self.cur, self.n = 0, 0
+        self._order, self._done = [], []
+        self._cache = {}
+
+    def _views(self):
+        """(local slot, peers' slots as a ready-made pointer array) of the current (index, step): built once — a forward is
+        enqueued in ~80 us of host time, seven tensor views and their checks per step would add half of that again."""
+        key = (self.cur, self.n)
+        v = self._cache.get(key)
+        if v is None:
+            import ctypes
+            i, n, r = self.cur, self.n, self.rank
+            local = self.recv[i][r][n]
+            remote = [self._peer[p][i][r][n] for p in range(self.world) if p != r]
+            ptrs = (ctypes.c_void_p * len(remote))(*[t.data_ptr() for t in remote])
+            v = self._cache[key] = (local, PeerSlots(ptrs, len(remote), tuple(local.shape), remote))
+        return v
+
+    def slot(self) -> torch.Tensor:
+        if self.n == 0:
+            i = self.cur
+            self._retire(i)                                   # (only on the first laps / after a flush: normally retired a bucket ago)
+            self._retire((i + 1) % self.NBUF)                 # the bucket two launches back: hand its results out NOW, so that
+            #                                                   everybody's consent for that index is in long before its next use
+            if self.free[i] is not None:
+                if not self.free[i].query():
+                    torch.cuda.current_stream().wait_event(self.free[i])
+                self.free[i] = None
+        return self._views()[0]
+
+    def peers(self):
+        return self._views()[1]
+
+    def _launch(self) -> None:
+        i = self.cur
+        self.filled[i] = self.n
+        done = torch.cuda.Event()
+        done.record()                                          # this rank's forwards of the bucket (and their remote stores) are enqueued
+        with torch.cuda.stream(self.xs):
+            self.xs.wait_event(done)
+            self._hdl.barrier(channel=i)                       # … and complete on every rank: the bucket is readable everywhere
+            got = torch.cuda.Event()
+            got.record()
+        self.work[i] = got
+        self._order.append(i)
+        self.cur = (i + 1) % self.NBUF
+        self.n = 0
+
+    def _retire(self, i: int) -> None:
+        while i in self._order:
+            j = self._order.pop(0)
+            got = self.work[j]
+            self.work[j] = None
+            if not got.query():
+                torch.cuda.current_stream().wait_event(got)
+            if self.keep:
+                self._done.extend(self.recv[j][:, s].clone() for s in range(self.filled[j]))
+            taken = torch.cuda.Event()
+            taken.record()                                     # this rank no longer needs index j …
+            with torch.cuda.stream(self.fs):
+                self.fs.wait_event(taken)
+                self._hdl.barrier(channel=self.NBUF + j)       # … and neither does anybody else: it may be written again
+                free = torch.cuda.Event()
+                free.record()
+            self.free[j] = free
+
+
+def make_bucketed_gather(b_local: int, n_logits: int, steps: int, device, group=None, keep: bool = False, prefer_peer: bool = True,
+                         kind: str = "pull"):
+    """(gather, description): the copy-engine pull (``kind="pull"``: PeerBucketedGather, the default — measured faster) or the
+    exchange fused into the forward (``kind="push"``: PushBucketedGather) when the ranks can map each other's memory, else —
+    or with ``prefer_peer=False`` — the NCCL / gloo all-gather.  Every rank must take the same branch: the outcome of the attempt is agreed on with one
+    all-reduce."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     dev = torch.device(device)
     if prefer_peer and world > 1 and dev.type == "cuda":
+        cls = PushBucketedGather if kind == "push" else PeerBucketedGather
         g, ok = None, 1
         try:
-            g = PeerBucketedGather(b_local, n_logits, steps, dev, group, keep)
+            g = cls(b_local, n_logits, steps, dev, group, keep)
         except Exception:                                  # no peer access / symmetric memory unavailable on this box
             ok = 0
         flag = torch.tensor([ok], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
         if int(flag.item()) == 1:
-            return g, "peer-memory pull (symmetric memory + copy engines, 2 one-CTA barriers per bucket)"
+            return g, ("logits stored to every rank's symmetric-memory bucket by the token-stage kernel itself (pmg_forward_bcast), "
+                       "2 one-CTA barriers per bucket on side streams" if kind == "push" else
+                       "peer-memory pull (symmetric memory + copy engines, 2 one-CTA barriers per bucket)")
         del g
     return BucketedGather(b_local, n_logits, steps, device, group, keep), "all_gather_into_tensor"
 
@@ -273,8 +397,8 @@ class ShardedPMG:
         bg, out = None, []
         for xb in batches:
             if bg is None:
-                bg = BucketedGather(xb.shape[0], self.model._n_logits, steps_per_gather, xb.device, self.group, keep=True)
-            self.model.forward_packed(xb, out=bg.slot())
+                bg, _ = make_bucketed_gather(xb.shape[0], self.model._n_logits, steps_per_gather, xb.device, self.group, keep=True)
+            self.model.forward_packed(xb, out=bg.slot(), also=bg.peers())
             bg.commit()
             out.extend(t.reshape(-1, t.shape[-1]).clone() for t in bg.pop())     # the views die when the bucket is reused
         if bg is not None:

@@ -128,6 +128,17 @@ int pmg_forward(const pmg_config* cfg, const void* packed, const void* x, int x_
                 int B, int H, int W, float* logits, float* gram, const pmg_taps* taps,
                 void* workspace, size_t workspace_bytes, unsigned flags, pmg_stream_t stream);
 
+/* pmg_forward whose packed logits are ALSO stored to n_peers (<= 15) further destinations — `peer_logits` is a HOST array of
+ * DEVICE pointers, each to a (B, sum(ncls)) fp32 buffer that may live in the peer-mapped memory of another GPU.  This is the
+ * data-parallel exchange of the path (north_star: "a final gather of per-task logits over NVLink"; reference counterpart: none,
+ * the reference is single-device) fused into the compute: the token-stage kernel stores every logit to all destinations from
+ * its own epilogue as posted NVLink writes — no collective kernel, no copy-engine transfer, no SM beyond the forward's own.
+ * Paths without that kernel (generic, PMG_FLAG_NO_FUSED_ENCODER) copy after the fact.  The caller fences (a barrier across
+ * the ranks after this stream's work) before anyone reads a destination; pmg_b200.runner.PushBucketedGather does. */
+int pmg_forward_bcast(const pmg_config* cfg, const void* packed, const void* x, int x_dtype,
+                      int B, int H, int W, float* logits, float* const* peer_logits, int n_peers,
+                      void* workspace, size_t workspace_bytes, unsigned flags, pmg_stream_t stream);
+
 /* Same forward, with a CUDA event recorded on `stream` after every kernel; synchronises the stream and
  * returns the device time of each stage (names are static strings owned by the library).  Used by
  * bench.py for the per-kernel roofline; not a product path. */
