@@ -181,6 +181,32 @@ def test_forward_into_gather_bucket_slots():
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("path", ["fused", "unfused_encoder", "generic"])
+def test_forward_bcast_stores_the_logits_everywhere(path):
+    """forward_packed(x, out=…, also=[…]) (pmg_forward_bcast): every extra destination receives exactly the logits — written by
+    the token-stage kernel's own epilogue on the default path, copied after the fact on the paths without that kernel.  (The
+    multi-GPU use, peer-mapped destinations, is checked on real GPUs by bench.py's gather_check.)"""
+    from pmg_b200.runner import PeerSlots
+    import ctypes
+    _, hp, tasks = load_contract()
+    m = _model(hp, tasks, 3, generic=(path == "generic"))
+    m.fused_encoder = path != "unfused_encoder"
+    x = torch.from_numpy(synth.images(41, 9)).cuda().to(torch.bfloat16)      # 9 images: a full 7-image tile and a ragged one
+    with torch.no_grad():
+        want = m.forward_packed(x).clone()
+        out = torch.full((9, 52), 7.0, device="cuda")
+        also = [torch.full((9, 52), -3.0, device="cuda") for _ in range(3)]
+        got = m.forward_packed(x, out=out, also=also)
+        slots = PeerSlots((ctypes.c_void_p * 2)(also[0].data_ptr(), also[2].data_ptr()), 2, (9, 52), also)
+        also[0].fill_(0); also[2].fill_(0)
+        m.forward_packed(x, out=out, also=slots)
+        with pytest.raises(ValueError):
+            m.forward_packed(x, also=[torch.empty((9, 51), device="cuda")])
+    assert got.data_ptr() == out.data_ptr() and torch.equal(out, want)
+    for t in also:
+        assert torch.equal(t, want)
+
+
 def test_gram_microbench_kernel_matches_matmul():
     from pmg_b200.gram import gram_batched
     gen = torch.Generator(device="cuda").manual_seed(0)
