@@ -99,3 +99,17 @@ def test_reference_loaders_run_unchanged(tmp_path, capsys):
             sys.modules.pop(k, None)
             if v is not None:
                 sys.modules[k] = v
+
+
+def test_host_pipeline_piece_schedule():
+    """HostPipeline cuts a host batch into H2D pieces: uniform `chunk`-sized pieces, the last one halving down to
+    `tail_chunk` (the forward of the LAST piece is what nothing can overlap).  Pure host logic."""
+    from pmg_b200.runner import HostPipeline
+    hp = HostPipeline.__new__(HostPipeline)
+    for chunk, tail, B, want in [(512, 32, 1024, [512, 256, 128, 64, 32, 32]), (128, 32, 1024, [128] * 7 + [64, 32, 32]),
+                                 (8, 8, 21, [8, 8, 5]), (512, 32, 5, [5]), (512, 32, 33, [1, 32]), (512, 32, 0, [])]:
+        hp.chunk, hp.tail_chunk = chunk, min(tail, chunk)
+        edges = hp._schedule(B)
+        assert [b - a for a, b in edges] == want, (chunk, tail, B, edges)
+        assert all(edges[i][1] == edges[i + 1][0] for i in range(len(edges) - 1))
+        assert (edges[0][0], edges[-1][1]) == (0, B) if B else edges == []
