@@ -277,7 +277,11 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sW = smem;
     float* sQKV = reinterpret_cast<float*>(smem + ENC_OFF_QKV);
-    uint8_t* sH = smem + ENC_OFF_QKV;               // FFN hidden tile [plane hi/lo][kb 2] × 8 KB (FFN phase only)
+    // FFN hidden tile [plane hi/lo][kb 2] × 8 KB, DOUBLE-BUFFERED (FFN phase only): buffer 0 in the head-buffer region, buffer 1 in
+    // the O tile — both idle during the FFN — so the epilogue of chunk c+1 writes while FFN2 still reads chunk c (with one buffer
+    // the two were serialised: ≈3 k cycles per chunk instead of the MMAs' 3 k for FFN1 + FFN2 together)
+    uint8_t* sH0 = smem + ENC_OFF_QKV;
+    uint8_t* sH1 = smem + ENC_OFF_O;
     float* sSC = reinterpret_cast<float*>(smem + ENC_OFF_QKV);   // heads result (after the last layer only)
     uint8_t* sA = smem + ENC_OFF_A;
     uint8_t* sO = smem + ENC_OFF_O;
@@ -297,10 +301,10 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
     uint64_t* x_full = bb + 8;
     uint64_t* dh_full = bb + 9;         // [2]
     uint64_t* dh_empty = bb + 11;       // [2]
-    uint64_t* h_ready = bb + 13;
-    uint64_t* h_free = bb + 14;
+    uint64_t* h_ready = bb + 13;        // [2]
+    uint64_t* h_free = bb + 16;         // [2]
     uint64_t* sc_full = bb + 15;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bb + 16);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bb + 18);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;   // provably warp-uniform
     const int wq = warp & 3;
@@ -314,7 +318,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
             mbar_init(&dq_full[i], 1); mbar_init(&dq_empty[i], 6);
             mbar_init(&dh_full[i], 1); mbar_init(&dh_empty[i], 8);
         }
-        mbar_init(h_ready, 8); mbar_init(h_free, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&h_ready[i], 8); mbar_init(&h_free[i], 1); }
         mbar_init(qkv_full, 6); mbar_init(qkv_empty, ENC_ATTN_WARPS); mbar_init(o_ready, 4 * ENC_ATTN_WARPS); mbar_init(x_full, 1); mbar_init(sc_full, 1);
         fence_barrier_init();
     }
@@ -374,7 +378,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
             constexpr uint32_t id192 = make_idesc_bf16(128, 192, 0, 0);
             constexpr uint32_t id128 = make_idesc_bf16(128, 128, 0, 0);
             constexpr uint32_t id64 = make_idesc_bf16(128, 64, 0, 0);
-            const uint32_t aW = smem_u32(sW), aA = smem_u32(sA), aO = smem_u32(sO), aH = smem_u32(sH);
+            const uint32_t aW = smem_u32(sW), aA = smem_u32(sA), aO = smem_u32(sO), aH0 = smem_u32(sH0), aH1 = smem_u32(sH1);
             const uint32_t tX = tmem_base, tS = tmem_base + 192;
             uint32_t wi = 0, na = 0, hq = 0, no = 0, hc = 0;
             // one weight k-block against one [64 × 64] hi/lo operand k-block: D (+)= (A_hi + A_lo) · Wᵀ
@@ -397,14 +401,15 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
             };
             auto free_w = [&]() { umma_commit(&w_empty[wi % ENC_NSTAGE]); ++wi; };
             auto ffn2 = [&](uint32_t pc) {               // x += H(chunk pc) · W2[:, 128·chunk ..]ᵀ
-                mbar_wait(h_ready, pc & 1);
+                const uint32_t hb = pc & 1, aH = hb ? aH1 : aH0;
+                mbar_wait(&h_ready[hb], (pc >> 1) & 1);
                 tc_fence_after();
                 for (int kb = 0; kb < 2; ++kb) {
                     const uint32_t w = wait_w();
                     mma_stage(aH + kb * ENC_KB, aH + 2 * ENC_KB + kb * ENC_KB, tX, id192, w, false);
                     free_w();
                 }
-                umma_commit(h_free);
+                umma_commit(&h_free[hb]);
             };
             ENC_T(0);
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -604,8 +609,8 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                         split_bf16x2(h0, h1, hi[i >> 1], lo[i >> 1]);
                         split_bf16x2(h2, h3, hi[(i >> 1) + 1], lo[(i >> 1) + 1]);
                     }
-                    mbar_wait(h_free, (hc & 1) ^ 1);                                  // FFN2 of the previous chunk has read the H tile
-                    uint8_t* hrow = sH + (g >> 1) * ENC_KB + m * 128;                  // hidden columns 32g.. → k-block g/2, chunks 4(g%2)..+3
+                    mbar_wait(&h_free[b], ((hc >> 1) & 1) ^ 1);                        // FFN2 of the chunk two back has read this H buffer
+                    uint8_t* hrow = (b ? sH1 : sH0) + (g >> 1) * ENC_KB + m * 128;     // hidden columns 32g.. → k-block g/2, chunks 4(g%2)..+3
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int sw = ((4 * (g & 1) + j) ^ (m & 7)) << 4;
@@ -614,7 +619,7 @@ __global__ void __launch_bounds__(ENC_THREADS, 1) encoder_kernel(const EncParams
                     }
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(h_ready);
+                    if (lane == 0) mbar_arrive(&h_ready[b]);
                     ENC_TC(109 + 40 * l + c);
                 }
                 // ---- x += FFN done: + bias ----
