@@ -165,7 +165,7 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
     # kernel-side state is rebuilt on demand; keep it out of pickles / deepcopies
     def __getstate__(self):
         st = dict(self.__dict__)
-        for k in ("_packed", "_packed_key", "_ws", "_lock", "_staged"):
+        for k in ("_packed", "_packed_key", "_ws", "_lock", "_staged", "_abi_cache"):
             st.pop(k, None)
         c = st.pop("_cfg")
         st["_cfg_tuple"] = (c.input_nc, c.ndf, c.patch_size, c.patch_div, c.gram_channels, c.d_model,
@@ -212,8 +212,18 @@ class MultiTaskPatchGANGramModelNonOverlapV2(nn.Module):
             out += [self.classifiers[t].weight, self.classifiers[t].bias]
         return out
 
+    def invalidate_packed(self) -> None:
+        """Call after REPLACING a Parameter object of the module (``m.token_proj.weight = nn.Parameter(…)``).  In-place updates,
+        ``load_state_dict`` and ``.to()`` are noticed without it (tensor version counters / storage pointers / the epoch)."""
+        self._bump_epoch()
+
     def _ensure_packed(self, device: torch.device, stream_ptr: int) -> torch.Tensor:
-        params = self._abi_params()
+        # the walk over the module tree is half of this function's host time (the other half: 78 version / pointer reads): the
+        # Parameter objects themselves only change identity on explicit replacement, so the list is kept per weights epoch
+        c = getattr(self, "_abi_cache", None)
+        if c is None or c[0] != self._weights_epoch:
+            c = self._abi_cache = (self._weights_epoch, self._abi_params())
+        params = c[1]
         key = (device, tuple((p.data_ptr(), p._version) for p in params))
         if self._packed is not None and key == self._packed_key:
             return self._packed
